@@ -1,0 +1,305 @@
+"""CPU oracle for the SAC target step -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import this module.  The product path
+(``da_sac_b200``) never does: it fails loudly when ``libsac_b200.so`` is missing.
+
+What it is: a functional PyTorch-CPU fp32 restatement of the reference's hot
+path (``Trainer._step_target`` -> ``SAC.forward`` -> backward), written from the
+reference's behaviour, each function citing the file:line it follows
+(paths relative to /root/reference).
+
+Parity pin: the reference ships no tests / golden vectors,
+so the pin is generated: ``tests/golden/make_golden.py`` imports the *real*
+reference modules from /root/reference in the build container, runs them on the
+seeded weights/inputs of ``da_sac_b200.synth`` and stores the outputs under
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks this oracle against
+those files.  The arithmetic itself lives in PyTorch (torch 2.11.0+cu128,
+torchvision 0.26.0 as installed -- the reference does not pin a version):
+``F.interpolate(bilinear, align_corners=True)``, ``F.softmax``,
+``F.affine_grid`` + ``F.grid_sample(bilinear, zeros, align_corners=False)``,
+``F.cross_entropy``; ``upsample_explicit`` / ``warp_explicit`` below restate
+those published formulas without calling ATen's kernels and are cross-checked
+in the tests.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.SyncBatchNorm default eps (deeplabv2.py:14)
+
+
+# --------------------------------------------------------------------------
+# Backbone: DeepLabV2_ResNet101 (models/deeplabv2.py:54-227)
+# --------------------------------------------------------------------------
+
+def _bn_eval(x, p, prefix):
+    # frozen BN: eval-mode statistics, trainable affine (basenet.py:86-100)
+    return F.batch_norm(x, p[prefix + ".running_mean"], p[prefix + ".running_var"],
+                        p[prefix + ".weight"], p[prefix + ".bias"], False, 0.0, BN_EPS)
+
+
+def _bottleneck(x, p, prefix, stride, dilation, has_ds):
+    # Bottleneck.forward (deeplabv2.py:77-99); stride sits on conv1 (:59)
+    out = F.conv2d(x, p[prefix + ".conv1.weight"], None, stride)
+    out = F.relu(_bn_eval(out, p, prefix + ".bn1"))
+    out = F.conv2d(out, p[prefix + ".conv2.weight"], None, 1, dilation, dilation)
+    out = F.relu(_bn_eval(out, p, prefix + ".bn2"))
+    out = F.conv2d(out, p[prefix + ".conv3.weight"], None, 1)
+    out = _bn_eval(out, p, prefix + ".bn3")
+    if has_ds:
+        res = F.conv2d(x, p[prefix + ".downsample.0.weight"], None, stride)
+        res = _bn_eval(res, p, prefix + ".downsample.1")
+    else:
+        res = x
+    return F.relu(out + res)
+
+
+def resnet101_logits(p, x, taps=None):
+    """ResNet.forward (deeplabv2.py:160-171). ``p``: state_dict-like mapping with
+    keys ``model.*``. Returns logits [n,19,h,w]. ``taps`` (optional dict) gets
+    intermediate activations for layer-wise kernel tests."""
+    x = F.conv2d(x, p["model.conv1.weight"], None, 2, 3)
+    x = F.relu(_bn_eval(x, p, "model.bn1"))
+    if taps is not None: taps["stem"] = x
+    x = F.max_pool2d(x, 3, 2, 1, ceil_mode=True)          # deeplabv2.py:126
+    if taps is not None: taps["pool"] = x
+    cfg = ((64, 3, 1, 1), (128, 4, 2, 1), (256, 23, 1, 2), (512, 3, 1, 4))
+    for li, (planes, blocks, stride, dil) in enumerate(cfg, start=1):
+        for b in range(blocks):
+            x = _bottleneck(x, p, "model.layer%d.%d" % (li, b), stride if b == 0 else 1, dil, b == 0)
+        if taps is not None: taps["layer%d" % li] = x
+    # Classifier_Module.forward (deeplabv2.py:112-116): sum of 4 dilated convs
+    out = None
+    for i, d in enumerate((6, 12, 18, 24)):
+        o = F.conv2d(x, p["model.layer5.conv2d_list.%d.weight" % i],
+                     p["model.layer5.conv2d_list.%d.bias" % i], 1, d, d)
+        out = o if out is None else out + o
+    return out
+
+
+def backbone_forward(p, im, y=None):
+    """DeepLabV2_ResNet101.forward (deeplabv2.py:213-227)."""
+    logits = resnet101_logits(p, im)
+    logits_up = F.interpolate(logits, im.shape[-2:], mode="bilinear", align_corners=True)
+    if y is None:
+        return logits, logits_up
+    ce = F.cross_entropy(logits_up, y, ignore_index=255, reduction="none")
+    return {"loss_ce": ce.mean().view(1)}, {"logits_up": logits_up, "logits": logits}
+
+
+# --------------------------------------------------------------------------
+# Explicit restatements of the ATen formulas
+# --------------------------------------------------------------------------
+
+def upsample_explicit(X, H, W):
+    """bilinear, align_corners=True (aten upsample_bilinear2d):
+    sy = i*(h-1)/(H-1); y0=floor(sy); y1=min(y0+1,h-1); ly=sy-y0."""
+    n, c, h, w = X.shape
+    def axis(o, i):
+        scale = (i - 1) / (o - 1) if o > 1 else 0.0
+        s = torch.arange(o, dtype=torch.float32) * torch.tensor(scale, dtype=torch.float32)
+        i0 = s.floor().long().clamp(max=i - 1)
+        i1 = (i0 + 1).clamp(max=i - 1)
+        l1 = s - i0.float()
+        return i0, i1, l1
+    y0, y1, ly = axis(H, h)
+    x0, x1, lx = axis(W, w)
+    ly = ly.view(1, 1, H, 1); lx = lx.view(1, 1, 1, W)
+    top = X[:, :, y0][:, :, :, x0] * (1 - lx) + X[:, :, y0][:, :, :, x1] * lx
+    bot = X[:, :, y1][:, :, :, x0] * (1 - lx) + X[:, :, y1][:, :, :, x1] * lx
+    return top * (1 - ly) + bot * ly
+
+
+def warp_explicit(X, M):
+    """grid_sample(X, affine_grid(M, align_corners=False), bilinear, zeros,
+    align_corners=False): x=(2j+1)/W-1, (u,v)=M.(x,y,1), ix=((u+1)W-1)/2,
+    4 taps, out-of-range taps contribute 0 (models/sac.py:289-290,300-301,309-310)."""
+    n, c, H, W = X.shape
+    xs = (2 * torch.arange(W, dtype=torch.float32) + 1) / W - 1
+    ys = (2 * torch.arange(H, dtype=torch.float32) + 1) / H - 1
+    gx = xs.view(1, 1, W).expand(n, H, W)
+    gy = ys.view(1, H, 1).expand(n, H, W)
+    M = M.float()
+    u = M[:, 0, 0].view(n, 1, 1) * gx + M[:, 0, 1].view(n, 1, 1) * gy + M[:, 0, 2].view(n, 1, 1)
+    v = M[:, 1, 0].view(n, 1, 1) * gx + M[:, 1, 1].view(n, 1, 1) * gy + M[:, 1, 2].view(n, 1, 1)
+    ix = ((u + 1) * W - 1) / 2
+    iy = ((v + 1) * H - 1) / 2
+    x0 = ix.floor(); y0 = iy.floor(); x1 = x0 + 1; y1 = y0 + 1
+    out = torch.zeros_like(X)
+    flat = X.reshape(n, c, H * W)
+    for (xx, yy, wgt) in ((x0, y0, (x1 - ix) * (y1 - iy)), (x1, y0, (ix - x0) * (y1 - iy)),
+                          (x0, y1, (x1 - ix) * (iy - y0)), (x1, y1, (ix - x0) * (iy - y0))):
+        ok = (xx >= 0) & (xx <= W - 1) & (yy >= 0) & (yy <= H - 1)
+        idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long().view(n, 1, H * W).expand(n, c, H * W)
+        val = flat.gather(2, idx).view(n, c, H, W)
+        out = out + val * (wgt * ok.float()).view(n, 1, H, W)
+    return out
+
+
+def _warp(X, M):
+    grid = F.affine_grid(M, size=list(X.shape), align_corners=False)
+    return F.grid_sample(X, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+
+
+# --------------------------------------------------------------------------
+# SAC tail (models/sac.py)
+# --------------------------------------------------------------------------
+
+def update_running_conf(running_conf, probs, cfg, tolerance=1e-8):
+    """SAC._update_running_conf (sac.py:104-117); returns the new buffer."""
+    B, C, H, W = probs.shape
+    probs_avg = probs.mean(0).view(C, -1).mean(-1)
+    rc = running_conf.clone()
+    new_index = (probs_avg > tolerance) & (rc == cfg.THRESHOLD_BETA)
+    rc[new_index] = probs_avg[new_index]
+    rc = rc * cfg.STAT_MOMENTUM
+    rc = rc + (1 - cfg.STAT_MOMENTUM) * probs_avg
+    return rc
+
+
+def avg_pool(probs, T, tolerance=0.1):
+    """SAC._avg_pool (sac.py:238-269), world_size 1 (no _gather)."""
+    _, C, H, W = probs.shape
+    probs_T = probs.view(-1, T, C, H, W)
+    s = probs_T.sum(1, keepdim=True)
+    z = s.sum(2, keepdim=True)
+    mask = (z > tolerance).type_as(probs)
+    avg = s / z.clamp(1e-3)
+    avg = avg.expand(-1, T, -1, -1, -1)
+    mask = mask.expand(-1, T, -1, -1, -1)
+    return avg.flatten(0, 1), mask.flatten(0, 1)
+
+
+def refine(slow_logits, hw, T, affine, affine_inv, ignore_mask, running_conf, cfg, training=True):
+    """SAC._refine (sac.py:271-313). Returns (teacher_refined, new running_conf, diags)."""
+    H, W = hw
+    up = F.interpolate(slow_logits, (H, W), mode="bilinear", align_corners=True)   # :275
+    probs = F.softmax(up, 1)                                                       # :276
+    if training:
+        running_conf = update_running_conf(running_conf, probs, cfg)               # :278-279
+    probs = probs * (1 - ignore_mask[:, None].type_as(probs))                      # :282
+    aligned = _warp(probs, affine)                                                 # :289-290
+    valid_aligned = _warp(torch.ones_like(aligned), affine_inv)                    # :299-301
+    refined_aligned, valid = avg_pool(aligned * valid_aligned, T)                  # :305
+    grid_inv = F.affine_grid(affine_inv, size=list(probs.shape), align_corners=False)
+    refined = F.grid_sample(refined_aligned, grid_inv, align_corners=False)        # :309
+    refined_valid = F.grid_sample(valid, grid_inv, align_corners=False)            # :310
+    refined = refined * refined_valid                                              # :311
+    return refined, running_conf, {"teacher_aligned": aligned, "teacher_init": up}
+
+
+def pseudo_labels_probs(probs, ignore_augm, running_conf, cfg, discount=True):
+    """SAC._pseudo_labels_probs + _threshold_discount (sac.py:151-187)."""
+    B, C, H, W = probs.shape
+    max_conf, max_idx = probs.max(1, keepdim=True)
+    peaks = torch.zeros_like(probs)
+    peaks.scatter_(1, max_idx, max_conf)
+    top_peaks, _ = peaks.view(B, C, -1).max(-1)
+    top_peaks = top_peaks * cfg.RUN_CONF_UPPER
+    if discount:
+        top_peaks = top_peaks * (1.0 - torch.exp(-running_conf / cfg.THRESHOLD_BETA)).view(1, C)
+    top_peaks = top_peaks.clamp(cfg.RUN_CONF_LOWER)
+    above = peaks.gt(top_peaks.view(B, C, 1, 1)).type_as(probs)
+    ignore = above.sum(1, keepdim=True) != 1
+    labels = max_idx.clone()
+    labels[ignore] = 255
+    labels = labels.squeeze(1)
+    labels[ignore_augm] = 255
+    return labels, max_conf, max_idx, top_peaks
+
+
+def focal_ce_conf(logits_up, pseudo_gt, teacher_conf, running_conf, p=3):
+    """SAC._focal_ce_conf (sac.py:134-149) INCLUDING the [B,H,W]*[B,1,H,W]
+    -> [B,B,H,W] broadcast of :148 (written here as the equivalent
+    mean_{j,p} ce[j,p] * mean_i conf[i,p])."""
+    w = (1 - running_conf.clamp(0.0)) ** p
+    ce = F.cross_entropy(logits_up, pseudo_gt, weight=w, ignore_index=255, reduction="none")
+    m = teacher_conf.mean(0)              # [1,H,W] batch-mean confidence
+    return (ce * m).mean()
+
+
+def focal_ce_conf_literal(logits_up, pseudo_gt, teacher_conf, running_conf, p=3):
+    """Literal form of sac.py:148 (materialises [B,B,H,W]); small inputs only."""
+    w = (1 - running_conf.clamp(0.0)) ** p
+    ce = F.cross_entropy(logits_up, pseudo_gt, weight=w, ignore_index=255, reduction="none")
+    return (ce * teacher_conf).mean()
+
+
+def teacher_diff(slow, fast):
+    """distance part of SAC._momentum_update (sac.py:83-102)."""
+    d = torch.zeros(())
+    for k, v in fast.items():
+        if k.split(".")[-1] in ("weight", "bias", "running_mean", "running_var"):
+            d = d + torch.norm(slow[k] - v.detach())
+    return d.view(1)
+
+
+def momentum_update(slow, fast, m):
+    """EMA part of SAC._momentum_update with update=True (sac.py:95-97)."""
+    for k, v in fast.items():
+        if k.split(".")[-1] in ("weight", "bias", "running_mean", "running_var"):
+            slow[k].mul_(m).add_(v.detach() * (1.0 - m))
+
+
+def sac_target_forward(student, teacher, running_conf, batch, T, cfg, training=True):
+    """SAC.forward with use_teacher=True, teacher already initialised
+    (sac.py:331-378). ``student``/``teacher``: state_dict-like mappings
+    (student leaves may require grad). Returns (losses, outs, new running_conf)."""
+    x, y, x2, affine, affine_inv = batch
+    y = y.clone()
+    ignore_mask = (y == -1)                                            # :337
+    y[ignore_mask] = 255                                               # :338
+    losses, outs = backbone_forward(student, x, y)                     # :340
+    with torch.no_grad():
+        slow_logits, _ = backbone_forward(teacher, x2)                 # :350
+        refined, rc, diags = refine(slow_logits, x2.shape[-2:], T, affine, affine_inv,
+                                    ignore_mask, running_conf, cfg, training)       # :353
+        labels, conf, idx, thr = pseudo_labels_probs(refined, ignore_mask, rc, cfg, cfg.CONF_DISCOUNT)  # :357
+    loss = focal_ce_conf(outs["logits_up"], labels, conf, rc, cfg.FOCAL_P)          # :360
+    losses["self_ce"] = loss.view(1)                                                # :361
+    with torch.no_grad():
+        losses["teacher_diff"] = teacher_diff(teacher, student)                     # :374
+    outs.update(teacher_logits=slow_logits, teacher_refined=refined, teacher_conf=conf,
+                teacher_labels=labels, teacher_idx=idx, thresholds=thr, running_conf=rc,
+                mask_gt=y, **diags)
+    return losses, outs, rc
+
+
+def parameter_groups(student, lr, wd):
+    """BaseNet.parameter_groups for DeepLabV2_ResNet101 (basenet.py:102-139,
+    deeplabv2.py:203-211): [old W (wd), old b, new W x10 (wd), new b x20]."""
+    groups = ({"params": [], "weight_decay": wd, "lr": lr}, {"params": [], "weight_decay": 0.0, "lr": 2 * lr},
+              {"params": [], "weight_decay": wd, "lr": 10 * lr}, {"params": [], "weight_decay": 0.0, "lr": 20 * lr})
+    for k, v in student.items():
+        if not (k.endswith(".weight") or k.endswith(".bias")):
+            continue
+        new = k.startswith("model.layer5.")
+        isw = k.endswith(".weight")
+        groups[(2 if new else 0) + (0 if isw else 1)]["params"].append(v)
+    return list(groups)
+
+
+def sac_target_step(student, teacher, running_conf, batch, T, cfg, optim=None):
+    """Trainer._step_target with train=True, TARGET_ONLY semantics
+    (train.py:211-233): forward, LR_TARGET*self_ce backward, SGD step."""
+    losses, outs, rc = sac_target_forward(student, teacher, running_conf, batch, T, cfg, True)
+    if optim is not None:
+        optim.zero_grad()
+    (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+    if optim is not None:
+        optim.step()
+    return losses, outs, rc
+
+
+def as_leaf_params(sd):
+    """state_dict -> mapping whose weight/bias entries are autograd leaves."""
+    out = OrderedDict()
+    for k, v in sd.items():
+        if k.endswith(".weight") or k.endswith(".bias"):
+            out[k] = v.clone().requires_grad_(True)
+        else:
+            out[k] = v.clone()
+    return out
