@@ -1,0 +1,23 @@
+// Error reporting, ABI version and launch accounting for libsac_b200.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+#include "sacb_common.cuh"
+#include "../../include/sacb.h"
+
+namespace sacb {
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace sacb
+
+extern "C" const char* sacb_last_error(void) { return sacb::g_err; }
+extern "C" int sacb_abi_version(void) { return SACB_ABI_VERSION; }
+extern "C" int64_t sacb_launch_count(void) { return (int64_t)sacb::g_launches.load(); }

@@ -1,0 +1,653 @@
+// tcgen05 implicit-GEMM convolution kernels (fprop / dgrad / wgrad) for sm_100a.
+//
+// One persistent, warp-specialised kernel family:
+//   warp 0      : TMA producer  (im2col-mode tensor maps for the activation operand, tiled maps for the other)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 2..5  : epilogue (tcgen05.ld from a double-buffered TMEM accumulator, fused math, global stores)
+// Operands are bf16 "split planes" (x = hi + lo); every K step issues lo*hi + hi*lo + hi*hi into the same
+// fp32 TMEM accumulator, which restores fp32-level accuracy at 3 MMAs per step (DESIGN.md "precision").
+//
+// Replaces: cuDNN conv fprop / bwd-data / bwd-filter behind nn.Conv2d in
+// /root/reference/models/deeplabv2.py:59-70,107,122,147 and the eval-mode BN / ReLU / residual that follow
+// (deeplabv2.py:77-99).
+#include <atomic>
+#include <mutex>
+#include <cstdio>
+#include "sacb_common.cuh"
+#include "../../include/sacb.h"
+
+namespace sacb {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int BM = 128;          // UMMA M (TMEM lanes)
+constexpr int BK = 64;           // K elements per stage = one 128-byte swizzle row
+constexpr int GEMM_THREADS = 192;
+constexpr uint32_t A_BYTES = BM * BK * 2;   // one bf16 plane of the 128x64 (or 2 x 64x64) operand tile
+
+template <int BN> struct TileCfg {
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+struct GemmArgs {
+  int M_total, N_total, n_valid;
+  int num_m_tiles, num_n_tiles;
+  int taps, S, dil;
+  int kc_blocks;
+  int P, Q, stride, lower;
+  const float* scale; const float* shift; const float* add_f32;
+  const uint16_t* add_hi; const uint16_t* add_lo; const uint16_t* mask_hi;
+  int relu;
+  uint16_t* out_hi; uint16_t* out_lo; float* out_f32; float* out_nchw;
+};
+
+struct WgradArgs {
+  int k_valid, Kg, C;
+  int taps, S, dil, P, Q, stride, lower;
+  int num_pix_blocks, blocks_per_split;
+  int m_tiles, n_tiles, splits;
+  int swap;     // 0: rows = output channels (G), cols = input channels (X); 1: rows = X channels, cols = G channels
+  float* dw;
+};
+
+struct PipeState {
+  int stage; uint32_t phase;
+  template <int STAGES> SACB_DEVINL void advance() { if (++stage == STAGES) { stage = 0; phase ^= 1; } }
+};
+
+SACB_DEVINL uint8_t* align1024(uint8_t* p) {
+  uintptr_t v = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<uint8_t*>((v + 1023) & ~uintptr_t(1023));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused epilogue for one thread = one output row (pixel), 32 consecutive output channels
+// ------------------------------------------------------------------------------------------------
+SACB_DEVINL void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_bits_to_float(u.x & 0xFFFF); f[1] = bf16_bits_to_float(u.x >> 16);
+  f[2] = bf16_bits_to_float(u.y & 0xFFFF); f[3] = bf16_bits_to_float(u.y >> 16);
+  f[4] = bf16_bits_to_float(u.z & 0xFFFF); f[5] = bf16_bits_to_float(u.z >> 16);
+  f[6] = bf16_bits_to_float(u.w & 0xFFFF); f[7] = bf16_bits_to_float(u.w >> 16);
+}
+
+SACB_DEVINL void epilogue_row(const GemmArgs& a, uint32_t (&r)[32], int m, int c0) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  const size_t row = (size_t)m * a.N_total + c0;
+  if (a.scale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c0) + i);
+      float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + c0) + i);
+      v[4 * i + 0] = fmaf(v[4 * i + 0], sc.x, sh.x); v[4 * i + 1] = fmaf(v[4 * i + 1], sc.y, sh.y);
+      v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
+    }
+  }
+  if (a.add_f32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(a.add_f32 + row) + i);
+      v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    }
+  }
+  if (a.add_hi) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 h = __ldg(reinterpret_cast<const uint4*>(a.add_hi + row) + i);
+      uint4 l = __ldg(reinterpret_cast<const uint4*>(a.add_lo + row) + i);
+      float fh[8], fl[8];
+      unpack8(h, fh); unpack8(l, fl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] += fh[j] + fl[j];
+    }
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (a.mask_hi) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 h = __ldg(reinterpret_cast<const uint4*>(a.mask_hi + row) + i);
+      float fh[8];
+      unpack8(h, fh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] = fh[j] > 0.f ? v[8 * i + j] : 0.f;
+    }
+  }
+  if (a.out_hi) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
+        uint16_t h0 = float_to_bf16_bits(x0), h1 = float_to_bf16_bits(x1);
+        uint16_t l0 = float_to_bf16_bits(x0 - bf16_bits_to_float(h0));
+        uint16_t l1 = float_to_bf16_bits(x1 - bf16_bits_to_float(h1));
+        ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      }
+      reinterpret_cast<uint4*>(a.out_hi + row)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      reinterpret_cast<uint4*>(a.out_lo + row)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+  if (a.out_f32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      reinterpret_cast<float4*>(a.out_f32 + row)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  if (a.out_nchw) {
+    const int pq = a.P * a.Q;
+    const int n_img = m / pq;
+    const int rem = m - n_img * pq;
+    float* base = a.out_nchw + (size_t)n_img * a.n_valid * pq + rem;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < a.n_valid) base[(size_t)(c0 + i) * pq] = v[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad:  D[pixels, K] = sum_{taps, c} im2col(X)[pixels, c] * Wt[tap][K][c]     (both operands K-major)
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                 const GemmArgs a) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = a.num_m_tiles * a.num_n_tiles;
+  const int k_blocks = a.taps * a.kc_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const int pq = a.P * a.Q;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_idx = tile / a.num_n_tiles, n_idx = tile - m_idx * a.num_n_tiles;
+        const int m0 = m_idx * BM;
+        const int n_img = m0 / pq;
+        const int rem = m0 - n_img * pq;
+        const int p = rem / a.Q, q = rem - p * a.Q;
+        const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int r = tap / a.S, s = tap - r * a.S;
+          const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
+          for (int cb = 0; cb < a.kc_blocks; ++cb) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[ps.stage], Cfg::STAGE_BYTES);
+            tma_load_im2col(&tmAh, &full_bar[ps.stage], st, cb * BK, w0, h0, n_img, ow, oh);
+            tma_load_im2col(&tmAl, &full_bar[ps.stage], st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            tma_load_3d(&tmBh, &full_bar[ps.stage], st + 2 * A_BYTES, cb * BK, n_idx * BN, tap);
+            tma_load_3d(&tmBl, &full_bar[ps.stage], st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, n_idx * BN, tap);
+            ps.advance<STAGES>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 32, 16, 1024);
+            const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 32, 16, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 32, 16, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+            tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+            tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            accumulate = 1;
+          }
+          tc_commit(&empty_bar[ps.stage]);
+          ps.advance<STAGES>();
+        }
+        tc_commit(&tfull_bar[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_idx = tile / a.num_n_tiles, n_idx = tile - m_idx * a.num_n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int m = m_idx * BM + quad * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+        tmem_ld_wait();
+        if (m < a.M_total) epilogue_row(a, r, m, n_idx * BN + ch * 32);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad:  D[rows, cols] (+)= sum_{pixels} A[pixels, rows] * B[pixels, cols]   (both operands MN-major)
+//   swap=0: rows = output channels (G, tiled map), cols = input channels (X, im2col map)
+//   swap=1: rows = input channels (X, im2col map), cols = output channels (G, tiled map)
+// work item = (row tile, col tile, filter tap, K split); results accumulated with fp32 atomics.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
+                  const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                  const WgradArgs a) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t BOX_BYTES = 64 * 64 * 2;   // [64 pixels][64 channels] bf16
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmGh); prefetch_tmap(&tmGl); prefetch_tmap(&tmXh); prefetch_tmap(&tmXl);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_work = a.m_tiles * a.n_tiles * a.taps * a.splits;
+
+  // work -> (split, tap, n_idx, m_idx); split fastest so that one (tile, tap)'s partial sums are in flight together
+  auto decode = [&](int wk, int& m_idx, int& n_idx, int& tap, int& kb0, int& kb1) {
+    const int split = wk % a.splits; wk /= a.splits;
+    tap = wk % a.taps; wk /= a.taps;
+    n_idx = wk % a.n_tiles; m_idx = wk / a.n_tiles;
+    kb0 = split * a.blocks_per_split;
+    kb1 = min(kb0 + a.blocks_per_split, a.num_pix_blocks);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const int pq = a.P * a.Q;
+      for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+        int m_idx, n_idx, tap, kb0, kb1;
+        decode(wk, m_idx, n_idx, tap, kb0, kb1);
+        const int r = tap / a.S, s = tap - r * a.S;
+        const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int m0 = kb * 64;
+          const int n_img = m0 / pq;
+          const int rem = m0 - n_img * pq;
+          const int p = rem / a.Q, q = rem - p * a.Q;
+          const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
+          mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+          uint64_t* fb = &full_bar[ps.stage];
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          uint8_t* sa_hi = st; uint8_t* sa_lo = st + A_BYTES;
+          uint8_t* sb_hi = st + 2 * A_BYTES; uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
+          if (!a.swap) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d(&tmGh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+              tma_load_2d(&tmGl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              tma_load_im2col(&tmXh, fb, sb_hi + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
+              tma_load_im2col(&tmXl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              tma_load_im2col(&tmXh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+              tma_load_im2col(&tmXl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+            }
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              tma_load_2d(&tmGh, fb, sb_hi + j * BOX_BYTES, n_idx * BN + j * 64, m0);
+              tma_load_2d(&tmGl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, m0);
+            }
+          }
+          ps.advance<STAGES>();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
+      for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+        int m_idx, n_idx, tap, kb0, kb1;
+        decode(wk, m_idx, n_idx, tap, kb0, kb1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k) {
+            // MN-major SW128: 16 K rows (pixels) = 2048 B per step; 64-channel chunks BOX_BYTES apart (LBO);
+            // 8-row groups 1024 B apart (SBO).
+            const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 2048, BOX_BYTES, 1024);
+            tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+            tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+            tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            accumulate = 1;
+          }
+          tc_commit(&empty_bar[ps.stage]);
+          ps.advance<STAGES>();
+        }
+        tc_commit(&tfull_bar[acc]);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+      int m_idx, n_idx, tap, kb0, kb1;
+      decode(wk, m_idx, n_idx, tap, kb0, kb1);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_idx * BM + quad * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+        tmem_ld_wait();
+        const int col0 = n_idx * BN + ch * 32;
+        if (!a.swap) {
+          if (row < a.k_valid) {
+            float* dst = a.dw + ((size_t)row * a.taps + tap) * a.C + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(r[i]));
+          }
+        } else {
+          if (row < a.C) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < a.k_valid)
+                atomicAdd(a.dw + ((size_t)(col0 + i) * a.taps + tap) * a.C + row, __uint_as_float(r[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_tiled = nullptr;
+static EncodeIm2colFn g_im2col = nullptr;
+static int g_driver_version = 0;
+static int g_num_sms = 0;
+static std::once_flag g_once;
+static int g_init_status = 0;
+
+static void init_once() {
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+    g_init_status = -1; return;
+  }
+  g_tiled = reinterpret_cast<EncodeTiledFn>(f);
+  f = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) != cudaSuccess || !f) {
+    g_init_status = -1; return;
+  }
+  g_im2col = reinterpret_cast<EncodeIm2colFn>(f);
+  cudaDriverGetVersion(&g_driver_version);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+static int ensure_init() {
+  std::call_once(g_once, init_once);
+  if (g_init_status != 0) { set_error("libsac_b200: cannot resolve cuTensorMapEncode* driver entry points"); return -3; }
+  return 0;
+}
+
+// bf16 [N,H,W,C] activation plane, im2col mode, box = 64 channels x `pixels` pixels, SWIZZLE_128B
+static int make_im2col_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int pad, int R, int dil,
+                           int stride, int pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (R - 1) * dil, pad - (R - 1) * dil};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                        64, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed: %d (N=%d H=%d W=%d C=%d pad=%d R=%d dil=%d stride=%d)",
+                                     (int)r, N, H, W, C, pad, R, dil, stride); return -4; }
+  // Small-tensor workaround used by CUTLASS for drivers <= 13.1 (cute/atom/copy_traits_sm90_im2col.hpp).
+  if (g_driver_version <= 13010 && (size_t)N * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+// bf16 row-major [rows][cols] (cols contiguous) optionally with a third dim; box = 64 cols x box_rows rows
+static int make_tiled_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                          const cuuint32_t* box) {
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return -4; }
+  return 0;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                       const GemmArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TileCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  conv_gemm_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, st>>>(ah, al, bh, bl, a);
+  g_launches++;
+  SACB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
+                        const WgradArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)TileCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  const int work = a.m_tiles * a.n_tiles * a.taps * a.splits;
+  const int grid = work < g_num_sms ? work : g_num_sms;
+  conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, st>>>(gh, gl, xh, xl, a);
+  g_launches++;
+  SACB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sacb
+
+using namespace sacb;
+
+extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
+  SACB_REQUIRE(d && d->size == sizeof(SacbConvGemm), "sacb_conv_gemm: bad descriptor size");
+  if (int e = ensure_init()) return e;
+  SACB_REQUIRE(d->C % 64 == 0, "sacb_conv_gemm: C=%d must be a multiple of 64", d->C);
+  SACB_REQUIRE(d->K % 32 == 0, "sacb_conv_gemm: K=%d must be a multiple of 32", d->K);
+  SACB_REQUIRE(d->R == d->S, "sacb_conv_gemm: square filters only");
+  const int P = (d->H + 2 * d->pad - (d->R - 1) * d->dil - 1) / d->stride + 1;
+  const int Q = (d->W + 2 * d->pad - (d->S - 1) * d->dil - 1) / d->stride + 1;
+  SACB_REQUIRE(P == d->P && Q == d->Q, "sacb_conv_gemm: P,Q (%d,%d) inconsistent with geometry (%d,%d)", d->P, d->Q, P, Q);
+  SACB_REQUIRE(d->pad <= 128 && (d->R - 1) * d->dil <= 255, "sacb_conv_gemm: pad/dilation outside im2col TMA limits");
+  const int BN = (d->K % 128 == 0) ? 128 : (d->K % 64 == 0 ? 64 : 32);
+  CUtensorMap ah, al, bh, bl;
+  if (int e = make_im2col_map(&ah, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM)) return e;
+  if (int e = make_im2col_map(&al, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM)) return e;
+  cuuint64_t wd[3] = {(cuuint64_t)d->C, (cuuint64_t)d->K, (cuuint64_t)(d->R * d->S)};
+  cuuint64_t ws[2] = {(cuuint64_t)d->C * 2, (cuuint64_t)d->C * d->K * 2};
+  cuuint32_t wb[3] = {64, (cuuint32_t)BN, 1};
+  if (int e = make_tiled_map(&bh, d->wt_hi, 3, wd, ws, wb)) return e;
+  if (int e = make_tiled_map(&bl, d->wt_lo, 3, wd, ws, wb)) return e;
+  GemmArgs a;
+  a.M_total = d->N * P * Q; a.N_total = d->K; a.n_valid = d->k_valid;
+  a.num_m_tiles = (a.M_total + BM - 1) / BM; a.num_n_tiles = d->K / BN;
+  a.taps = d->R * d->S; a.S = d->S; a.dil = d->dil; a.kc_blocks = d->C / 64;
+  a.P = P; a.Q = Q; a.stride = d->stride; a.lower = -d->pad;
+  a.scale = d->scale; a.shift = d->shift; a.add_f32 = d->add_f32;
+  a.add_hi = (const uint16_t*)d->add_hi; a.add_lo = (const uint16_t*)d->add_lo; a.mask_hi = (const uint16_t*)d->mask_hi;
+  a.relu = d->relu;
+  a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
+  SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
+  SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
+  SACB_REQUIRE(d->k_valid == d->K || (!d->out_hi && !d->out_f32 && !d->add_f32 && !d->add_hi && !d->mask_hi),
+               "sacb_conv_gemm: k_valid < K only supported with the NCHW output");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 128: return launch_gemm<128>(ah, al, bh, bl, a, st);
+    case 64: return launch_gemm<64>(ah, al, bh, bl, a, st);
+    default: return launch_gemm<32>(ah, al, bh, bl, a, st);
+  }
+}
+
+extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
+  SACB_REQUIRE(d && d->size == sizeof(SacbConvWgrad), "sacb_conv_wgrad: bad descriptor size");
+  if (int e = ensure_init()) return e;
+  SACB_REQUIRE(d->C % 64 == 0 && d->K % 64 == 0, "sacb_conv_wgrad: C=%d, K=%d must be multiples of 64", d->C, d->K);
+  SACB_REQUIRE(d->R == d->S, "sacb_conv_wgrad: square filters only");
+  const int P = (d->H + 2 * d->pad - (d->R - 1) * d->dil - 1) / d->stride + 1;
+  const int Q = (d->W + 2 * d->pad - (d->S - 1) * d->dil - 1) / d->stride + 1;
+  SACB_REQUIRE(P == d->P && Q == d->Q, "sacb_conv_wgrad: P,Q inconsistent with geometry");
+  CUtensorMap gh, gl, xh, xl;
+  if (int e = make_im2col_map(&xh, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
+  if (int e = make_im2col_map(&xl, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
+  const long long M = (long long)d->N * P * Q;
+  cuuint64_t gd[2] = {(cuuint64_t)d->K, (cuuint64_t)M};
+  cuuint64_t gs[1] = {(cuuint64_t)d->K * 2};
+  cuuint32_t gb[2] = {64, 64};
+  if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
+  if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
+  WgradArgs a;
+  a.k_valid = d->k_valid; a.Kg = d->K; a.C = d->C;
+  a.taps = d->R * d->S; a.S = d->S; a.dil = d->dil; a.P = P; a.Q = Q; a.stride = d->stride; a.lower = -d->pad;
+  a.num_pix_blocks = (int)((M + 63) / 64);
+  a.dw = d->dw;
+  // few valid output channels (ASPP head, 19 classes): put the wide input-channel dim on the 128 TMEM lanes
+  a.swap = (d->k_valid <= 64 && d->C >= 128) ? 1 : 0;
+  int BN;
+  if (!a.swap) { BN = (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
+  else { BN = 64; a.m_tiles = (d->C + BM - 1) / BM; a.n_tiles = d->K / 64; }
+  int splits = d->splits;
+  if (splits <= 0) {
+    const int base = a.m_tiles * a.n_tiles * a.taps;
+    splits = (4 * g_num_sms + base - 1) / base;
+    const int max_splits = a.num_pix_blocks / 8 > 0 ? a.num_pix_blocks / 8 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > a.num_pix_blocks) splits = a.num_pix_blocks;
+  a.blocks_per_split = (a.num_pix_blocks + splits - 1) / splits;
+  a.splits = (a.num_pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 128) return launch_wgrad<128>(gh, gl, xh, xl, a, st);
+  return launch_wgrad<64>(gh, gl, xh, xl, a, st);
+}

@@ -1,0 +1,125 @@
+"""ctypes binding of libsac_b200.so (the C ABI declared in include/sacb.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, an exception is raised (``SacbError``).  PyTorch is used only for device
+memory and streams; the structs below carry raw device pointers.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsac_b200.so")
+
+
+class SacbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise SacbError("libsac_b200.so not built (run `python -c 'import __graft_entry__ as g; g.build()'`): " + LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.sacb_last_error.restype = C.c_char_p
+        _lib.sacb_launch_count.restype = C.c_int64
+        if hasattr(_lib, "sacb_tail_part_sums_elems"):
+            _lib.sacb_tail_part_sums_elems.restype = C.c_size_t
+        if _lib.sacb_abi_version() != 1:
+            raise SacbError("libsac_b200.so ABI version mismatch")
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise SacbError("%s failed (%d): %s" % (what, rc, lib().sacb_last_error().decode()))
+
+
+def ptr(t):
+    """device pointer of a tensor (or None)"""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "libsac_b200 needs contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(lib().sacb_launch_count())
+
+
+_vp = C.c_void_p
+
+
+class ConvGemm(C.Structure):
+    _fields_ = [("size", C.c_uint32),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("K", C.c_int32), ("k_valid", C.c_int32),
+                ("R", C.c_int32), ("S", C.c_int32), ("stride", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
+                ("P", C.c_int32), ("Q", C.c_int32),
+                ("x_hi", _vp), ("x_lo", _vp), ("wt_hi", _vp), ("wt_lo", _vp),
+                ("scale", _vp), ("shift", _vp), ("add_f32", _vp), ("add_hi", _vp), ("add_lo", _vp), ("mask_hi", _vp),
+                ("relu", C.c_int32),
+                ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp)]
+
+
+class ConvWgrad(C.Structure):
+    _fields_ = [("size", C.c_uint32),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("K", C.c_int32), ("k_valid", C.c_int32),
+                ("R", C.c_int32), ("S", C.c_int32), ("stride", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
+                ("P", C.c_int32), ("Q", C.c_int32),
+                ("x_hi", _vp), ("x_lo", _vp), ("g_hi", _vp), ("g_lo", _vp), ("dw", _vp),
+                ("splits", C.c_int32)]
+
+
+class Tail(C.Structure):
+    _fields_ = [("size", C.c_uint32),
+                ("BT", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32),
+                ("teacher_logits", _vp), ("y", _vp), ("affine", _vp), ("affine_inv", _vp), ("running_conf", _vp),
+                ("training", C.c_int32), ("discount", C.c_int32),
+                ("beta", C.c_float), ("stat_momentum", C.c_float), ("conf_upper", C.c_float), ("conf_lower", C.c_float),
+                ("pooled", _vp), ("part_sums", _vp), ("peaks", _vp),
+                ("conf", _vp), ("idx", _vp), ("labels", _vp), ("conf_mean", _vp), ("thresholds", _vp), ("refined", _vp)]
+
+
+class Loss(C.Structure):
+    _fields_ = [("size", C.c_uint32),
+                ("BT", C.c_int32), ("C", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("logits", _vp), ("y", _vp), ("labels", _vp), ("conf_mean", _vp), ("running_conf", _vp),
+                ("focal_p", C.c_float),
+                ("losses", _vp), ("scratch", _vp),
+                ("grad_scale", C.c_float),
+                ("dlogits", _vp)]
+
+
+def conv_out_hw(H, W, R, stride, dil, pad):
+    return ((H + 2 * pad - (R - 1) * dil - 1) // stride + 1, (W + 2 * pad - (R - 1) * dil - 1) // stride + 1)
+
+
+def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift=None, add_f32=None, add_hi=None,
+              add_lo=None, mask_hi=None, relu=False, out_hi=None, out_lo=None, out_f32=None, out_nchw=None):
+    """geom = (N, H, W, C, K, R, stride, dil, pad)"""
+    N, H, W, Cc, K, R, s, d, p = geom
+    P, Q = conv_out_hw(H, W, R, s, d, p)
+    desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
+                    ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
+                    ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw))
+    check(lib().sacb_conv_gemm(C.byref(desc), stream()), "sacb_conv_gemm")
+
+
+def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
+    N, H, W, Cc, K, R, s, d, p = geom
+    P, Q = conv_out_hw(H, W, R, s, d, p)
+    desc = ConvWgrad(C.sizeof(ConvWgrad), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
+                     ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), ptr(dw), splits)
+    check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad")

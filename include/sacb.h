@@ -1,0 +1,189 @@
+/* libsac_b200 -- C ABI of the B200-native SAC target step (sm_100a).
+ *
+ * The reference (visinf/da-sac) has no FFI layer: its hot path is the Python
+ * module contract models.get_model(...) -> SAC.forward(...) consumed by
+ * train.py:88-104,211-250.  These entry points are what a binding for that
+ * path binds to (INTEGRATION.md shows the ctypes stub); each one cites the
+ * reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions: every function returns 0 on success, <0 on error
+ * (sacb_last_error() gives the message); nothing throws across the ABI; the
+ * caller owns every buffer; all work is asynchronous on `stream`
+ * (a cudaStream_t passed as void*); device pointers must be 16-byte aligned
+ * (activation planes 128-byte).  No torch types appear here.
+ *
+ * Activation layout ("split planes"): an fp32 activation tensor x[N,H,W,C]
+ * (NHWC) is held as two bf16 planes hi = bf16(x), lo = bf16(x - hi), so that
+ * x = hi + lo to ~2^-17 relative; convolutions evaluate
+ * hi*hi + lo*hi + hi*lo on the tcgen05 tensor cores with fp32 accumulation in
+ * TMEM ("bf16x3", fp32-equivalent accuracy; SURVEY.md section 7 precision).
+ */
+#ifndef SACB_H_
+#define SACB_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SACB_ABI_VERSION 1
+
+const char* sacb_last_error(void);
+int sacb_abi_version(void);
+/* number of kernels launched by this library since process start (bench.py "gpu_launches") */
+int64_t sacb_launch_count(void);
+
+/* ---------------------------------------------------------------- convolution as implicit GEMM
+ * Replaces nn.Conv2d forward (models/deeplabv2.py:59-70,107,122,147) fused with the
+ * eval-mode SyncBatchNorm affine, residual add and ReLU that follow it
+ * (deeplabv2.py:77-99), and -- with flipped/transposed weights -- the autograd
+ * data-gradient of the same conv (train.py:232).
+ *
+ *   acc[m, k]  = sum_{r,s,c} X[n, p*stride - pad + r*dil, q*stride - pad + s*dil, c] * Wt[r*S+s][k][c]
+ *   v          = acc * scale[k] + shift[k]            (if scale != NULL)
+ *   v         += add_f32[m*K + k]                      (if add_f32)
+ *   v         += add_hi[m*K+k] + add_lo[m*K+k]         (if add_hi)
+ *   v          = max(v, 0)                             (if relu)
+ *   v          = mask_hi[m*K+k] > 0 ? v : 0            (if mask_hi; ReLU backward)
+ *   out_hi/out_lo[m*K+k] = split(v); out_f32[m*K+k] = v; out_nchw[((n*k_valid+k)*P+p)*Q+q] = v
+ * with m = (n*P + p)*Q + q.                                                          */
+typedef struct SacbConvGemm {
+  uint32_t size;              /* sizeof(SacbConvGemm), ABI versioning */
+  int32_t N, H, W, C;         /* input NHWC; C % 64 == 0 */
+  int32_t K;                  /* output channels as stored in wt (multiple of the N tile: 32, 64 or 128) */
+  int32_t k_valid;            /* channels actually written (<= K) */
+  int32_t R, S, stride, dil, pad;
+  int32_t P, Q;               /* output spatial size */
+  const void* x_hi; const void* x_lo;     /* bf16 [N,H,W,C] */
+  const void* wt_hi; const void* wt_lo;   /* bf16 [R*S][K][C] */
+  const float* scale; const float* shift; /* [K] or NULL */
+  const float* add_f32;                   /* [M,K] or NULL */
+  const void* add_hi; const void* add_lo; /* bf16 [M,K] or NULL */
+  const void* mask_hi;                    /* bf16 [M,K] or NULL */
+  int32_t relu;
+  void* out_hi; void* out_lo;             /* bf16 [M,K] or NULL */
+  float* out_f32;                         /* [M,K] or NULL */
+  float* out_nchw;                        /* [N,k_valid,P,Q] or NULL */
+} SacbConvGemm;
+int sacb_conv_gemm(const SacbConvGemm* d, void* stream);
+
+/* Filter gradient (autograd of nn.Conv2d w.r.t. weight, train.py:232):
+ *   dw[k][r*S+s][c] += sum_{n,p,q} G[n,p,q,k] * X[n, p*stride-pad+r*dil, q*stride-pad+s*dil, c]
+ * accumulated with fp32 atomics into dw (caller zero-fills). G and X are split planes. */
+typedef struct SacbConvWgrad {
+  uint32_t size;
+  int32_t N, H, W, C;         /* input X NHWC, C % 64 == 0 */
+  int32_t K;                  /* channels of G as stored (multiple of 64) */
+  int32_t k_valid;            /* rows of dw written */
+  int32_t R, S, stride, dil, pad;
+  int32_t P, Q;
+  const void* x_hi; const void* x_lo;   /* bf16 [N,H,W,C] */
+  const void* g_hi; const void* g_lo;   /* bf16 [N,P,Q,K] */
+  float* dw;                            /* fp32 [k_valid][R*S][C] */
+  int32_t splits;                       /* split-K factor over pixels; 0 = auto */
+} SacbConvWgrad;
+int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream);
+
+/* ---------------------------------------------------------------- elementwise / layout kernels
+ * (declared in sacb_elem.cu; see DESIGN.md for the reference lines each replaces) */
+
+/* fp32 NCHW image -> stem conv 7x7 s2 p3 (3->64) + BN affine + ReLU -> split planes NHWC
+ * (deeplabv2.py:160-163). w: fp32 [64][3][7][7]. */
+int sacb_stem_fwd(const float* x_nchw, const float* w, const float* scale, const float* shift,
+                  void* out_hi, void* out_lo, int N, int H, int W, int P, int Q, void* stream);
+/* dW of the stem conv: g split planes [N,P,Q,64] (already masked by ReLU), x fp32 NCHW -> dw[64][3][7][7] (+=) */
+int sacb_stem_wgrad(const float* x_nchw, const void* g_hi, const void* g_lo, float* dw,
+                    int N, int H, int W, int P, int Q, void* stream);
+/* MaxPool2d(3, 2, 1, ceil_mode=True) on split planes (deeplabv2.py:126); idx = argmax tap (uint8) for backward */
+int sacb_maxpool_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx,
+                     int N, int H, int W, int C, int P, int Q, void* stream);
+/* g_in[n,h,w,c] = (sum of g_out over windows whose argmax is (h,w)) masked by in_hi > 0 -> split planes */
+int sacb_maxpool_bwd(const float* g_out, const uint8_t* idx, const void* in_hi, void* gin_hi, void* gin_lo,
+                     int N, int H, int W, int C, int P, int Q, void* stream);
+/* out = split( mask_hi>0 ? (a + b) : 0 ), a/b fp32 [n] (b may be NULL); mask_hi may be NULL */
+int sacb_add_mask_split(const float* a, const float* b, const void* mask_hi, void* out_hi, void* out_lo,
+                        int64_t n, void* stream);
+/* scatter a compact stride-2 1x1 data gradient back to the full map:
+ * out[n,h,w,c] = (h,w even ? a[n,h/2,w/2,c] (+ b) : 0) masked by mask_hi > 0 -> split planes */
+int sacb_scatter2_mask_split(const float* a, const float* b, const void* mask_hi, void* out_hi, void* out_lo,
+                             int N, int H, int W, int C, int P, int Q, void* stream);
+/* colsum[c] = sum_m (hi[m,c] + lo[m,c])  (BN d(beta), conv d(bias)); fp32 atomics into zeroed colsum */
+int sacb_colsum(const void* hi, const void* lo, float* colsum, int64_t M, int C, void* stream);
+/* weight preparation (per step): OIHW fp32 -> fprop planes [R*S][Kpad][C] and, if wt_* != NULL,
+ * dgrad planes [R*S][Cpad? no: C][K] flipped+transposed and scaled by scale[k] (NULL = 1) */
+int sacb_prep_weight(const float* w_oihw, const float* scale, int K, int C, int R, int S, int Kpad,
+                     void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, void* stream);
+/* BN fold (basenet.py:97-100 eval-mode statistics, trainable affine):
+ * scale = gamma * rsqrt(var + eps), shift = beta - mean * scale */
+int sacb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 float* scale, float* shift, int C, void* stream);
+/* finalize a conv+BN unit's parameter gradients from the raw filter gradient (DESIGN.md "BN backward"):
+ * dw_oihw[k][c][r][s] = scale[k] * dwraw[k][rs][c];
+ * dgamma[k] = (sum_{rs,c} w[k][c][r][s] * dwraw[k][rs][c] - mean[k] * dbeta[k]) * rsqrt(var[k]+eps) */
+int sacb_wgrad_finalize(const float* dwraw, const float* w_oihw, const float* scale, const float* mean,
+                        const float* var, float eps, const float* dbeta, float* dw_oihw, float* dgamma,
+                        int K, int C, int R, int S, void* stream);
+
+/* ---------------------------------------------------------------- SAC tail (models/sac.py)
+ * teacher logits -> pseudo labels; replaces SAC._refine + _update_running_conf + _avg_pool +
+ * _pseudo_labels_probs (sac.py:104-117,151-187,238-313). */
+typedef struct SacbTail {
+  uint32_t size;
+  int32_t BT, T, C, h, w, H, W;
+  const float* teacher_logits;   /* [BT,C,h,w] fp32 NCHW */
+  const int64_t* y;              /* [BT,H,W]; -1 = augmentation padding (sac.py:337) */
+  const float* affine;           /* [BT,2,3] */
+  const float* affine_inv;       /* [BT,2,3] */
+  float* running_conf;           /* [C] in/out (updated if training) */
+  int32_t training, discount;
+  float beta, stat_momentum, conf_upper, conf_lower;
+  /* workspace */
+  float* pooled;                 /* [BT/T,H,W,C+1] fp32: averaged probs + valid mask */
+  float* part_sums;              /* [nblocks(BT*H*W/256), C] partial class sums; sized by sacb_tail_workspace */
+  float* peaks;                  /* [BT,C] */
+  /* outputs */
+  float* conf;                   /* [BT,H,W] */
+  uint8_t* idx;                  /* [BT,H,W] */
+  uint8_t* labels;               /* [BT,H,W]  (255 = ignore) */
+  float* conf_mean;              /* [H,W]  batch-mean confidence (the [B,B,H,W] broadcast of sac.py:148) */
+  float* thresholds;             /* [BT,C] */
+  float* refined;                /* optional [BT,C,H,W] teacher_refined, NULL to skip */
+} SacbTail;
+int sacb_teacher_tail(const SacbTail* d, void* stream);
+size_t sacb_tail_part_sums_elems(int BT, int C, int H, int W);
+
+/* student loss (deeplabv2.py:217-224 + sac.py:134-149): fused upsample + log-softmax + weighted NLL */
+typedef struct SacbLoss {
+  uint32_t size;
+  int32_t BT, C, h, w, H, W;
+  const float* logits;           /* [BT,C,h,w] student */
+  const int64_t* y;              /* [BT,H,W] ground truth as given (-1 and 255 ignored) */
+  const uint8_t* labels;         /* pseudo labels */
+  const float* conf_mean;        /* [H,W] */
+  const float* running_conf;     /* [C] */
+  float focal_p;
+  float* losses;                 /* [2] : loss_ce, self_ce (zeroed by the call) */
+  double* scratch;               /* [2] */
+  /* backward */
+  float grad_scale;              /* d(total)/d(self_ce), e.g. LR_TARGET */
+  float* dlogits;                /* [BT,C,h,w] or NULL */
+} SacbLoss;
+int sacb_student_loss_fwd(const SacbLoss* d, void* stream);
+int sacb_student_loss_bwd(const SacbLoss* d, void* stream);
+/* bilinear align_corners=True upsample [B,C,h,w] -> [B,C,H,W] (F.interpolate, deeplabv2.py:217) */
+int sacb_upsample(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- optimiser-side multi-tensor kernels
+ * flat fp32 buffers with a segment table (one segment per tensor). */
+/* SAC._momentum_update (sac.py:83-102): out[0] = sum_seg ||slow-fast||_2 ; if update: slow = m*slow+(1-m)*fast */
+int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_offsets, int nseg, float momentum,
+                  int update, float* seg_sq, float* out, void* stream);
+/* torch.optim.SGD step (base_trainer.py:61-66): per-segment lr / weight decay, momentum buffer in place */
+int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_offsets, const float* seg_lr,
+             const float* seg_wd, int nseg, float momentum, int first_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SACB_H_ */
