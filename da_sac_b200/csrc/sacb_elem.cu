@@ -1,0 +1,516 @@
+// Bandwidth-bound glue kernels around the conv GEMMs: stem conv (3 input channels, CUDA cores), max-pool,
+// ReLU-mask / split / scatter, column sums, weight re-layout, BN folding and BN-gradient finalisation.
+// All activations are bf16 split planes in NHWC (see include/sacb.h).
+#include <atomic>
+#include "sacb_common.cuh"
+#include "../../include/sacb.h"
+
+namespace sacb {
+extern std::atomic<long long> g_launches;
+
+SACB_DEVINL float ld_split(const uint16_t* hi, const uint16_t* lo, size_t i) {
+  return bf16_bits_to_float(hi[i]) + bf16_bits_to_float(lo[i]);
+}
+SACB_DEVINL void st_split(uint16_t* hi, uint16_t* lo, size_t i, float v) {
+  uint16_t h = float_to_bf16_bits(v);
+  hi[i] = h;
+  lo[i] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+}
+SACB_DEVINL void unpack8f(const uint4& u, float* f) {
+  f[0] = bf16_bits_to_float(u.x & 0xFFFF); f[1] = bf16_bits_to_float(u.x >> 16);
+  f[2] = bf16_bits_to_float(u.y & 0xFFFF); f[3] = bf16_bits_to_float(u.y >> 16);
+  f[4] = bf16_bits_to_float(u.z & 0xFFFF); f[5] = bf16_bits_to_float(u.z >> 16);
+  f[6] = bf16_bits_to_float(u.w & 0xFFFF); f[7] = bf16_bits_to_float(u.w >> 16);
+}
+SACB_DEVINL void split8(const float* v, uint4& h, uint4& l) {
+  uint32_t ph[4], pl[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint16_t h0 = float_to_bf16_bits(v[2 * j]), h1 = float_to_bf16_bits(v[2 * j + 1]);
+    uint16_t l0 = float_to_bf16_bits(v[2 * j] - bf16_bits_to_float(h0));
+    uint16_t l1 = float_to_bf16_bits(v[2 * j + 1] - bf16_bits_to_float(h1));
+    ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  }
+  h = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  l = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem: conv 7x7 stride 2 pad 3, 3 -> 64, + BN affine + ReLU   (deeplabv2.py:160-163)
+// block = 8x16 output pixels, 256 threads; thread = 2 horizontally adjacent pixels x 16 channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_TW = 16, ST_TH = 8;
+constexpr int ST_PW = ST_TW * 2 + 5, ST_PH = ST_TH * 2 + 5;   // input patch 37x37
+
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
+                const float* __restrict__ shift, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                int N, int H, int W, int P, int Q) {
+  __shared__ float sw[147 * 64];                 // [tap][k]
+  __shared__ float sx[3][ST_PH][ST_PW + 1];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.z, p0 = blockIdx.y * ST_TH, q0 = blockIdx.x * ST_TW;
+  for (int i = tid; i < 147 * 64; i += 256) {
+    const int k = i & 63, tap = i >> 6;            // tap = (c*7 + r)*7 + s, w is [k][c][r][s]
+    sw[i] = w[k * 147 + tap];
+  }
+  const int h0 = p0 * 2 - 3, w0 = q0 * 2 - 3;
+  for (int i = tid; i < 3 * ST_PH * ST_PW; i += 256) {
+    const int c = i / (ST_PH * ST_PW), rem = i - c * ST_PH * ST_PW;
+    const int yy = rem / ST_PW, xx = rem - yy * ST_PW;
+    const int hh = h0 + yy, ww = w0 + xx;
+    sx[c][yy][xx] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((size_t)(n * 3 + c) * H + hh) * W + ww] : 0.f;
+  }
+  __syncthreads();
+  const int cg = tid & 3;            // 16-channel group
+  constexpr int NPX = 2;
+  const int pg = tid >> 2;           // 64 groups of 2 pixels: row = pg / 8, col group = pg % 8
+  const int py = pg >> 3, px0 = (pg & 7) * NPX;
+  float acc[NPX][16];
+#pragma unroll
+  for (int i = 0; i < NPX; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 7; ++r) {
+      const float* xr = &sx[c][py * 2 + r][px0 * 2];
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float4* wp = reinterpret_cast<const float4*>(&sw[((c * 7 + r) * 7 + s) * 64 + cg * 16]);
+        float wv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float4 t = wp[j]; wv[4 * j] = t.x; wv[4 * j + 1] = t.y; wv[4 * j + 2] = t.z; wv[4 * j + 3] = t.w; }
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) {
+          const float xv = xr[i * 2 + s];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+        }
+      }
+    }
+  const int p = p0 + py;
+  if (p >= P) return;
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    const int q = q0 + px0 + i;
+    if (q >= Q) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = cg * 16 + j;
+      v[j] = fmaxf(fmaf(acc[i][j], scale[k], shift[k]), 0.f);
+    }
+    const size_t o = (((size_t)n * P + p) * Q + q) * 64 + cg * 16;
+    uint4 h, l;
+    split8(v, h, l);
+    *reinterpret_cast<uint4*>(out_hi + o) = h; *reinterpret_cast<uint4*>(out_lo + o) = l;
+    split8(v + 8, h, l);
+    *reinterpret_cast<uint4*>(out_hi + o + 8) = h; *reinterpret_cast<uint4*>(out_lo + o + 8) = l;
+  }
+}
+
+// Stem filter gradient: dw[k][c][r][s] += sum_{n,p,q} g[n,p,q,k] * x[n,c,2p-3+r,2q-3+s]
+// persistent blocks loop over 8x16 output tiles; thread = (k, group of taps); one atomic per output per block.
+constexpr int SW_TW = 16, SW_TH = 8;
+constexpr int SW_PW = SW_TW * 2 + 5, SW_PH = SW_TH * 2 + 5;   // 37 x 21
+constexpr int SW_TAPS_PER_GROUP = 37;                          // 147 taps over 4 groups (last group 36)
+
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ g_hi, const uint16_t* __restrict__ g_lo,
+                  float* __restrict__ dw, int N, int H, int W, int P, int Q) {
+  __shared__ float sg[SW_TH * SW_TW][64];
+  __shared__ float sx[3 * SW_PH * SW_PW];
+  const int tid = threadIdx.x;
+  const int k = tid & 63, grp = tid >> 6;
+  const int tap0 = grp * SW_TAPS_PER_GROUP;
+  const int ntaps = min(SW_TAPS_PER_GROUP, 147 - tap0);
+  float acc[SW_TAPS_PER_GROUP];
+#pragma unroll
+  for (int i = 0; i < SW_TAPS_PER_GROUP; ++i) acc[i] = 0.f;
+  const int tiles_x = (Q + SW_TW - 1) / SW_TW, tiles_y = (P + SW_TH - 1) / SW_TH;
+  const int total = N * tiles_x * tiles_y;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int n = t / (tiles_x * tiles_y);
+    const int rem = t - n * tiles_x * tiles_y;
+    const int p0 = (rem / tiles_x) * SW_TH, q0 = (rem % tiles_x) * SW_TW;
+    __syncthreads();
+    for (int i = tid; i < SW_TH * SW_TW * 64; i += 256) {
+      const int kk = i & 63, px = i >> 6;
+      const int p = p0 + px / SW_TW, q = q0 + px % SW_TW;
+      float v = 0.f;
+      if (p < P && q < Q) v = ld_split(g_hi, g_lo, (((size_t)n * P + p) * Q + q) * 64 + kk);
+      sg[px][kk] = v;
+    }
+    const int h0 = p0 * 2 - 3, w0 = q0 * 2 - 3;
+    for (int i = tid; i < 3 * SW_PH * SW_PW; i += 256) {
+      const int c = i / (SW_PH * SW_PW), r2 = i - c * SW_PH * SW_PW;
+      const int yy = r2 / SW_PW, xx = r2 - yy * SW_PW;
+      const int hh = h0 + yy, ww = w0 + xx;
+      sx[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((size_t)(n * 3 + c) * H + hh) * W + ww] : 0.f;
+    }
+    __syncthreads();
+    for (int px = 0; px < SW_TH * SW_TW; ++px) {
+      const float gv = sg[px][k];
+      const int py = px / SW_TW, pxx = px % SW_TW;
+      const int base = (py * 2) * SW_PW + pxx * 2;
+#pragma unroll
+      for (int i = 0; i < SW_TAPS_PER_GROUP; ++i) {
+        if (i < ntaps) {
+          const int tap = tap0 + i;
+          const int c = tap / 49, rs = tap - c * 49;
+          const int r = rs / 7, s = rs - r * 7;
+          acc[i] = fmaf(gv, sx[c * SW_PH * SW_PW + base + r * SW_PW + s], acc[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < SW_TAPS_PER_GROUP; ++i)
+    if (i < ntaps) atomicAdd(&dw[k * 147 + tap0 + i], acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool2d(3, stride 2, pad 1, ceil_mode=True)   (deeplabv2.py:126)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
+                                   uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int P, int Q) {
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (C / 8));
+    size_t t = i / (C / 8);
+    const int q = (int)(t % Q); t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float best[8]; uint4 bh, bl; int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    uint32_t bhh[8], bll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { bhh[j] = 0; bll[j] = 0; }
+    for (int r = 0; r < 3; ++r) {
+      const int hh = p * 2 - 1 + r;
+      if (hh < 0 || hh >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int ww = q * 2 - 1 + s;
+        if (ww < 0 || ww >= W) continue;
+        const size_t o = (((size_t)n * H + hh) * W + ww) * C + cv * 8;
+        const uint4 h = *reinterpret_cast<const uint4*>(in_hi + o);
+        const uint4 l = *reinterpret_cast<const uint4*>(in_lo + o);
+        float fh[8], fl[8];
+        unpack8f(h, fh); unpack8f(l, fl);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = fh[j] + fl[j];
+          if (v > best[j]) {                      // first maximum in scan order wins (ATen max_pool2d)
+            best[j] = v; bi[j] = r * 3 + s;
+            bhh[j] = (hw[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+            bll[j] = (lw[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+          }
+        }
+      }
+    }
+    bh = make_uint4(bhh[0] | (bhh[1] << 16), bhh[2] | (bhh[3] << 16), bhh[4] | (bhh[5] << 16), bhh[6] | (bhh[7] << 16));
+    bl = make_uint4(bll[0] | (bll[1] << 16), bll[2] | (bll[3] << 16), bll[4] | (bll[5] << 16), bll[6] | (bll[7] << 16));
+    const size_t oo = (((size_t)n * P + p) * Q + q) * C + cv * 8;
+    *reinterpret_cast<uint4*>(out_hi + oo) = bh;
+    *reinterpret_cast<uint4*>(out_lo + oo) = bl;
+    uint32_t i0 = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    uint32_t i1 = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + oo) = make_uint2(i0, i1);
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ g_out, const uint8_t* __restrict__ idx,
+                                   const uint16_t* __restrict__ in_hi, uint16_t* __restrict__ gin_hi,
+                                   uint16_t* __restrict__ gin_lo, int N, int H, int W, int C, int P, int Q) {
+  const size_t total = (size_t)N * H * W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    size_t t = i / C;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc = 0.f;
+    if (bf16_bits_to_float(in_hi[i]) > 0.f) {
+      const int pl = (h) / 2, ph = (h + 1) / 2;       // windows p with 2p-1 <= h <= 2p+1
+      const int ql = (w) / 2, qh = (w + 1) / 2;
+      for (int p = pl; p <= ph; ++p) {
+        if (p >= P) continue;
+        const int r = h - (2 * p - 1);
+        if (r < 0 || r > 2) continue;
+        for (int q = ql; q <= qh; ++q) {
+          if (q >= Q) continue;
+          const int s = w - (2 * q - 1);
+          if (s < 0 || s > 2) continue;
+          const size_t o = (((size_t)n * P + p) * Q + q) * C + c;
+          if (idx[o] == r * 3 + s) acc += g_out[o];
+        }
+      }
+    }
+    st_split(gin_hi, gin_lo, i, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise: (a [+ b]) masked by forward activation > 0, written as split planes
+// ------------------------------------------------------------------------------------------------
+__global__ void add_mask_split_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                      const uint16_t* __restrict__ mask_hi, uint16_t* __restrict__ out_hi,
+                                      uint16_t* __restrict__ out_lo, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    const float4 a0 = reinterpret_cast<const float4*>(a)[2 * i], a1 = reinterpret_cast<const float4*>(a)[2 * i + 1];
+    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    if (b) {
+      const float4 b0 = reinterpret_cast<const float4*>(b)[2 * i], b1 = reinterpret_cast<const float4*>(b)[2 * i + 1];
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (mask_hi) {
+      float m[8];
+      unpack8f(reinterpret_cast<const uint4*>(mask_hi)[i], m);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+    }
+    uint4 h, l;
+    split8(v, h, l);
+    reinterpret_cast<uint4*>(out_hi)[i] = h;
+    reinterpret_cast<uint4*>(out_lo)[i] = l;
+  }
+}
+
+__global__ void scatter2_mask_split_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                           const uint16_t* __restrict__ mask_hi, uint16_t* __restrict__ out_hi,
+                                           uint16_t* __restrict__ out_lo, int N, int H, int W, int C, int P, int Q) {
+  const size_t total = (size_t)N * H * W * (C / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (C / 8));
+    size_t t = i / (C / 8);
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (!(h & 1) && !(w & 1) && (h >> 1) < P && (w >> 1) < Q) {
+      const size_t o = ((((size_t)n * P + (h >> 1)) * Q + (w >> 1)) * C + cv * 8) / 4;
+      const float4 a0 = reinterpret_cast<const float4*>(a)[o], a1 = reinterpret_cast<const float4*>(a)[o + 1];
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+      if (b) {
+        const float4 b0 = reinterpret_cast<const float4*>(b)[o], b1 = reinterpret_cast<const float4*>(b)[o + 1];
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (mask_hi) {
+        float m[8];
+        unpack8f(reinterpret_cast<const uint4*>(mask_hi)[i], m);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+      }
+    }
+    uint4 hh, ll;
+    split8(v, hh, ll);
+    reinterpret_cast<uint4*>(out_hi)[i] = hh;
+    reinterpret_cast<uint4*>(out_lo)[i] = ll;
+  }
+}
+
+// column sums of a split-plane matrix [M, C]: thread = 8 channels x 64 rows, atomics into colsum
+__global__ void colsum_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                              float* __restrict__ colsum, long long M, int C) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cv >= C / 8) return;
+  const long long r0 = (long long)blockIdx.y * 64;
+  const long long r1 = r0 + 64 < M ? r0 + 64 : M;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const size_t o = ((size_t)r * C) / 8 + cv;
+    float fh[8], fl[8];
+    unpack8f(reinterpret_cast<const uint4*>(hi)[o], fh);
+    unpack8f(reinterpret_cast<const uint4*>(lo)[o], fl);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += fh[j] + fl[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&colsum[cv * 8 + j], acc[j]);
+}
+
+// weight re-layout (per optimiser step):  OIHW fp32 -> fprop planes [RS][Kf][C] and dgrad planes [RS][C][Kt]
+__global__ void prep_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, int K, int C, int R,
+                                   int S, int Kf, int Kt, uint16_t* __restrict__ wf_hi, uint16_t* __restrict__ wf_lo,
+                                   uint16_t* __restrict__ wt_hi, uint16_t* __restrict__ wt_lo) {
+  const int RS = R * S;
+  const size_t nf = wf_hi ? (size_t)RS * Kf * C : 0;
+  const size_t nt = wt_hi ? (size_t)RS * C * Kt : 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nf + nt; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int c = (int)(i % C);
+      size_t t = i / C;
+      const int k = (int)(t % Kf);
+      const int rs = (int)(t / Kf);
+      float v = 0.f;
+      if (k < K) v = w[((size_t)k * C + c) * RS + rs];
+      st_split(wf_hi, wf_lo, i, v);
+    } else {
+      const size_t j = i - nf;
+      const int k = (int)(j % Kt);
+      size_t t = j / Kt;
+      const int c = (int)(t % C);
+      const int rs = (int)(t / C);
+      float v = 0.f;
+      if (k < K) {
+        v = w[((size_t)k * C + c) * RS + (RS - 1 - rs)];     // 180-degree flipped tap
+        if (scale) v *= scale[k];
+      }
+      st_split(wt_hi, wt_lo, j, v);
+    }
+  }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // same operation order as ATen's batch_norm inference path: invstd = 1/sqrt(var+eps)
+  const float invstd = 1.0f / sqrtf(var[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean[c] * sc;
+}
+
+// block per output channel k
+__global__ void __launch_bounds__(256)
+wgrad_finalize_kernel(const float* __restrict__ dwraw, const float* __restrict__ w, const float* __restrict__ scale,
+                      const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                      const float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dgamma, int K,
+                      int C, int RS) {
+  const int k = blockIdx.x;
+  const float sc = scale ? scale[k] : 1.f;
+  float dot = 0.f;
+  const size_t base = (size_t)k * RS * C;
+  for (int i = threadIdx.x; i < RS * C; i += blockDim.x) {
+    const int rs = i / C, c = i - rs * C;
+    const float g = dwraw[base + i];                 // [k][rs][c]
+    const size_t o = base + (size_t)c * RS + rs;     // [k][c][rs]
+    dot = fmaf(w[o], g, dot);
+    dw[o] = sc * g;
+  }
+  if (dgamma) {
+    __shared__ float red[8];
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffff, dot, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      dgamma[k] = (s - mean[k] * dbeta[k]) * (1.0f / sqrtf(var[k] + eps));
+    }
+  }
+}
+
+static inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace sacb
+
+using namespace sacb;
+#define ST ((cudaStream_t)stream)
+#define LAUNCHED() do { g_launches++; SACB_CHECK_CUDA(cudaGetLastError()); } while (0)
+
+extern "C" int sacb_stem_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out_hi,
+                             void* out_lo, int N, int H, int W, int P, int Q, void* stream) {
+  SACB_REQUIRE(P == (H + 6 - 7) / 2 + 1 && Q == (W + 6 - 7) / 2 + 1, "sacb_stem_fwd: bad output size");
+  dim3 grid((Q + ST_TW - 1) / ST_TW, (P + ST_TH - 1) / ST_TH, N);
+  stem_fwd_kernel<<<grid, 256, 0, ST>>>(x, w, scale, shift, (uint16_t*)out_hi, (uint16_t*)out_lo, N, H, W, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_stem_wgrad(const float* x, const void* g_hi, const void* g_lo, float* dw, int N, int H, int W, int P,
+                               int Q, void* stream) {
+  stem_wgrad_kernel<<<148 * 2, 256, 0, ST>>>(x, (const uint16_t*)g_hi, (const uint16_t*)g_lo, dw, N, H, W, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_maxpool_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx, int N,
+                                int H, int W, int C, int P, int Q, void* stream) {
+  SACB_REQUIRE(C % 8 == 0, "sacb_maxpool_fwd: C %% 8");
+  int Pe = (H + 2 - 3 + 1) / 2 + 1; if ((Pe - 1) * 2 >= H + 1) --Pe;
+  int Qe = (W + 2 - 3 + 1) / 2 + 1; if ((Qe - 1) * 2 >= W + 1) --Qe;
+  SACB_REQUIRE(P == Pe && Q == Qe, "sacb_maxpool_fwd: bad ceil-mode output size (%d,%d) vs (%d,%d)", P, Q, Pe, Qe);
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint16_t*)in_hi, (const uint16_t*)in_lo,
+                                                          (uint16_t*)out_hi, (uint16_t*)out_lo, idx, N, H, W, C, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_maxpool_bwd(const float* g_out, const uint8_t* idx, const void* in_hi, void* gin_hi, void* gin_lo,
+                                int N, int H, int W, int C, int P, int Q, void* stream) {
+  const size_t total = (size_t)N * H * W * C;
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(g_out, idx, (const uint16_t*)in_hi, (uint16_t*)gin_hi,
+                                                          (uint16_t*)gin_lo, N, H, W, C, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_add_mask_split(const float* a, const float* b, const void* mask_hi, void* out_hi, void* out_lo,
+                                   int64_t n, void* stream) {
+  SACB_REQUIRE(n % 8 == 0, "sacb_add_mask_split: n %% 8");
+  add_mask_split_kernel<<<grid_for((size_t)n / 8, 256), 256, 0, ST>>>(a, b, (const uint16_t*)mask_hi, (uint16_t*)out_hi,
+                                                                     (uint16_t*)out_lo, (size_t)n / 8);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_scatter2_mask_split(const float* a, const float* b, const void* mask_hi, void* out_hi, void* out_lo,
+                                        int N, int H, int W, int C, int P, int Q, void* stream) {
+  SACB_REQUIRE(C % 8 == 0, "sacb_scatter2_mask_split: C %% 8");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  scatter2_mask_split_kernel<<<grid_for(total, 256), 256, 0, ST>>>(a, b, (const uint16_t*)mask_hi, (uint16_t*)out_hi,
+                                                                  (uint16_t*)out_lo, N, H, W, C, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_colsum(const void* hi, const void* lo, float* colsum, int64_t M, int C, void* stream) {
+  SACB_REQUIRE(C % 8 == 0, "sacb_colsum: C %% 8");
+  const int threads = 64;
+  dim3 grid((C / 8 + threads - 1) / threads, (unsigned)((M + 63) / 64));
+  colsum_kernel<<<grid, threads, 0, ST>>>((const uint16_t*)hi, (const uint16_t*)lo, colsum, (long long)M, C);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_prep_weight(const float* w, const float* scale, int K, int C, int R, int S, int Kf, int Kt,
+                                void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, void* stream) {
+  const size_t n = (wf_hi ? (size_t)R * S * Kf * C : 0) + (wt_hi ? (size_t)R * S * C * Kt : 0);
+  if (n == 0) return 0;
+  prep_weight_kernel<<<grid_for(n, 256), 256, 0, ST>>>(w, scale, K, C, R, S, Kf, Kt, (uint16_t*)wf_hi, (uint16_t*)wf_lo,
+                                                      (uint16_t*)wt_hi, (uint16_t*)wt_lo);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                            float* scale, float* shift, int C, void* stream) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_wgrad_finalize(const float* dwraw, const float* w, const float* scale, const float* mean,
+                                   const float* var, float eps, const float* dbeta, float* dw, float* dgamma, int K,
+                                   int C, int R, int S, void* stream) {
+  wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, K, C, R * S);
+  LAUNCHED();
+  return 0;
+}

@@ -599,8 +599,6 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
-  SACB_REQUIRE(d->k_valid == d->K || (!d->out_hi && !d->out_f32 && !d->add_f32 && !d->add_hi && !d->mask_hi),
-               "sacb_conv_gemm: k_valid < K only supported with the NCHW output");
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
     case 128: return launch_gemm<128>(ah, al, bh, bl, a, st);

@@ -1,0 +1,419 @@
+"""Layer executor for DeepLabV2-ResNet101 on libsac_b200 (host side, Python).
+
+This is the part of the reference that lives in ``models/deeplabv2.py`` (ResNet /
+Bottleneck / Classifier_Module forward) plus what autograd derives from it,
+re-expressed as a fixed schedule of C-ABI kernel calls:
+
+* activations: bf16 split planes, NHWC (include/sacb.h);
+* every conv + frozen-BN (+ReLU) (+residual) unit is ONE ``sacb_conv_gemm`` launch;
+* backward of a unit = one ``sacb_conv_gemm`` (data gradient, with the ReLU mask of the
+  producer fused) + one ``sacb_conv_wgrad`` + ``sacb_colsum`` (d beta) +
+  ``sacb_wgrad_finalize`` (dW re-layout, d gamma from <W, dW_raw>).
+
+No PyTorch op touches the activations; torch provides memory and streams only.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+BN_EPS = 1e-5
+NUM_CLASSES = 19
+
+
+class ConvSpec(object):
+    __slots__ = ("name", "bn", "K", "C", "R", "stride", "dil", "pad", "hin", "win", "hout", "wout", "Kf", "Kt")
+
+    def __init__(self, name, bn, K, Cc, R, stride, dil, pad):
+        self.name, self.bn, self.K, self.C, self.R = name, bn, K, Cc, R
+        self.stride, self.dil, self.pad = stride, dil, pad
+        self.Kf = (K + 31) // 32 * 32       # rows of the fprop weight planes
+        self.Kt = (K + 63) // 64 * 64       # reduction length of the dgrad weight planes
+
+    def geom(self, N):
+        return (N, self.hin, self.win, self.C, self.Kf, self.R, self.stride, self.dil, self.pad)
+
+    def geom_dgrad(self, N):
+        # data gradient of a stride-1 conv = conv of G with flipped/transposed weights, same pad/dilation
+        return (N, self.hout, self.wout, self.Kt, self.C, self.R, 1, self.dil, self.pad if self.stride == 1 else 0)
+
+
+def build_resnet101(H, W):
+    """Layer table of ResNet(Bottleneck, [3,4,23,3]) + ASPP (/root/reference/models/deeplabv2.py:118-171)
+    with spatial sizes resolved for an H x W input."""
+    specs = {}
+    order = []
+
+    def add(name, bn, K, Cc, R, stride, dil, pad, hin, win):
+        s = ConvSpec(name, bn, K, Cc, R, stride, dil, pad)
+        s.hin, s.win = hin, win
+        s.hout, s.wout = L.conv_out_hw(hin, win, R, stride, dil, pad)
+        specs[name] = s
+        order.append(name)
+        return s
+
+    stem = add("model.conv1", "model.bn1", 64, 3, 7, 2, 1, 3, H, W)
+    ph = (stem.hout + 2 - 3 + 1) // 2 + 1
+    pw = (stem.wout + 2 - 3 + 1) // 2 + 1
+    if (ph - 1) * 2 >= stem.hout + 1: ph -= 1
+    if (pw - 1) * 2 >= stem.wout + 1: pw -= 1
+    blocks = []
+    inplanes, h, w = 64, ph, pw
+    for li, (planes, nblocks, stride, dil) in enumerate(((64, 3, 1, 1), (128, 4, 2, 1), (256, 23, 1, 2), (512, 3, 1, 4)), 1):
+        for b in range(nblocks):
+            p = "model.layer%d.%d" % (li, b)
+            s = stride if b == 0 else 1
+            c1 = add(p + ".conv1", p + ".bn1", planes, inplanes, 1, s, 1, 0, h, w)
+            c2 = add(p + ".conv2", p + ".bn2", planes, planes, 3, 1, dil, dil, c1.hout, c1.wout)
+            c3 = add(p + ".conv3", p + ".bn3", planes * 4, planes, 1, 1, 1, 0, c2.hout, c2.wout)
+            ds = add(p + ".downsample.0", p + ".downsample.1", planes * 4, inplanes, 1, s, 1, 0, h, w) if b == 0 else None
+            blocks.append((p, c1, c2, c3, ds))
+            inplanes, h, w = planes * 4, c3.hout, c3.wout
+    aspp = [add("model.layer5.conv2d_list.%d" % i, None, NUM_CLASSES, 2048, 3, 1, d, d, h, w)
+            for i, d in enumerate((6, 12, 18, 24))]
+    return dict(specs=specs, order=order, stem=stem, pool_hw=(ph, pw), blocks=blocks, aspp=aspp, out_hw=(h, w))
+
+
+def param_layout(net):
+    """Flat-buffer layout in the reference's state_dict order: every float tensor whose key ends in
+    weight / bias / running_mean / running_var (the set SAC._momentum_update walks, sac.py:88-91)."""
+    entries = []   # (key, shape, is_param)
+    for name in net["order"]:
+        s = net["specs"][name]
+        entries.append((name + ".weight", (s.K, s.C, s.R, s.R), True))
+        if s.bn is None:
+            entries.append((name + ".bias", (s.K,), True))
+        else:
+            entries.append((s.bn + ".weight", (s.K,), True))
+            entries.append((s.bn + ".bias", (s.K,), True))
+            entries.append((s.bn + ".running_mean", (s.K,), False))
+            entries.append((s.bn + ".running_var", (s.K,), False))
+    offs, o = {}, 0
+    for key, shape, is_p in entries:
+        n = 1
+        for d in shape: n *= d
+        offs[key] = (o, n, shape, is_p)
+        o += (n + 3) // 4 * 4       # keep every tensor 16-byte aligned
+    return entries, offs, o
+
+
+class FlatParams(object):
+    """One contiguous fp32 buffer holding a backbone's parameters and BN statistics."""
+
+    def __init__(self, net, device):
+        self.entries, self.offs, self.total = param_layout(net)
+        self.buf = torch.zeros(self.total, device=device, dtype=torch.float32)
+
+    def view(self, key):
+        o, n, shape, _ = self.offs[key]
+        return self.buf[o:o + n].view(shape)
+
+    def load(self, sd, prefix=""):
+        for key, _, _ in self.entries:
+            self.view(key).copy_(sd[prefix + key])
+
+    def ranges(self, params_only=False):
+        r = []
+        for key, _, is_p in self.entries:
+            if params_only and not is_p: continue
+            o, n, _, _ = self.offs[key]
+            r += [o, o + n]
+        return r
+
+
+class WeightPlanes(object):
+    """bf16 split planes of every conv's weights in the layouts the GEMM kernels consume, plus the folded
+    BN affine (scale/shift).  Rebuilt from a FlatParams by ``prepare`` (once per optimiser step for the
+    student, once per EMA update for the teacher)."""
+
+    def __init__(self, net, device, with_dgrad):
+        self.net, self.with_dgrad = net, with_dgrad
+        nf = nt = nsc = 0
+        self.off = {}
+        for name in net["order"]:
+            s = net["specs"][name]
+            if s.C == 3:
+                self.off[name] = (None, None, nsc)
+            else:
+                self.off[name] = (nf, nt, nsc)
+                nf += s.R * s.R * s.Kf * s.C
+                nt += s.R * s.R * s.C * s.Kt
+            nsc += s.Kf
+        bf = torch.bfloat16
+        self.wf_hi = torch.empty(nf, device=device, dtype=bf); self.wf_lo = torch.empty(nf, device=device, dtype=bf)
+        if with_dgrad:
+            self.wt_hi = torch.empty(nt, device=device, dtype=bf); self.wt_lo = torch.empty(nt, device=device, dtype=bf)
+        self.scale = torch.ones(nsc, device=device); self.shift = torch.zeros(nsc, device=device)
+
+    def wf(self, name):
+        s = self.net["specs"][name]; o = self.off[name][0]; n = s.R * s.R * s.Kf * s.C
+        return self.wf_hi[o:o + n], self.wf_lo[o:o + n]
+
+    def wt(self, name):
+        s = self.net["specs"][name]; o = self.off[name][1]; n = s.R * s.R * s.C * s.Kt
+        return self.wt_hi[o:o + n], self.wt_lo[o:o + n]
+
+    def affine(self, name):
+        s = self.net["specs"][name]; o = self.off[name][2]
+        return self.scale[o:o + s.Kf], self.shift[o:o + s.Kf]
+
+    def prepare(self, flat):
+        lib, st = L.lib(), L.stream()
+        for name in self.net["order"]:
+            s = self.net["specs"][name]
+            sc, sh = self.affine(name)
+            if s.bn is not None:
+                L.check(lib.sacb_bn_fold(L.ptr(flat.view(s.bn + ".weight")), L.ptr(flat.view(s.bn + ".bias")),
+                                         L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
+                                         C.c_float(BN_EPS), L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
+            else:
+                sh[:s.K].copy_(flat.view(name + ".bias"))
+            if s.C == 3:
+                continue
+            fh, fl = self.wf(name)
+            th, tl = self.wt(name) if self.with_dgrad else (None, None)
+            L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc) if s.bn is not None else None,
+                                         s.K, s.C, s.R, s.R, s.Kf, s.Kt, L.ptr(fh), L.ptr(fl), L.ptr(th), L.ptr(tl), st),
+                    "sacb_prep_weight")
+
+
+class Planes(object):
+    """a bf16 hi/lo pair viewed as [M, C]"""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+
+class BufferPool(object):
+    """fixed set of max-size scratch buffers handed out round-robin by name"""
+
+    def __init__(self, n_elems, count, dtype, device):
+        self.bufs = [torch.empty(n_elems, device=device, dtype=dtype) for _ in range(count)]
+        self.free = list(range(count))
+        self.used = {}
+
+    def get(self, tag, n):
+        assert tag not in self.used, tag
+        i = self.free.pop()
+        self.used[tag] = i
+        return self.bufs[i][:n]
+
+    def put(self, tag):
+        self.free.append(self.used.pop(tag))
+
+    def reset(self):
+        self.free = list(range(len(self.bufs))); self.used = {}
+
+
+class ResNet101Engine(object):
+    def __init__(self, N, H, W, device):
+        self.N, self.H, self.W, self.device = N, H, W, device
+        self.net = build_resnet101(H, W)
+        net = self.net
+        bf = torch.bfloat16
+        # student activations kept for backward
+        self.act = {}
+        st = net["stem"]
+        def planes(m, c):
+            return Planes(torch.empty(m * c, device=device, dtype=bf), torch.empty(m * c, device=device, dtype=bf))
+        self.act["stem"] = planes(N * st.hout * st.wout, 64)
+        ph, pw = net["pool_hw"]
+        self.act["pool"] = planes(N * ph * pw, 64)
+        self.pool_idx = torch.empty(N * ph * pw * 64, device=device, dtype=torch.uint8)
+        max_elems = N * st.hout * st.wout * 64
+        for (p, c1, c2, c3, ds) in net["blocks"]:
+            for c in (c1, c2, c3):
+                self.act[c.name] = planes(N * c.hout * c.wout, c.K)
+                max_elems = max(max_elems, N * c.hout * c.wout * c.K)
+            if ds is not None:
+                self.act[ds.name] = planes(N * ds.hout * ds.wout, ds.K)
+        self.max_elems = max_elems
+        # teacher ping-pong planes / gradient planes / fp32 scratch
+        self.tpool_hi = BufferPool(max_elems, 5, bf, device); self.tpool_lo = BufferPool(max_elems, 5, bf, device)
+        self.fpool = BufferPool(max_elems, 2, torch.float32, device)
+        oh, ow = net["out_hw"]
+        self.head_acc = torch.empty(N * oh * ow * 32, device=device)
+        self.g5 = planes(N * oh * ow, 64)
+        self.dwraw = torch.empty(max(s.Kt * s.R * s.R * s.C for s in net["specs"].values()), device=device)
+
+    # ------------------------------------------------------------------ forward
+    def _tplanes(self, tag, n):
+        return Planes(self.tpool_hi.get(tag, n), self.tpool_lo.get(tag, n))
+
+    def _tput(self, tag):
+        self.tpool_hi.put(tag); self.tpool_lo.put(tag)
+
+    def forward(self, flat, wp, x, logits_out, keep):
+        """x: fp32 NCHW [N,3,H,W]; logits_out: fp32 NCHW [N,19,h,w]. keep=True stores activations for backward."""
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        stem = net["stem"]
+        ph, pw = net["pool_hw"]
+        self.tpool_hi.reset(); self.tpool_lo.reset()
+        get = (lambda tag, n: self.act[tag]) if keep else self._tplanes
+        put = (lambda tag: None) if keep else self._tput
+        sc, sh = wp.affine(stem.name)
+        a_stem = get("stem", N * stem.hout * stem.wout * 64)
+        L.check(lib.sacb_stem_fwd(L.ptr(x), L.ptr(flat.view(stem.name + ".weight")), L.ptr(sc), L.ptr(sh),
+                                  L.ptr(a_stem.hi), L.ptr(a_stem.lo), N, self.H, self.W, stem.hout, stem.wout, st), "sacb_stem_fwd")
+        a = get("pool", N * ph * pw * 64)
+        L.check(lib.sacb_maxpool_fwd(L.ptr(a_stem.hi), L.ptr(a_stem.lo), L.ptr(a.hi), L.ptr(a.lo), L.ptr(self.pool_idx),
+                                     N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_fwd")
+        put("stem")
+        xtag = "pool"
+        for (p, c1, c2, c3, ds) in net["blocks"]:
+            o1 = get(c1.name, N * c1.hout * c1.wout * c1.K)
+            self._unit(wp, c1, a, o1, relu=True)
+            o2 = get(c2.name, N * c2.hout * c2.wout * c2.K)
+            self._unit(wp, c2, o1, o2, relu=True)
+            put(c1.name)
+            if ds is not None:
+                r = get(ds.name, N * ds.hout * ds.wout * ds.K)
+                self._unit(wp, ds, a, r, relu=False)
+            else:
+                r = a
+            o3 = get(c3.name, N * c3.hout * c3.wout * c3.K)
+            self._unit(wp, c3, o2, o3, relu=True, res=r)
+            put(c2.name)
+            if ds is not None: put(ds.name)
+            put(xtag)
+            a, xtag = o3, c3.name
+        # ASPP head: sum of 4 dilated 3x3 convs + biases (deeplabv2.py:112-116), accumulated in fp32
+        for i, s in enumerate(net["aspp"]):
+            fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+            last = i == len(net["aspp"]) - 1
+            L.conv_gemm(a.hi, a.lo, fh, fl, s.geom(N), k_valid=s.K, scale=sc, shift=sh,
+                        add_f32=self.head_acc if i > 0 else None, out_f32=None if last else self.head_acc,
+                        out_nchw=logits_out if last else None)
+        put(xtag)
+        return logits_out
+
+    def _unit(self, wp, s, xin, out, relu, res=None):
+        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+        L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), scale=sc, shift=sh,
+                    add_hi=None if res is None else res.hi, add_lo=None if res is None else res.lo,
+                    relu=relu, out_hi=out.hi, out_lo=out.lo)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, flat, wp, x, dlogits, grad):
+        """dlogits fp32 NCHW [N,19,h,w]; writes every parameter gradient into ``grad`` (FlatParams layout)."""
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        self.tpool_hi.reset(); self.tpool_lo.reset(); self.fpool.reset()
+        oh, ow = net["out_hw"]
+        M5 = N * oh * ow
+        # dlogits -> NHWC padded to 64 channels -> split planes
+        g = torch.zeros(M5, 64, device=self.device)
+        g[:, :NUM_CLASSES] = dlogits.permute(0, 2, 3, 1).reshape(M5, NUM_CLASSES)
+        L.check(lib.sacb_add_mask_split(L.ptr(g), None, None, L.ptr(self.g5.hi), L.ptr(self.g5.lo), C.c_int64(M5 * 64), st),
+                "sacb_add_mask_split")
+        dbias = torch.zeros(64, device=self.device)
+        L.check(lib.sacb_colsum(L.ptr(self.g5.hi), L.ptr(self.g5.lo), L.ptr(dbias), C.c_int64(M5), 64, st), "sacb_colsum")
+        blocks = net["blocks"]
+        xlast = self.act[blocks[-1][3].name]
+        acc = self.fpool.get("acc", M5 * 2048)
+        gout = self._tplanes("gout", M5 * 2048)
+        for i, s in enumerate(net["aspp"]):
+            grad.view(s.name + ".bias").copy_(dbias[:NUM_CLASSES])
+            self._wgrad(flat, wp, s, xlast, self.g5, grad, dbeta=None)
+            th, tl = wp.wt(s.name)
+            last = i == len(net["aspp"]) - 1
+            L.conv_gemm(self.g5.hi, self.g5.lo, th, tl, s.geom_dgrad(N), add_f32=acc if i > 0 else None,
+                        out_f32=None if last else acc, mask_hi=xlast.hi if last else None,
+                        out_hi=gout.hi if last else None, out_lo=gout.lo if last else None)
+        self.fpool.put("acc")
+        for bi in range(len(blocks) - 1, -1, -1):
+            (p, c1, c2, c3, ds) = blocks[bi]
+            xin = self.act[blocks[bi - 1][3].name] if bi > 0 else self.act["pool"]
+            o1, o2 = self.act[c1.name], self.act[c2.name]
+            M = N * c3.hout * c3.wout
+            # conv3 + bn3 (no ReLU between bn3 and the residual sum): g3 = gout
+            dbeta3 = self._dbeta(gout, M, c3.K)
+            self._wgrad(flat, wp, c3, o2, gout, grad, dbeta3)
+            g2 = self._tplanes("g2", M * c2.K)
+            th, tl = wp.wt(c3.name)
+            L.conv_gemm(gout.hi, gout.lo, th, tl, c3.geom_dgrad(N), mask_hi=o2.hi, out_hi=g2.hi, out_lo=g2.lo)
+            # conv2 + bn2 + relu
+            dbeta2 = self._dbeta(g2, M, c2.K)
+            self._wgrad(flat, wp, c2, o1, g2, grad, dbeta2)
+            g1 = self._tplanes("g1", M * c1.K)
+            th, tl = wp.wt(c2.name)
+            L.conv_gemm(g2.hi, g2.lo, th, tl, c2.geom_dgrad(N), mask_hi=o1.hi, out_hi=g1.hi, out_lo=g1.lo)
+            self._tput("g2")
+            # conv1 + bn1 + relu (and the downsample branch of the first block of a layer)
+            dbeta1 = self._dbeta(g1, M, c1.K)
+            self._wgrad(flat, wp, c1, xin, g1, grad, dbeta1)
+            if ds is not None:
+                self._wgrad(flat, wp, ds, xin, gout, grad, dbeta3)      # d beta of the downsample BN == d beta of bn3
+            Min = N * c1.hin * c1.win
+            th1, tl1 = wp.wt(c1.name)
+            if bi == 0:
+                # block input is the max-pool output: no ReLU mask, gradient continues through the pool
+                thd, tld = wp.wt(ds.name)
+                tmp = self.fpool.get("tmp", Min * c1.C)
+                L.conv_gemm(gout.hi, gout.lo, thd, tld, ds.geom_dgrad(N), out_f32=tmp)
+                gp = self.fpool.get("gpool", Min * c1.C)
+                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_f32=tmp, out_f32=gp)
+                self._tput("g1"); self._tput("gout")
+                break
+            gx = self._tplanes("gx", Min * c1.C)
+            if ds is None:
+                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_hi=gout.hi, add_lo=gout.lo, mask_hi=xin.hi,
+                            out_hi=gx.hi, out_lo=gx.lo)
+            elif c1.stride == 1:
+                thd, tld = wp.wt(ds.name)
+                tmp = self.fpool.get("tmp", Min * c1.C)
+                L.conv_gemm(gout.hi, gout.lo, thd, tld, ds.geom_dgrad(N), out_f32=tmp)
+                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_f32=tmp, mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo)
+                self.fpool.put("tmp")
+            else:
+                # stride-2 1x1 convs: compact data gradients on the 65x65 grid, scattered to the even pixels
+                thd, tld = wp.wt(ds.name)
+                ta = self.fpool.get("tmp", M * c1.C); tb = self.fpool.get("tmp2", M * c1.C)
+                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), out_f32=ta)
+                L.conv_gemm(gout.hi, gout.lo, thd, tld, ds.geom_dgrad(N), out_f32=tb)
+                L.check(lib.sacb_scatter2_mask_split(L.ptr(ta), L.ptr(tb), L.ptr(xin.hi), L.ptr(gx.hi), L.ptr(gx.lo),
+                                                     N, c1.hin, c1.win, c1.C, c1.hout, c1.wout, st), "sacb_scatter2_mask_split")
+                self.fpool.put("tmp"); self.fpool.put("tmp2")
+            self._tput("g1"); self._tput("gout")
+            # rename gx -> gout for the next (earlier) block
+            self.tpool_hi.used["gout"] = self.tpool_hi.used.pop("gx"); self.tpool_lo.used["gout"] = self.tpool_lo.used.pop("gx")
+            gout = gx
+        # max-pool backward (+ ReLU mask of the stem) and the stem conv
+        stem = net["stem"]
+        ph, pw = net["pool_hw"]
+        a_stem = self.act["stem"]
+        gs = self._tplanes("gstem", N * stem.hout * stem.wout * 64)
+        L.check(lib.sacb_maxpool_bwd(L.ptr(gp), L.ptr(self.pool_idx), L.ptr(a_stem.hi), L.ptr(gs.hi), L.ptr(gs.lo),
+                                     N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_bwd")
+        dbeta = self._dbeta(gs, N * stem.hout * stem.wout, 64)
+        dwraw = self.dwraw[:64 * 147]
+        dwraw.zero_()
+        L.check(lib.sacb_stem_wgrad(L.ptr(x), L.ptr(gs.hi), L.ptr(gs.lo), L.ptr(dwraw), N, self.H, self.W, stem.hout, stem.wout, st),
+                "sacb_stem_wgrad")
+        self._finalize(flat, wp, stem, dwraw, grad, dbeta, C_eff=147, RS=1)
+
+    def _dbeta(self, g, M, K):
+        d = torch.zeros(K, device=self.device)
+        L.check(L.lib().sacb_colsum(L.ptr(g.hi), L.ptr(g.lo), L.ptr(d), C.c_int64(M), K, L.stream()), "sacb_colsum")
+        return d
+
+    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
+        dwraw = self.dwraw[:s.K * s.R * s.R * s.C]
+        dwraw.zero_()
+        L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, dwraw, (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
+        self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R)
+
+    def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS):
+        lib, st = L.lib(), L.stream()
+        if s.bn is not None:
+            sc, _ = wp.affine(s.name)
+            grad.view(s.bn + ".bias").copy_(dbeta)
+            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), L.ptr(sc),
+                                            L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
+                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")),
+                                            L.ptr(grad.view(s.bn + ".weight")), s.K, C_eff, RS, 1, st), "sacb_wgrad_finalize")
+        else:
+            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), None, None, None,
+                                            C.c_float(BN_EPS), None, L.ptr(grad.view(s.name + ".weight")), None,
+                                            s.K, C_eff, RS, 1, st), "sacb_wgrad_finalize")

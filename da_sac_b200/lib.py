@@ -28,8 +28,8 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.sacb_last_error.restype = C.c_char_p
         _lib.sacb_launch_count.restype = C.c_int64
-        if hasattr(_lib, "sacb_tail_part_sums_elems"):
-            _lib.sacb_tail_part_sums_elems.restype = C.c_size_t
+        for f in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):
+            getattr(_lib, f).restype = C.c_size_t
         if _lib.sacb_abi_version() != 1:
             raise SacbError("libsac_b200.so ABI version mismatch")
     return _lib
@@ -88,7 +88,7 @@ class Tail(C.Structure):
                 ("teacher_logits", _vp), ("y", _vp), ("affine", _vp), ("affine_inv", _vp), ("running_conf", _vp),
                 ("training", C.c_int32), ("discount", C.c_int32),
                 ("beta", C.c_float), ("stat_momentum", C.c_float), ("conf_upper", C.c_float), ("conf_lower", C.c_float),
-                ("pooled", _vp), ("part_sums", _vp), ("peaks", _vp),
+                ("probs", _vp), ("pooled", _vp), ("part_sums", _vp), ("peaks", _vp),
                 ("conf", _vp), ("idx", _vp), ("labels", _vp), ("conf_mean", _vp), ("thresholds", _vp), ("refined", _vp)]
 
 

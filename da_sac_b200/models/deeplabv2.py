@@ -1,0 +1,198 @@
+"""DeepLabV2_ResNet101 on libsac_b200.
+
+Same constructor arguments, ``forward(im, y=None)`` contract, ``state_dict`` key layout
+(``model.conv1``, ``model.layer3.5.bn2`` ... ``model.layer5.conv2d_list.3``) and optimiser
+groups as /root/reference/models/deeplabv2.py:173-227, but the nn.Conv2d / nn.BatchNorm2d
+modules below are parameter containers only: compute runs in ``engine.ResNet101Engine``
+(tcgen05 implicit-GEMM kernels), wired into autograd by ``_BackboneFn`` so that DDP gradient
+hooks and ``torch.optim`` keep working on the real nn.Parameters."""
+import torch
+import torch.nn as nn
+
+from .basenet import BaseNet
+from .. import engine as E
+from .. import lib as L
+
+
+def _bn(c):
+    return nn.BatchNorm2d(c, eps=E.BN_EPS)
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, stride, dilation, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=stride, bias=False)
+        self.bn1 = _bn(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = _bn(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = _bn(planes * 4)
+        self.downsample = downsample
+
+
+class _Classifier(nn.Module):
+    def __init__(self, fan_in, dilations, num_classes):
+        super().__init__()
+        self.conv2d_list = nn.ModuleList(
+            [nn.Conv2d(fan_in, num_classes, 3, stride=1, padding=d, dilation=d, bias=True) for d in dilations])
+        for m in self.conv2d_list:
+            m.weight.data.normal_(0, 0.01)
+
+
+class _ResNetParams(nn.Module):
+    def __init__(self, layers, num_classes):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = _bn(64)
+        inplanes = 64
+        for li, (planes, n, stride, dil) in enumerate(((64, layers[0], 1, 1), (128, layers[1], 2, 1),
+                                                       (256, layers[2], 1, 2), (512, layers[3], 1, 4)), 1):
+            blocks = []
+            for b in range(n):
+                ds = None
+                if b == 0:
+                    ds = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False), _bn(planes * 4))
+                blocks.append(_Bottleneck(inplanes, planes, stride if b == 0 else 1, dil, ds))
+                inplanes = planes * 4
+            setattr(self, "layer%d" % li, nn.Sequential(*blocks))
+        self.layer5 = _Classifier(2048, (6, 12, 18, 24), num_classes)
+        for m in self.modules():                      # stock init of the reference (deeplabv2.py:135-141)
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.normal_(0, 0.01)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1); m.bias.data.zero_()
+
+
+class _BackboneFn(torch.autograd.Function):
+    """logits = ResNet101-DeepLabv2(x); all parameter gradients come from engine.backward"""
+
+    @staticmethod
+    def forward(ctx, net, eng, x, *params):
+        logits = torch.empty(x.shape[0], E.NUM_CLASSES, *eng.net["out_hw"], device=x.device)
+        eng.forward(net._flat, net._planes(True), x, logits, keep=True)
+        ctx.net, ctx.eng, ctx.x = net, eng, x
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net, eng = ctx.net, ctx.eng
+        eng.backward(net._flat, net._planes(True), ctx.x, dlogits.contiguous(), net._grad)
+        return (None, None, None) + tuple(net._grad.view(k) for k in net._param_keys)
+
+
+class DeepLabV2_ResNet101(BaseNet):
+    def __init__(self, num_classes=20, criterion=nn.CrossEntropyLoss(ignore_index=255, reduction="none"),
+                 pretrained=None, freeze_bn=False):
+        super().__init__()
+        assert num_classes == E.NUM_CLASSES, "libsac_b200 kernels are built for 19 classes"
+        self.model = _ResNetParams([3, 4, 23, 3], num_classes)
+        if pretrained is not None:
+            self.model.load_state_dict(torch.load(pretrained), strict=False)
+        if freeze_bn:
+            self._freeze_bn(self)
+        self._from_scratch(self.model.layer5)
+        self.criterion = criterion
+        self._flat = None
+        self._grad = None
+        self._wp = None
+        self._wp_version = -1
+        self._version = 0            # bumped whenever parameter values change
+        self._engines = {}
+
+    def lr_mult(self):
+        return 1., 10.
+
+    def lr_mult_bias(self):
+        return 2., 20.
+
+    # ---------------------------------------------------------------- flat parameter storage
+    def _named_tensors(self):
+        sd = dict(self.named_parameters())
+        sd.update(dict(self.named_buffers()))
+        return sd
+
+    def ensure_flat(self, device):
+        """(Re)home every parameter / BN statistic in one contiguous fp32 buffer (needed by the multi-tensor
+        EMA / SGD kernels and by the weight-plane preparation). Parameter objects keep their identity."""
+        tensors = self._named_tensors()
+        if self._flat is not None and self._flat.buf.device == device:
+            ok = all(tensors[k].data_ptr() == self._flat.view(k).data_ptr() for k, _, _ in self._flat.entries)
+            if ok:
+                return self._flat
+        net = E.build_resnet101(64, 64)
+        flat = E.FlatParams(net, device)
+        for k, _, _ in flat.entries:
+            v = flat.view(k)
+            v.copy_(tensors[k].detach())
+            tensors[k].data = v
+        self._flat = flat
+        self._grad = E.FlatParams(net, device)
+        self._param_keys = [k for k, _, is_p in flat.entries if is_p]
+        self._params = [tensors[k] for k in self._param_keys]
+        self._wp = None
+        self._version += 1
+        return flat
+
+    def mark_dirty(self):
+        self._version += 1
+
+    def _planes(self, with_dgrad):
+        if self._wp is None or self._wp.with_dgrad != with_dgrad:
+            self._wp = E.WeightPlanes(E.build_resnet101(64, 64), self._flat.buf.device, with_dgrad)
+            self._wp_version = -1
+        if self._wp_version != self._version:
+            self._wp.prepare(self._flat)
+            self._wp_version = self._version
+        return self._wp
+
+    def engine(self, N, H, W, shared=None):
+        key = (N, H, W)
+        cache = self._engines if shared is None else shared
+        if key not in cache:
+            cache[key] = E.ResNet101Engine(N, H, W, self._flat.buf.device)
+        return cache[key]
+
+    # ---------------------------------------------------------------- forward
+    def logits(self, im, engines=None, refresh=True):
+        """student (autograd) or teacher / inference (no-grad) forward. ``refresh`` re-derives the bf16 weight
+        planes and folded BN affine from the fp32 parameters (needed whenever an optimiser or EMA changed them)."""
+        self.ensure_flat(im.device)
+        im = im.contiguous().float()
+        eng = self.engine(im.shape[0], im.shape[2], im.shape[3], engines)
+        trainable = any(p.requires_grad for p in self._params)
+        if refresh:
+            self.mark_dirty()
+        if trainable and torch.is_grad_enabled():
+            return _BackboneFn.apply(self, eng, im, *self._params)
+        out = torch.empty(im.shape[0], E.NUM_CLASSES, *eng.net["out_hw"], device=im.device)
+        eng.forward(self._flat, self._planes(trainable), im, out, keep=False)
+        return out
+
+    def forward(self, im, y=None):
+        """(logits, logits_up) for inference, (losses, outs) with a label map (deeplabv2.py:213-227)."""
+        logits = self.logits(im)
+        H, W = im.shape[-2:]
+        up = upsample(logits.detach() if not logits.requires_grad else logits, H, W)
+        if y is None:
+            return logits, up
+        ce = self.criterion(up, y)
+        return {"loss_ce": ce.mean().view(1)}, {"logits_up": up, "logits": logits}
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        B, Cc, h, w = x.shape
+        out = torch.empty(B, Cc, H, W, device=x.device)
+        L.check(L.lib().sacb_upsample(L.ptr(x.contiguous()), L.ptr(out), B, Cc, h, w, H, W, L.stream()), "sacb_upsample")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raise L.SacbError("gradient through the materialised logits_up is not on the B200 hot path; "
+                          "use SAC.forward's fused student loss (losses['self_ce'])")
+
+
+def upsample(x, H, W):
+    """F.interpolate(x, (H, W), mode='bilinear', align_corners=True) (deeplabv2.py:217)"""
+    return _UpsampleFn.apply(x, H, W)

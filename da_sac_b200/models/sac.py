@@ -1,0 +1,218 @@
+"""SAC / SAC_Baseline on libsac_b200 -- the drop-in for /root/reference/models/sac.py.
+
+Same class names, constructor, buffers (``running_conf``, ``slow_init``), ``forward`` signature and
+``losses`` / ``net_outs`` contract (sac.py:315-378), so that ``train.py`` drives it unchanged:
+``losses[k]`` are CUDA tensors of shape [1], ``losses["self_ce"]`` carries autograd to every student
+parameter, ``y`` is mutated in place (-1 -> 255).  What differs is *how*: the teacher forward, the student
+forward/backward and the whole pseudo-label tail run as a fixed schedule of sm_100a kernels; the
+[BT,19,H,W] tensors of the reference (logits_up, teacher_refined, ...) are only materialised when a caller
+actually reads them from ``net_outs``."""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from .basenet import BaseNet
+from .. import engine as E
+from .. import lib as L
+
+
+class LazyOuts(dict):
+    """net_outs: big diagnostic tensors are produced on first access"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def lazy(self, key, fn):
+        self._lazy[key] = fn
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            v = self._lazy.pop(key)()
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def keys(self):
+        return list(dict.keys(self)) + list(self._lazy.keys())
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+
+class SAC_Baseline(BaseNet):
+    def __init__(self, cfg, backbone, rank, **kwargs):
+        super().__init__()
+        self.backbone = backbone
+        self.world_size = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = rank
+        if "criterion" in kwargs:
+            self.criterion = kwargs["criterion"]
+
+    def forward(self, x=None, y=None, x2=None, use_teacher=False, update_teacher=False):
+        return self.backbone(x, y)
+
+    def parameter_groups(self, base_lr, wd):
+        return self.backbone.parameter_groups(base_lr, wd)
+
+
+class _StudentLossFn(torch.autograd.Function):
+    """(loss_ce, self_ce) = fused upsample + log-softmax + NLL (deeplabv2.py:217-224, sac.py:134-149)"""
+
+    @staticmethod
+    def forward(ctx, sac, logits, y, tail):
+        desc, keep = sac._loss_desc(logits, y, tail, 0.0, None)
+        L.check(L.lib().sacb_student_loss_fwd(C.byref(desc), L.stream()), "sacb_student_loss_fwd")
+        ctx.sac, ctx.logits, ctx.y, ctx.tail = sac, logits, y, tail
+        return keep["losses"].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        # only self_ce is differentiated on the target step (train.py:231); loss_ce is monitoring (sac.py:340)
+        dlogits = torch.empty_like(ctx.logits)
+        desc, keep = ctx.sac._loss_desc(ctx.logits, ctx.y, ctx.tail, 1.0, dlogits)
+        L.check(L.lib().sacb_student_loss_bwd(C.byref(desc), L.stream()), "sacb_student_loss_bwd")
+        return None, dlogits * g[1], None, None
+
+
+class SAC(SAC_Baseline):
+    def __init__(self, cfg, backbone, slow_copy, rank, **kwargs):
+        super().__init__(cfg, backbone, rank, **kwargs)
+        self.cfg = cfg
+        assert cfg.CONF_POOL == "avg_pool" and cfg.LOSS == "focal_ce_conf", \
+            "libsac_b200 implements the default CONF_POOL=avg_pool / LOSS=focal_ce_conf path"
+        self.register_buffer("running_conf", torch.zeros(kwargs["num_classes"]))
+        self.slow_net = slow_copy
+        self.slow_net.eval()
+        for p in self.slow_net.parameters():
+            p.requires_grad = False
+        self.register_buffer("slow_init", torch.Tensor([False]))
+        self._engines = {}
+        self._ws = {}
+        self._seg = None
+
+    # ---------------------------------------------------------------- teacher EMA (sac.py:70-102)
+    def _segments(self, device):
+        if self._seg is None or self._seg[0].device != device:
+            f = self.backbone._flat
+            r = torch.tensor(f.ranges(), dtype=torch.int64, device=device)
+            self._seg = (r, len(f.entries), torch.zeros(len(f.entries), device=device), torch.zeros(1, device=device))
+        return self._seg
+
+    @torch.no_grad()
+    def _momentum_update(self, update=False):
+        dev = self.running_conf.device
+        fs, ft = self.backbone.ensure_flat(dev), self.slow_net.ensure_flat(dev)
+        if not self.slow_init[0]:
+            self.running_conf.fill_(self.cfg.THRESHOLD_BETA)
+            self.slow_init[0] = True
+            ft.buf.copy_(fs.buf)                        # slow_net.load_state_dict(backbone.state_dict())
+            self.slow_net.mark_dirty()
+            return torch.zeros(1, device=dev)
+        ranges, nseg, seg_sq, out = self._segments(dev)
+        L.check(L.lib().sacb_ema_norm(L.ptr(ft.buf), L.ptr(fs.buf), L.ptr(ranges), nseg, C.c_float(self.cfg.NET_MOMENTUM),
+                                      1 if update else 0, L.ptr(seg_sq), L.ptr(out), L.stream()), "sacb_ema_norm")
+        if update:
+            self.slow_net.mark_dirty()
+        return out.clone()
+
+    # ---------------------------------------------------------------- tail
+    def _workspace(self, BT, T, H, W, dev):
+        key = (BT, T, H, W)
+        if key not in self._ws:
+            lib = L.lib()
+            Cn = E.NUM_CLASSES
+            f32 = dict(device=dev, dtype=torch.float32)
+            self._ws[key] = dict(
+                probs=torch.empty(lib.sacb_tail_probs_elems(BT, Cn, H, W), **f32),
+                pooled=torch.empty(lib.sacb_tail_pooled_elems(BT // T, Cn, H, W), **f32),
+                part_sums=torch.empty(lib.sacb_tail_part_sums_elems(BT, Cn, H, W), **f32),
+                peaks=torch.empty(BT * Cn, **f32), thresholds=torch.empty(BT, Cn, **f32),
+                conf=torch.empty(BT, 1, H, W, **f32), idx=torch.empty(BT, 1, H, W, device=dev, dtype=torch.uint8),
+                labels=torch.empty(BT, H, W, device=dev, dtype=torch.uint8), conf_mean=torch.empty(H, W, **f32),
+                losses=torch.empty(2, **f32), scratch=torch.empty(2, device=dev, dtype=torch.float64))
+        return self._ws[key]
+
+    def _tail(self, teacher_logits, y_raw, affine, affine_inv, T, refined=None):
+        BT, Cn, h, w = teacher_logits.shape
+        H, W = y_raw.shape[-2:]
+        ws = self._workspace(BT, T, H, W, teacher_logits.device)
+        cfg = self.cfg
+        d = L.Tail(C.sizeof(L.Tail), BT, T, Cn, h, w, H, W, L.ptr(teacher_logits), L.ptr(y_raw),
+                   L.ptr(affine.contiguous().float()), L.ptr(affine_inv.contiguous().float()), L.ptr(self.running_conf),
+                   1 if self.training else 0, 1 if cfg.CONF_DISCOUNT else 0,
+                   cfg.THRESHOLD_BETA, cfg.STAT_MOMENTUM, cfg.RUN_CONF_UPPER, cfg.RUN_CONF_LOWER,
+                   L.ptr(ws["probs"]), L.ptr(ws["pooled"]), L.ptr(ws["part_sums"]), L.ptr(ws["peaks"]),
+                   L.ptr(ws["conf"]), L.ptr(ws["idx"]), L.ptr(ws["labels"]), L.ptr(ws["conf_mean"]),
+                   L.ptr(ws["thresholds"]), L.ptr(refined))
+        L.check(L.lib().sacb_teacher_tail(C.byref(d), L.stream()), "sacb_teacher_tail")
+        return ws
+
+    def _loss_desc(self, logits, y, tail, grad_scale, dlogits):
+        BT, Cn, h, w = logits.shape
+        H, W = y.shape[-2:]
+        keep = tail
+        d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), L.ptr(tail["labels"]),
+                   L.ptr(tail["conf_mean"]), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
+                   L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits))
+        return d, keep
+
+    # ---------------------------------------------------------------- forward (sac.py:315-378)
+    def forward(self, x, y=None, x2=None, affine=None, affine_inv=None,
+                use_teacher=False, update_teacher=False, reset_teacher=False, T=None, teacher=False):
+        dev = x.device
+        self.backbone.ensure_flat(dev); self.slow_net.ensure_flat(dev)
+        if y is None:                                                    # inference-only mode (sac.py:324-329)
+            net = self.slow_net if teacher else self.backbone
+            with torch.no_grad():
+                logits = net.logits(x, self._engines, refresh=True)
+            from .deeplabv2 import upsample
+            return logits, upsample(logits, *x.shape[-2:])
+        if reset_teacher:
+            self.slow_init[0] = False
+        y_raw = y.clone()                                                # keeps the -1 padding marker for the kernels
+        y[y == -1] = 255                                                 # in-place on the caller's tensor (sac.py:337-338)
+        losses = {}
+        H, W = x.shape[-2:]
+        if update_teacher:
+            losses["teacher_diff"] = self._momentum_update(True)         # sac.py:342-344
+        tail = None
+        if use_teacher:
+            self.slow_net.eval()
+            with torch.no_grad():                                        # sac.py:348-350
+                t_logits = self.slow_net.logits(x2, self._engines, refresh=False)
+            tail = self._tail(t_logits, y_raw, affine, affine_inv, T)   # sac.py:353-357
+        s_logits = self.backbone.logits(x, self._engines, refresh=True)  # sac.py:340
+        if tail is None:
+            BT = x.shape[0]
+            tail = self._workspace(BT, 1, H, W, dev)
+            tail["labels"].fill_(255); tail["conf_mean"].zero_()
+        both = _StudentLossFn.apply(self, s_logits, y_raw, tail)
+        losses["loss_ce"] = both[0:1]
+        outs = LazyOuts(logits=s_logits)
+        from .deeplabv2 import upsample
+        outs.lazy("logits_up", lambda: upsample(s_logits.detach(), H, W))
+        if use_teacher:
+            losses["self_ce"] = both[1:2]                                # sac.py:360-361
+            outs["teacher_conf"] = tail["conf"]
+            outs["running_conf"] = self.running_conf
+            outs.lazy("teacher_labels", lambda: tail["labels"].long())
+            outs.lazy("teacher_init", lambda: upsample(t_logits, H, W))
+
+            def _refined():
+                r = torch.empty(x.shape[0], E.NUM_CLASSES, H, W, device=dev)
+                saved = self.running_conf.clone(); was = self.training
+                self.training = False                                     # do not update running_conf twice
+                self._tail(t_logits, y_raw, affine, affine_inv, T, refined=r)
+                self.training = was; self.running_conf.copy_(saved)
+                return r
+            outs.lazy("teacher_refined", _refined)
+            losses["teacher_diff"] = self._momentum_update(False)        # sac.py:374
+        return losses, outs
+
+    def parameter_groups(self, base_lr, wd):
+        return self.backbone.parameter_groups(base_lr, wd)

@@ -110,9 +110,9 @@ int sacb_scatter2_mask_split(const float* a, const float* b, const void* mask_hi
                              int N, int H, int W, int C, int P, int Q, void* stream);
 /* colsum[c] = sum_m (hi[m,c] + lo[m,c])  (BN d(beta), conv d(bias)); fp32 atomics into zeroed colsum */
 int sacb_colsum(const void* hi, const void* lo, float* colsum, int64_t M, int C, void* stream);
-/* weight preparation (per step): OIHW fp32 -> fprop planes [R*S][Kpad][C] and, if wt_* != NULL,
- * dgrad planes [R*S][Cpad? no: C][K] flipped+transposed and scaled by scale[k] (NULL = 1) */
-int sacb_prep_weight(const float* w_oihw, const float* scale, int K, int C, int R, int S, int Kpad,
+/* weight preparation (per optimiser step): OIHW fp32 -> fprop planes wf[R*S][Kf][C] (rows >= K zero) and,
+ * if wt_* != NULL, dgrad planes wt[R*S][C][Kt] = w[k][c][R-1-r][S-1-s] * scale[k] (scale NULL = 1; k >= K zero) */
+int sacb_prep_weight(const float* w_oihw, const float* scale, int K, int C, int R, int S, int Kf, int Kt,
                      void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, void* stream);
 /* BN fold (basenet.py:97-100 eval-mode statistics, trainable affine):
  * scale = gamma * rsqrt(var + eps), shift = beta - mean * scale */
@@ -138,9 +138,10 @@ typedef struct SacbTail {
   float* running_conf;           /* [C] in/out (updated if training) */
   int32_t training, discount;
   float beta, stat_momentum, conf_upper, conf_lower;
-  /* workspace */
-  float* pooled;                 /* [BT/T,H,W,C+1] fp32: averaged probs + valid mask */
-  float* part_sums;              /* [nblocks(BT*H*W/256), C] partial class sums; sized by sacb_tail_workspace */
+  /* workspace (element counts from sacb_tail_*_elems) */
+  float* probs;                  /* [BT,H*W,CP] masked teacher probabilities, pixel-major */
+  float* pooled;                 /* [BT/T,H*W,CP2] averaged probs (0..C-1) + valid mask (C) */
+  float* part_sums;              /* [BT*ceil(H*W/256), C] partial class sums */
   float* peaks;                  /* [BT,C] */
   /* outputs */
   float* conf;                   /* [BT,H,W] */
@@ -152,6 +153,8 @@ typedef struct SacbTail {
 } SacbTail;
 int sacb_teacher_tail(const SacbTail* d, void* stream);
 size_t sacb_tail_part_sums_elems(int BT, int C, int H, int W);
+size_t sacb_tail_probs_elems(int BT, int C, int H, int W);
+size_t sacb_tail_pooled_elems(int G, int C, int H, int W);
 
 /* student loss (deeplabv2.py:217-224 + sac.py:134-149): fused upsample + log-softmax + weighted NLL */
 typedef struct SacbLoss {
@@ -175,12 +178,12 @@ int sacb_student_loss_bwd(const SacbLoss* d, void* stream);
 int sacb_upsample(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------- optimiser-side multi-tensor kernels
- * flat fp32 buffers with a segment table (one segment per tensor). */
+ * flat fp32 buffers with a segment table: seg_ranges[2*i], seg_ranges[2*i+1] = [begin, end) of tensor i. */
 /* SAC._momentum_update (sac.py:83-102): out[0] = sum_seg ||slow-fast||_2 ; if update: slow = m*slow+(1-m)*fast */
-int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_offsets, int nseg, float momentum,
+int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_ranges, int nseg, float momentum,
                   int update, float* seg_sq, float* out, void* stream);
 /* torch.optim.SGD step (base_trainer.py:61-66): per-segment lr / weight decay, momentum buffer in place */
-int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_offsets, const float* seg_lr,
+int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_ranges, const float* seg_lr,
              const float* seg_wd, int nseg, float momentum, int first_step, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,148 @@
+"""GPU parity of the full SAC target step (through da_sac_b200.models -> C ABI) against the CPU oracle and
+the golden vectors of the real reference.  Bars (BASELINE.json north_star): logits within 1e-3 relative
+(max-norm and rel-L2), pseudo-label masks bit-exact given identical teacher logits."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_GROUPS, K, HW = 2, 2, (128, 128)
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu(); b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item(), ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def planes_to_nchw(pl, N, H, W, Cc):
+    return (pl.hi.float() + pl.lo.float()).view(N, H, W, Cc).permute(0, 3, 1, 2)
+
+
+@pytest.fixture(scope="module")
+def net():
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    cfg = synth.ModelCfg()
+    m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    m.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    m.cuda()
+    m.train()
+    return m, cfg
+
+
+def test_backbone_forward_matches_oracle(net):
+    from da_sac_b200 import synth
+    from oracle import sac_oracle as O
+    m, cfg = net
+    x = synth.make_target_batch(N_GROUPS, K, HW, seed=0)[0]
+    sd = synth.make_backbone_params(seed=123)
+    taps = {}
+    with torch.no_grad():
+        ref = O.resnet101_logits(sd, x, taps)
+    bb = m.backbone
+    bb.ensure_flat(torch.device("cuda"))
+    eng = bb.engine(x.shape[0], HW[0], HW[1])
+    out = torch.empty(x.shape[0], 19, *eng.net["out_hw"], device="cuda")
+    eng.forward(bb._flat, bb._planes(True), x.cuda(), out, keep=True)
+    torch.cuda.synchronize()
+    st = eng.net["stem"]
+    e_stem = rel(planes_to_nchw(eng.act["stem"], x.shape[0], st.hout, st.wout, 64), taps["stem"])
+    ph, pw = eng.net["pool_hw"]
+    e_pool = rel(planes_to_nchw(eng.act["pool"], x.shape[0], ph, pw, 64), taps["pool"])
+    errs = {"stem": e_stem, "pool": e_pool}
+    for li, last in ((1, "model.layer1.2.conv3"), (2, "model.layer2.3.conv3"), (3, "model.layer3.22.conv3"), (4, "model.layer4.2.conv3")):
+        s = eng.net["specs"][last]
+        errs["layer%d" % li] = rel(planes_to_nchw(eng.act[last], x.shape[0], s.hout, s.wout, s.K), taps["layer%d" % li])
+    errs["logits"] = rel(out, ref)
+    print(errs)
+    for k, (l2, mx) in errs.items():
+        assert l2 < 1e-3 and mx < 1e-3, (k, l2, mx, errs)
+    assert errs["logits"][1] < 2e-4      # bf16x3 should sit far inside the 1e-3 bar
+
+
+def test_tail_labels_bit_exact_on_golden_teacher_logits(net, golden):
+    """identical teacher logits in -> identical pseudo-label masks out (outside the audited-ambiguous pixels)"""
+    from da_sac_b200 import synth
+    m, cfg = net
+    _, y, _, A, Ai = synth.make_target_batch(N_GROUPS, K, HW, seed=0)
+    for step in (0, 1):
+        pre = "s%d_" % step
+        tl = torch.from_numpy(golden[pre + "teacher_logits"]).cuda()
+        # running_conf before this step's update: beta at step 0, golden s0 value at step 1
+        rc0 = torch.full((19,), cfg.THRESHOLD_BETA) if step == 0 else torch.from_numpy(golden["s0_running_conf"])
+        m.running_conf.copy_(rc0.cuda())
+        m.train()
+        ws = m._tail(tl, y.cuda(), A.cuda(), Ai.cuda(), K)
+        torch.cuda.synchronize()
+        assert rel(m.running_conf, golden[pre + "running_conf"])[1] < 1e-5
+        lab = ws["labels"].cpu()
+        glab = torch.from_numpy(golden[pre + "teacher_labels"])
+        conf = ws["conf"].cpu()
+        gconf = torch.from_numpy(golden[pre + "teacher_conf"])
+        assert (conf - gconf).abs().max() < 2e-5, (conf - gconf).abs().max()
+        amb = torch.from_numpy(golden[pre + "ambiguous"])
+        mism = (lab != glab)
+        print("step", step, "label mismatches", int(mism.sum()), "of which ambiguous", int((mism & amb).sum()))
+        assert int((mism & ~amb).sum()) == 0
+        assert int(mism.sum()) <= int(amb.sum())
+        # size-independent self-consistency: labels are an integer function of (conf, idx, thresholds, y)
+        thr = ws["thresholds"].cpu()
+        idx = ws["idx"].cpu().long().squeeze(1)
+        exp = torch.where(conf.squeeze(1) > thr.gather(1, idx.view(idx.shape[0], -1)).view_as(idx), idx, torch.full_like(idx, 255))
+        exp[y == -1] = 255
+        assert torch.equal(exp.to(torch.uint8), lab)
+
+
+def test_two_training_steps_match_reference_golden(net, golden):
+    from da_sac_b200 import synth
+    m, cfg = net
+    m.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    m.slow_init[0] = False
+    m.running_conf.zero_()
+    m.train()
+    groups = m.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY)
+    optim = torch.optim.SGD(groups, momentum=cfg.MOMENTUM)
+    batch = synth.make_target_batch(N_GROUPS, K, HW, seed=0)
+    names = [str(n) for n in golden["grad_names"]]
+    params = dict(m.backbone.named_parameters())
+    for step in (0, 1):
+        x, y, x2, A, Ai = [t.clone().cuda() for t in batch]
+        losses, outs = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=(step == 0), T=K)
+        optim.zero_grad()
+        (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+        torch.cuda.synchronize()
+        pre = "s%d_" % step
+        assert (y.cpu() == torch.from_numpy(golden[pre + "mask_gt"]).long()).all()       # in-place -1 -> 255
+        l2, mx = rel(outs["logits"].detach(), golden[pre + "logits"])
+        print("step", step, "student logits rel-L2 %.2e max %.2e" % (l2, mx))
+        assert l2 < 1e-3 and mx < 1e-3
+        assert rel(outs["running_conf"], golden[pre + "running_conf"])[1] < 1e-4
+        lab = outs["teacher_labels"].cpu().to(torch.uint8)
+        glab = torch.from_numpy(golden[pre + "teacher_labels"])
+        agree = (lab == glab).float().mean().item()
+        print("step", step, "pseudo-label agreement end-to-end %.6f" % agree)
+        assert agree > 0.999
+        assert rel(outs["teacher_conf"], golden[pre + "teacher_conf"])[1] < 1e-3
+        assert rel(outs["teacher_refined"][:, :, ::4, ::4], golden[pre + "teacher_refined_sub"])[1] < 1e-3
+        for k in ("self_ce", "loss_ce", "teacher_diff"):
+            g = float(golden[pre + k].reshape(-1)[0]); v = float(losses[k].detach().reshape(-1)[0])
+            print(k, v, g)
+            assert abs(v - g) <= 2e-3 * max(abs(g), 1e-3), (k, v, g)
+        gn = golden[pre + "grad_norms"]
+        mine = np.array([params[n].grad.double().norm().item() for n in names])
+        relerr = np.abs(mine - gn) / np.maximum(gn, 1e-12)
+        print("step", step, "grad-norm max rel err %.2e (%s)" % (relerr.max(), names[int(relerr.argmax())]))
+        assert relerr.max() < 1e-2
+        for key in golden.files:
+            if key.startswith(pre + "grad::"):
+                n = key.split("::")[1]
+                g = params[n].grad
+                g = g.flatten()[:60000] if g.numel() > 60000 else g
+                e = rel(g.reshape(golden[key].shape), golden[key])[0]
+                print("   grad", n, "rel-L2 %.2e" % e)
+                assert e < 1e-2, key
+        if step == 0:
+            optim.step()
+            v = m.backbone.model.layer3[5].conv2.weight.detach().flatten()[:60000]
+            assert rel(v, golden["s0_post_step::model.layer3.5.conv2.weight"])[1] < 1e-5
