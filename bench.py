@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""Benchmark of the SAC target training step (BASELINE.json metric: target-crops/sec, 512x512, K=3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one ``Trainer._step_target(train=True)`` with TARGET_ONLY semantics
+(/root/reference/train.py:211-250) on ``configs[1]`` of BASELINE.json: ResNet-101 DeepLabv2,
+8 view-groups x K=3 crops of 512x512 per GPU (weak scaling: every rank gets its own 8 groups).
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the oracle port of the reference's own
+CPU path on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TFLOP_PER_CROP = 1.506          # 4 x 376.52 GFLOP (teacher fwd + student fwd + dgrad + wgrad)
+NUM_GROUPS, GROUP_SIZE, CROP = 8, 3, (512, 512)
+METRIC = "target-crops/sec (512x512, K=3)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock / throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, n): n for n in dir(nv) if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason")}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and "None" not in n and "All" not in n:
+                        self.reasons.add(n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+                time.sleep(0.1)
+        except Exception as e:      # clocks are evidence, not a dependency of the measurement
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def run_reference(args, rank):
+    """the reference's own CPU implementation of the path: oracle port (torch CPU fp32, all host threads)"""
+    if rank != 0:
+        return
+    import torch
+    from da_sac_b200 import synth
+    from oracle import sac_oracle as O
+    cores = min(os.cpu_count() or 1, 32)         # oneDNN convs on 65x65 maps stop scaling past ~32 threads
+    torch.set_num_threads(cores)
+    cfg = synth.ModelCfg()
+    sd = synth.make_backbone_params(seed=123)
+    student = O.as_leaf_params(sd)
+    teacher = {k: v.detach().clone() for k, v in student.items()}
+    optim = torch.optim.SGD(O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    rc = torch.full((19,), cfg.THRESHOLD_BETA)
+    groups = 1                                   # bounded sample: 1 group x K=3 crops of 512x512 per step
+    batch = synth.make_target_batch(groups, GROUP_SIZE, CROP, seed=0)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, _, rc = O.sac_target_step(student, teacher, rc, batch, GROUP_SIZE, cfg, optim=optim)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    crops = groups * GROUP_SIZE * len(times)
+    v = crops / total
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ResNet-101 DeepLabv2 SAC target step, %d group x K=%d crops %dx%d per step (bounded CPU sample of configs[1])" % (groups, GROUP_SIZE, CROP[0], CROP[1])},
+            "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps of 1 group x K=3 crops 512x512 (oracle/sac_oracle.py, torch CPU fp32)" % len(times)},
+            "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--groups", type=int, default=NUM_GROUPS, help="view-groups per GPU (default: configs[1])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        if args.steps > 3: args.steps = 3
+        if args.warmup > 1: args.warmup = 1
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from da_sac_b200 import lib as L, synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import TargetStepper
+
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()        # fail loudly if the CUDA extension is missing
+
+    cfg = synth.ModelCfg()
+    net = get_model(cfg, rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    net.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    net.to(dev).train()
+    stepper = TargetStepper(net, cfg, GROUP_SIZE, dev)
+    host = stepper.stage_host(synth.make_target_batch(args.groups, GROUP_SIZE, CROP, seed=rank))
+    dev_batch = stepper.h2d(host)
+    crops_per_step = args.groups * GROUP_SIZE * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, e2e):
+        for _ in range(n):
+            if e2e:
+                b = stepper.h2d(host)                              # pinned host -> device every step
+                stepper.step(b, read_losses=True)                  # + loss scalars device -> host
+            else:
+                b = tuple(t.clone() if i == 1 else t for i, t in enumerate(dev_batch))   # y is mutated in place
+                stepper.step(b, read_losses=False)
+
+    def timed(n, e2e):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(n, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)              # max over ranks
+        return float(ms)
+
+    run(args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = L.launch_count()
+    ms = timed(args.steps, False)
+    launches = L.launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    run(1, True)
+    ms_e2e = timed(args.steps, True)
+
+    value = crops_per_step * args.steps / (ms / 1e3)
+    e2e = crops_per_step * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    pk = peaks()
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream (one extra step)
+    L.profile_begin()
+    run(1, False)
+    prof = L.profile_end()
+    by = {}
+    for kind, flops, t in prof:
+        a = by.setdefault(kind, [0.0, 0.0, 0]); a[0] += flops; a[1] += t; a[2] += 1
+    dom = max(by, key=lambda k: by[k][1])
+    achieved = by[dom][0] / (by[dom][1] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["sustained"], "traffic": None, "launches": by[dom][2],
+                "share_of_step": by[dom][1] / (ms / args.steps),
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3 split), so frac <= 1/3 by construction" % pk["src"],
+                "step_tensor_frac": value / world * TFLOP_PER_CROP / pk["sustained"],
+                "kernels": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]} for k, v in by.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (bf16 hi/lo split operands, fp32 TMEM accumulation; fp32-equivalent)", "data": "synthetic",
+            "config": {"workload": "ResNet-101 DeepLabv2 SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % (args.groups, GROUP_SIZE, CROP[0], CROP[1]),
+                       "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world,
+                       "l2": "inputs larger than L2 (>20 GB of activations per step)"},
+            "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import sac_oracle as O
+        cores = min(os.cpu_count() or 1, 32)
+        torch.set_num_threads(cores)
+        sd = synth.make_backbone_params(seed=123)
+        student = O.as_leaf_params(sd)
+        teacher = {k: v.detach().clone() for k, v in student.items()}
+        rc = torch.full((19,), cfg.THRESHOLD_BETA)
+        cb = synth.make_target_batch(1, GROUP_SIZE, CROP, seed=0)
+        t0 = time.perf_counter()
+        O.sac_target_step(student, teacher, rc, cb, GROUP_SIZE, cfg, optim=None)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": GROUP_SIZE / dt, "unit": "crops/s", "cores": cores, "kind": "port",
+                                "sample": "1 step of 1 group x K=3 crops 512x512 (oracle/sac_oracle.py, torch CPU fp32, no warm-up)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

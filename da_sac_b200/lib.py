@@ -102,6 +102,33 @@ class Loss(C.Structure):
                 ("dlogits", _vp)]
 
 
+# optional per-launch CUDA-event profiling of the GEMM kernels (used by bench.py's roofline leg only)
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    return [(kind, flops, e0.elapsed_time(e1)) for (kind, flops, e0, e1) in rec]
+
+
+def _prof_wrap(kind, flops, fn):
+    if _prof is None:
+        return fn()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    _prof.append((kind, flops, e0, e1))
+    return r
+
+
 def conv_out_hw(H, W, R, stride, dil, pad):
     return ((H + 2 * pad - (R - 1) * dil - 1) // stride + 1, (W + 2 * pad - (R - 1) * dil - 1) // stride + 1)
 
@@ -114,7 +141,9 @@ def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift
     desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                     ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
                     ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw))
-    check(lib().sacb_conv_gemm(C.byref(desc), stream()), "sacb_conv_gemm")
+    kind = "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))
+    flops = 2.0 * N * P * Q * (K if k_valid is None else k_valid) * Cc * R * R
+    _prof_wrap(kind, flops, lambda: check(lib().sacb_conv_gemm(C.byref(desc), stream()), "sacb_conv_gemm"))
 
 
 def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
@@ -122,4 +151,5 @@ def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
     P, Q = conv_out_hw(H, W, R, s, d, p)
     desc = ConvWgrad(C.sizeof(ConvWgrad), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                      ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), ptr(dw), splits)
-    check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad")
+    flops = 2.0 * N * P * Q * (K if k_valid is None else k_valid) * Cc * R * R
+    _prof_wrap("conv_wgrad", flops, lambda: check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad"))

@@ -1,0 +1,133 @@
+"""Target-step driver: the B200-side mirror of ``Trainer._step_target`` / ``_prep_batch``
+(/root/reference/train.py:157-250) with TRAIN.TARGET_ONLY semantics.
+
+``TargetStepper.step(batch_target, update_teacher)``:
+    H2D (optional, pinned) -> SAC.forward (teacher fwd, tail, student fwd, fused loss)
+    -> zero_grad -> (LR_TARGET * self_ce).backward() -> gradient all-reduce (mean over ranks, NCCL)
+    -> SGD (one multi-tensor kernel over the flat parameter buffer) -> loss scalars.
+
+Data parallelism follows the reference: whole view-groups are partitioned across ranks
+(``shard_groups``), every rank holds a full replica, the only exchange is the gradient all-reduce."""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+
+def shard_groups(num_groups, world_size, rank):
+    """indices of the view-groups rank ``rank`` owns (datasets/__init__.py:64: NUM_GROUPS // ngpus per GPU)"""
+    if num_groups % world_size != 0:
+        raise ValueError("NUM_GROUPS=%d does not split over %d ranks" % (num_groups, world_size))
+    per = num_groups // world_size
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def shard_batch(batch, group_size, world_size, rank):
+    """slice a flattened [G*T, ...] target batch to this rank's groups (train.py:186-187 early-out path)"""
+    G = batch[0].shape[0] // group_size
+    idx = shard_groups(G, world_size, rank)
+    lo, hi = idx[0] * group_size, (idx[-1] + 1) * group_size
+    return tuple(t[lo:hi] for t in batch)
+
+
+def allreduce_mean_(buf):
+    """DDP semantics for gradients: sum over ranks, divide by world size (train.py:104). In place."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf)
+        buf.div_(dist.get_world_size())
+    return buf
+
+
+class FusedSGD(object):
+    """torch.optim.SGD(momentum, weight_decay per group) semantics (base_trainer.py:61-66) as ONE kernel over
+    the backbone's flat parameter / gradient buffers. ``param_groups`` come from ``net.parameter_groups``."""
+
+    def __init__(self, backbone, param_groups, momentum=0.9):
+        self.backbone, self.momentum = backbone, momentum
+        self.param_groups = param_groups
+        self._built = None
+        self.steps = 0
+
+    def _build(self):
+        bb = self.backbone
+        flat = bb._flat
+        by_id = {}
+        for g in self.param_groups:
+            for p in g["params"]:
+                by_id[id(p)] = (g["lr"], g["weight_decay"])
+        tensors = dict(bb.named_parameters())
+        ranges, lr, wd = [], [], []
+        for key, _, is_p in flat.entries:
+            if not is_p: continue
+            p = tensors[key]
+            if id(p) not in by_id: continue
+            o, n, _, _ = flat.offs[key]
+            ranges += [o, o + n]; lr.append(by_id[id(p)][0]); wd.append(by_id[id(p)][1])
+        dev = flat.buf.device
+        self._built = dict(flat=flat, ranges=torch.tensor(ranges, dtype=torch.int64, device=dev),
+                           lr=torch.tensor(lr, dtype=torch.float32, device=dev),
+                           wd=torch.tensor(wd, dtype=torch.float32, device=dev), n=len(lr),
+                           mom=torch.zeros_like(flat.buf))
+
+    def set_lr(self, param_groups):
+        self.param_groups = param_groups
+        self._built = None
+
+    def zero_grad(self):
+        for g in self.param_groups:
+            for p in g["params"]:
+                p.grad = None
+
+    def step(self):
+        bb = self.backbone
+        if self._built is None or self._built["flat"] is not bb._flat:
+            mom = self._built["mom"] if self._built is not None and self._built["flat"] is bb._flat else None
+            self._build()
+            if mom is not None: self._built["mom"] = mom
+        b = self._built
+        L.check(L.lib().sacb_sgd(L.ptr(b["flat"].buf), L.ptr(bb._grad.buf), L.ptr(b["mom"]), L.ptr(b["ranges"]),
+                                 L.ptr(b["lr"]), L.ptr(b["wd"]), b["n"], C.c_float(self.momentum),
+                                 1 if self.steps == 0 else 0, L.stream()), "sacb_sgd")
+        self.steps += 1
+        bb.mark_dirty()
+
+
+class TargetStepper(object):
+    def __init__(self, net, cfg_model, group_size, device, lr=None, weight_decay=None):
+        self.net, self.cfg, self.T, self.device = net, cfg_model, group_size, device
+        net.backbone.ensure_flat(device); net.slow_net.ensure_flat(device)
+        groups = net.parameter_groups(cfg_model.LR if lr is None else lr,
+                                      cfg_model.WEIGHT_DECAY if weight_decay is None else weight_decay)
+        self.optim = FusedSGD(net.backbone, groups, cfg_model.MOMENTUM)
+        self.iter = 0
+        self._pinned = None
+        self._host_losses = None
+
+    def stage_host(self, batch):
+        """pinned host copies of a batch (what a DataLoader with pin_memory hands to train.py:183)"""
+        self._pinned = tuple(t.contiguous().pin_memory() for t in batch)
+        return self._pinned
+
+    def h2d(self, host_batch):
+        return tuple(t.to(self.device, non_blocking=True) for t in host_batch)
+
+    def step(self, batch, update_teacher=None, read_losses=False):
+        """one Trainer._step_target(train=True) on device-resident tensors; returns losses (tensors or floats)"""
+        if update_teacher is None:
+            update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)          # train.py:294
+        x, y, x2, A, Ai = batch
+        losses, outs = self.net(x, y, x2, A, Ai, use_teacher=True, update_teacher=update_teacher, T=self.T)
+        self.optim.zero_grad()                                                      # TARGET_ONLY (train.py:227-228)
+        (self.cfg.LR_TARGET * losses["self_ce"].mean()).backward()                  # train.py:231-232
+        allreduce_mean_(self.net.backbone._grad.buf)
+        self.optim.step()                                                           # train.py:233
+        self.iter += 1
+        if read_losses:
+            v = torch.cat([losses["loss_ce"].detach(), losses["self_ce"].detach(), losses["teacher_diff"].detach()])
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(v); v /= dist.get_world_size()                      # train.py:243-245
+            host = v.cpu()                                                          # .item() host sync (train.py:246)
+            return {"loss_ce": float(host[0]), "self_ce": float(host[1]), "teacher_diff": float(host[2])}
+        return losses
