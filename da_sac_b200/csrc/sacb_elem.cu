@@ -316,26 +316,56 @@ __global__ void scatter2_mask_split_kernel(const float* __restrict__ a, const fl
   }
 }
 
-// column sums of a split-plane matrix [M, C]: thread = 8 channels x 64 rows, atomics into colsum
-__global__ void colsum_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
-                              float* __restrict__ colsum, long long M, int C) {
-  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
-  if (cv >= C / 8) return;
-  const long long r0 = (long long)blockIdx.y * 64;
-  const long long r1 = r0 + 64 < M ? r0 + 64 : M;
+// column sums of a split-plane matrix [M, C]: block = (TX channel-vectors of 8) x (TY row lanes); each block
+// sweeps COLSUM_ROWS rows with TY rows in flight, reduces over TY in shared memory, then one atomic per channel.
+constexpr int COLSUM_ROWS = 512;
+__global__ void __launch_bounds__(256)
+colsum_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ colsum,
+              long long M, int C) {
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int cv = blockIdx.x * TX + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * COLSUM_ROWS;
+  const long long r1 = r0 + COLSUM_ROWS < M ? r0 + COLSUM_ROWS : M;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    const size_t o = ((size_t)r * C) / 8 + cv;
-    float fh[8], fl[8];
-    unpack8f(reinterpret_cast<const uint4*>(hi)[o], fh);
-    unpack8f(reinterpret_cast<const uint4*>(lo)[o], fl);
+  if (cv < C / 8) {
+    const uint4* ph = reinterpret_cast<const uint4*>(hi) + cv;
+    const uint4* pl = reinterpret_cast<const uint4*>(lo) + cv;
+    const size_t stride = (size_t)C / 8;
+    long long r = r0 + threadIdx.y;
+    for (; r + 3 * TY < r1; r += 4 * TY) {
+      uint4 h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += fh[j] + fl[j];
+      for (int u = 0; u < 4; ++u) { h[u] = __ldg(ph + (size_t)(r + u * TY) * stride); l[u] = __ldg(pl + (size_t)(r + u * TY) * stride); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float fh[8], fl[8];
+        unpack8f(h[u], fh); unpack8f(l[u], fl);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += fh[j] + fl[j];
+      }
+    }
+    for (; r < r1; r += TY) {
+      float fh[8], fl[8];
+      unpack8f(__ldg(ph + (size_t)r * stride), fh); unpack8f(__ldg(pl + (size_t)r * stride), fl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += fh[j] + fl[j];
+    }
   }
+  __shared__ float red[256][9];
+  const int t = threadIdx.y * TX + threadIdx.x;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&colsum[cv * 8 + j], acc[j]);
+  for (int j = 0; j < 8; ++j) red[t][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && cv < C / 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int y = 0; y < TY; ++y) s += red[y * TX + threadIdx.x][j];
+      atomicAdd(&colsum[cv * 8 + j], s);
+    }
+  }
 }
 
 // weight re-layout (per optimiser step):  OIHW fp32 -> fprop planes [RS][Kf][C] and dgrad planes [RS][C][Kt]
@@ -387,14 +417,15 @@ __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ dwraw, const float* __restrict__ w, const float* __restrict__ scale,
                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
                       const float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dgamma, int K,
-                      int C, int RS) {
+                      int C, int RS, int splits) {
   const int k = blockIdx.x;
   const float sc = scale ? scale[k] : 1.f;
   float dot = 0.f;
   const size_t base = (size_t)k * RS * C;
   for (int i = threadIdx.x; i < RS * C; i += blockDim.x) {
     const int rs = i / C, c = i - rs * C;
-    const float g = dwraw[base + i];                 // [k][rs][c]
+    float g = 0.f;                                   // [split][k][rs][c], summed in split order (deterministic)
+    for (int sp = 0; sp < splits; ++sp) g += dwraw[(size_t)sp * K * RS * C + base + i];
     const size_t o = base + (size_t)c * RS + rs;     // [k][c][rs]
     dot = fmaf(w[o], g, dot);
     dw[o] = sc * g;
@@ -483,9 +514,11 @@ extern "C" int sacb_scatter2_mask_split(const float* a, const float* b, const vo
 
 extern "C" int sacb_colsum(const void* hi, const void* lo, float* colsum, int64_t M, int C, void* stream) {
   SACB_REQUIRE(C % 8 == 0, "sacb_colsum: C %% 8");
-  const int threads = 64;
-  dim3 grid((C / 8 + threads - 1) / threads, (unsigned)((M + 63) / 64));
-  colsum_kernel<<<grid, threads, 0, ST>>>((const uint16_t*)hi, (const uint16_t*)lo, colsum, (long long)M, C);
+  const int cvs = C / 8;
+  const int tx = cvs >= 32 ? 32 : (cvs >= 16 ? 16 : 8);
+  dim3 block(tx, 256 / tx);
+  dim3 grid((cvs + tx - 1) / tx, (unsigned)((M + COLSUM_ROWS - 1) / COLSUM_ROWS));
+  colsum_kernel<<<grid, block, 0, ST>>>((const uint16_t*)hi, (const uint16_t*)lo, colsum, (long long)M, C);
   LAUNCHED();
   return 0;
 }
@@ -509,8 +542,8 @@ extern "C" int sacb_bn_fold(const float* gamma, const float* beta, const float* 
 
 extern "C" int sacb_wgrad_finalize(const float* dwraw, const float* w, const float* scale, const float* mean,
                                    const float* var, float eps, const float* dbeta, float* dw, float* dgamma, int K,
-                                   int C, int R, int S, void* stream) {
-  wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, K, C, R * S);
+                                   int C, int R, int S, int splits, void* stream) {
+  wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, K, C, R * S, splits);
   LAUNCHED();
   return 0;
 }

@@ -22,7 +22,9 @@ extern std::atomic<long long> g_launches;
 
 constexpr int BM = 128;          // UMMA M (TMEM lanes)
 constexpr int BK = 64;           // K elements per stage = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                       // two epilogue warps per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MAX_AFFINE = 2048;                   // scale/shift staged in shared memory (floats each)
 constexpr uint32_t A_BYTES = BM * BK * 2;   // one bf16 plane of the 128x64 (or 2 x 64x64) operand tile
 
 template <int BN> struct TileCfg {
@@ -30,7 +32,7 @@ template <int BN> struct TileCfg {
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 2 * MAX_AFFINE * sizeof(float);
 };
 
 struct GemmArgs {
@@ -74,7 +76,16 @@ SACB_DEVINL void unpack8(const uint4& u, float* f) {
   f[6] = bf16_bits_to_float(u.w & 0xFFFF); f[7] = bf16_bits_to_float(u.w >> 16);
 }
 
-SACB_DEVINL void epilogue_row(const GemmArgs& a, uint32_t (&r)[32], int m, int c0) {
+SACB_DEVINL void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
+                              uint32_t (&r)[32], int m, int c0) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -82,8 +93,8 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, uint32_t (&r)[32], int m, int c
   if (a.scale) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + c0) + i);
-      float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + c0) + i);
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * i);     // smem broadcast
+      const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * i);
       v[4 * i + 0] = fmaf(v[4 * i + 0], sc.x, sh.x); v[4 * i + 1] = fmaf(v[4 * i + 1], sc.y, sh.y);
       v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
     }
@@ -125,14 +136,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, uint32_t (&r)[32], int m, int c
     for (int i = 0; i < 4; ++i) {
       uint32_t ph[4], pl[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x0 = v[8 * i + 2 * j], x1 = v[8 * i + 2 * j + 1];
-        uint16_t h0 = float_to_bf16_bits(x0), h1 = float_to_bf16_bits(x1);
-        uint16_t l0 = float_to_bf16_bits(x0 - bf16_bits_to_float(h0));
-        uint16_t l1 = float_to_bf16_bits(x1 - bf16_bits_to_float(h1));
-        ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-      }
+      for (int j = 0; j < 4; ++j) split_pack(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], ph[j], pl[j]);
       reinterpret_cast<uint4*>(a.out_hi + row)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       reinterpret_cast<uint4*>(a.out_lo + row)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
@@ -170,16 +174,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES + 256);
+  float* s_shift = s_scale + MAX_AFFINE;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
   }
+  if (a.scale) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+  }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -255,19 +264,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;          // the two warps of a quadrant split the column chunks
+    constexpr int CHUNKS = BN / 32;
+    constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_idx = tile / a.num_n_tiles, n_idx = tile - m_idx * a.num_n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int m = m_idx * BM + quad * 32 + lane;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
-        tmem_ld_wait();
-        if (m < a.M_total) epilogue_row(a, r, m, n_idx * BN + ch * 32);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      uint32_t r[2][32];
+      if (half < CHUNKS) tmem_ld32(tbase + half * 32, r[0]);
+#pragma unroll
+      for (int j = 0; j < MY_CHUNKS; ++j) {
+        const int ch = half + 2 * j;
+        if (ch < CHUNKS) {
+          tmem_ld_wait();
+          if (j + 1 < MY_CHUNKS && ch + 2 < CHUNKS) tmem_ld32(tbase + (ch + 2) * 32, r[(j + 1) & 1]);
+          if (m < a.M_total) epilogue_row(a, s_scale, s_shift, r[j & 1], m, n_idx * BN + ch * 32);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -310,7 +327,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -420,31 +437,36 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
       int m_idx, n_idx, tap, kb0, kb1;
       decode(wk, m_idx, n_idx, tap, kb0, kb1);
+      const int split = wk % a.splits;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m_idx * BM + quad * 32 + lane;
+      float* part = a.dw + (size_t)split * a.k_valid * a.taps * a.C;      // this split's private partial sums
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half; ch < CHUNKS; ch += 2) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
         tmem_ld_wait();
         const int col0 = n_idx * BN + ch * 32;
         if (!a.swap) {
           if (row < a.k_valid) {
-            float* dst = a.dw + ((size_t)row * a.taps + tap) * a.C + col0;
+            float4* dst = reinterpret_cast<float4*>(part + ((size_t)row * a.taps + tap) * a.C + col0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, __uint_as_float(r[i]));
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                   __uint_as_float(r[4 * i + 3]));
           }
         } else {
           if (row < a.C) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (col0 + i < a.k_valid)
-                atomicAdd(a.dw + ((size_t)(col0 + i) * a.taps + tap) * a.C + row, __uint_as_float(r[i]));
+              if (col0 + i < a.k_valid) part[((size_t)(col0 + i) * a.taps + tap) * a.C + row] = __uint_as_float(r[i]);
           }
         }
       }
@@ -598,6 +620,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.relu = d->relu;
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
+  SACB_REQUIRE(d->scale == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged affine size", d->K);
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
@@ -607,7 +630,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   }
 }
 
-extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
+static int plan_wgrad(const SacbConvWgrad* d, WgradArgs& a, int& BN) {
   SACB_REQUIRE(d && d->size == sizeof(SacbConvWgrad), "sacb_conv_wgrad: bad descriptor size");
   if (int e = ensure_init()) return e;
   SACB_REQUIRE(d->C % 64 == 0 && d->K % 64 == 0, "sacb_conv_wgrad: C=%d, K=%d must be multiples of 64", d->C, d->K);
@@ -615,29 +638,19 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
   const int P = (d->H + 2 * d->pad - (d->R - 1) * d->dil - 1) / d->stride + 1;
   const int Q = (d->W + 2 * d->pad - (d->S - 1) * d->dil - 1) / d->stride + 1;
   SACB_REQUIRE(P == d->P && Q == d->Q, "sacb_conv_wgrad: P,Q inconsistent with geometry");
-  CUtensorMap gh, gl, xh, xl;
-  if (int e = make_im2col_map(&xh, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
-  if (int e = make_im2col_map(&xl, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
   const long long M = (long long)d->N * P * Q;
-  cuuint64_t gd[2] = {(cuuint64_t)d->K, (cuuint64_t)M};
-  cuuint64_t gs[1] = {(cuuint64_t)d->K * 2};
-  cuuint32_t gb[2] = {64, 64};
-  if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
-  if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
-  WgradArgs a;
   a.k_valid = d->k_valid; a.Kg = d->K; a.C = d->C;
   a.taps = d->R * d->S; a.S = d->S; a.dil = d->dil; a.P = P; a.Q = Q; a.stride = d->stride; a.lower = -d->pad;
   a.num_pix_blocks = (int)((M + 63) / 64);
   a.dw = d->dw;
-  // few valid output channels (ASPP head, 19 classes): put the wide input-channel dim on the 128 TMEM lanes
+  // few valid output channels: put the wide input-channel dim on the 128 TMEM lanes
   a.swap = (d->k_valid <= 64 && d->C >= 128) ? 1 : 0;
-  int BN;
   if (!a.swap) { BN = (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
   else { BN = 64; a.m_tiles = (d->C + BM - 1) / BM; a.n_tiles = d->K / 64; }
   int splits = d->splits;
   if (splits <= 0) {
     const int base = a.m_tiles * a.n_tiles * a.taps;
-    splits = (4 * g_num_sms + base - 1) / base;
+    splits = (2 * g_num_sms + base - 1) / base;
     const int max_splits = a.num_pix_blocks / 8 > 0 ? a.num_pix_blocks / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -645,6 +658,27 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
   if (splits > a.num_pix_blocks) splits = a.num_pix_blocks;
   a.blocks_per_split = (a.num_pix_blocks + splits - 1) / splits;
   a.splits = (a.num_pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split;
+  return 0;
+}
+
+extern "C" int sacb_conv_wgrad_splits(const SacbConvWgrad* d) {
+  WgradArgs a; int BN;
+  if (int e = plan_wgrad(d, a, BN)) return e;
+  return a.splits;
+}
+
+extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
+  WgradArgs a; int BN;
+  if (int e = plan_wgrad(d, a, BN)) return e;
+  CUtensorMap gh, gl, xh, xl;
+  if (int e = make_im2col_map(&xh, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
+  if (int e = make_im2col_map(&xl, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, 64)) return e;
+  const long long M = (long long)d->N * a.P * a.Q;
+  cuuint64_t gd[2] = {(cuuint64_t)d->K, (cuuint64_t)M};
+  cuuint64_t gs[1] = {(cuuint64_t)d->K * 2};
+  cuuint32_t gb[2] = {64, 64};
+  if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
+  if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (BN == 128) return launch_wgrad<128>(gh, gl, xh, xl, a, st);
   return launch_wgrad<64>(gh, gl, xh, xl, a, st);

@@ -127,19 +127,27 @@ tail_probs_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
   }
 }
 
-// running_conf update (sac.py:104-117), one warp
-__global__ void tail_running_conf_kernel(const float* __restrict__ part_sums, int nparts, int C, double inv_count,
-                                         float beta, float momentum, float* __restrict__ running_conf) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+// running_conf update (sac.py:104-117): one block, thread = (class, slice); fixed-order double reduction
+__global__ void __launch_bounds__(1024)
+tail_running_conf_kernel(const float* __restrict__ part_sums, int nparts, int C, double inv_count, float beta,
+                         float momentum, float* __restrict__ running_conf) {
+  __shared__ double red[32][32];
+  const int c = threadIdx.x, sl = threadIdx.y;       // blockDim = (32, 32)
   double s = 0.0;
-  for (int k = 0; k < nparts; ++k) s += (double)part_sums[(size_t)k * C + c];
-  const float avg = (float)(s * inv_count);
-  float rc = running_conf[c];
-  if (avg > 1e-8f && rc == beta) rc = avg;
-  rc = rc * momentum;
-  rc = rc + (1.f - momentum) * avg;
-  running_conf[c] = rc;
+  if (c < C)
+    for (int k = sl; k < nparts; k += 32) s += (double)part_sums[(size_t)k * C + c];
+  red[sl][c] = s;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    double tot = 0.0;
+    for (int k = 0; k < 32; ++k) tot += red[k][c];
+    const float avg = (float)(tot * inv_count);
+    float rc = running_conf[c];
+    if (avg > 1e-8f && rc == beta) rc = avg;
+    rc = rc * momentum;
+    rc = rc + (1.f - momentum) * avg;
+    running_conf[c] = rc;
+  }
 }
 
 // ---------------------------------------------------------------- T2: warp to the reference frame + K-view average
@@ -494,7 +502,7 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
   LAUNCHED();
   if (d->training) {
-    tail_running_conf_kernel<<<1, 32, 0, ST>>>(d->part_sums, nb * d->BT, C, 1.0 / ((double)d->BT * HW), d->beta,
+    tail_running_conf_kernel<<<1, dim3(32, 32), 0, ST>>>(d->part_sums, nb * d->BT, C, 1.0 / ((double)d->BT * HW), d->beta,
                                               d->stat_momentum, d->running_conf);
     LAUNCHED();
   }

@@ -398,13 +398,17 @@ class ResNet101Engine(object):
         L.check(L.lib().sacb_colsum(L.ptr(g.hi), L.ptr(g.lo), L.ptr(d), C.c_int64(M), K, L.stream()), "sacb_colsum")
         return d
 
-    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
-        dwraw = self.dwraw[:s.K * s.R * s.R * s.C]
-        dwraw.zero_()
-        L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, dwraw, (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
-        self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R)
+    def _dw_workspace(self, n):
+        if self.dwraw.numel() < n:
+            self.dwraw = torch.empty(n, device=self.device)
+        return self.dwraw
 
-    def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS):
+    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
+        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, self._dw_workspace,
+                                     (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
+        self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R, splits=splits)
+
+    def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS, splits=1):
         lib, st = L.lib(), L.stream()
         if s.bn is not None:
             sc, _ = wp.affine(s.name)
@@ -412,8 +416,8 @@ class ResNet101Engine(object):
             L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), L.ptr(sc),
                                             L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
                                             C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")),
-                                            L.ptr(grad.view(s.bn + ".weight")), s.K, C_eff, RS, 1, st), "sacb_wgrad_finalize")
+                                            L.ptr(grad.view(s.bn + ".weight")), s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")
         else:
             L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), None, None, None,
                                             C.c_float(BN_EPS), None, L.ptr(grad.view(s.name + ".weight")), None,
-                                            s.K, C_eff, RS, 1, st), "sacb_wgrad_finalize")
+                                            s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")

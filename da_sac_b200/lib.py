@@ -147,9 +147,21 @@ def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift
 
 
 def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
+    """dw: fp32 tensor, or a callable n_elems -> tensor used to size the split-K partial planes.
+    Returns (dw, n_splits): dw holds n_splits planes [k_valid][R*R][C] that sacb_wgrad_finalize sums."""
     N, H, W, Cc, K, R, s, d, p = geom
     P, Q = conv_out_hw(H, W, R, s, d, p)
-    desc = ConvWgrad(C.sizeof(ConvWgrad), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
-                     ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), ptr(dw), splits)
-    flops = 2.0 * N * P * Q * (K if k_valid is None else k_valid) * Cc * R * R
+    kv = K if k_valid is None else k_valid
+    desc = ConvWgrad(C.sizeof(ConvWgrad), N, H, W, Cc, K, kv, R, R, s, d, p, P, Q,
+                     ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), None, splits)
+    n = lib().sacb_conv_wgrad_splits(C.byref(desc))
+    if n <= 0:
+        check(n if n < 0 else -1, "sacb_conv_wgrad_splits")
+    need = n * kv * R * R * Cc
+    if callable(dw):
+        dw = dw(need)
+    assert dw.numel() >= need, "split-K workspace too small: %d < %d" % (dw.numel(), need)
+    desc.dw = ptr(dw)
+    flops = 2.0 * N * P * Q * kv * Cc * R * R
     _prof_wrap("conv_wgrad", flops, lambda: check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad"))
+    return dw, n

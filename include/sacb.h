@@ -69,8 +69,9 @@ typedef struct SacbConvGemm {
 int sacb_conv_gemm(const SacbConvGemm* d, void* stream);
 
 /* Filter gradient (autograd of nn.Conv2d w.r.t. weight, train.py:232):
- *   dw[k][r*S+s][c] += sum_{n,p,q} G[n,p,q,k] * X[n, p*stride-pad+r*dil, q*stride-pad+s*dil, c]
- * accumulated with fp32 atomics into dw (caller zero-fills). G and X are split planes. */
+ *   dw[split][k][r*S+s][c] = sum_{(n,p,q) in split} G[n,p,q,k] * X[n, p*stride-pad+r*dil, q*stride-pad+s*dil, c]
+ * Deterministic split-K: every split writes its own partial plane; sacb_wgrad_finalize sums them in order.
+ * sacb_conv_wgrad_splits(d) returns the number of planes (>= 1) so the caller can size dw. G, X: split planes. */
 typedef struct SacbConvWgrad {
   uint32_t size;
   int32_t N, H, W, C;         /* input X NHWC, C % 64 == 0 */
@@ -80,9 +81,10 @@ typedef struct SacbConvWgrad {
   int32_t P, Q;
   const void* x_hi; const void* x_lo;   /* bf16 [N,H,W,C] */
   const void* g_hi; const void* g_lo;   /* bf16 [N,P,Q,K] */
-  float* dw;                            /* fp32 [k_valid][R*S][C] */
-  int32_t splits;                       /* split-K factor over pixels; 0 = auto */
+  float* dw;                            /* fp32 [splits][k_valid][R*S][C] */
+  int32_t splits;                       /* requested split-K factor over pixels; 0 = auto */
 } SacbConvWgrad;
+int sacb_conv_wgrad_splits(const SacbConvWgrad* d);
 int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream);
 
 /* ---------------------------------------------------------------- elementwise / layout kernels
@@ -119,11 +121,12 @@ int sacb_prep_weight(const float* w_oihw, const float* scale, int K, int C, int 
 int sacb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                  float* scale, float* shift, int C, void* stream);
 /* finalize a conv+BN unit's parameter gradients from the raw filter gradient (DESIGN.md "BN backward"):
+ * dwraw[k][rs][c] = sum over `splits` partial planes (plane stride K*R*S*C);
  * dw_oihw[k][c][r][s] = scale[k] * dwraw[k][rs][c];
  * dgamma[k] = (sum_{rs,c} w[k][c][r][s] * dwraw[k][rs][c] - mean[k] * dbeta[k]) * rsqrt(var[k]+eps) */
 int sacb_wgrad_finalize(const float* dwraw, const float* w_oihw, const float* scale, const float* mean,
                         const float* var, float eps, const float* dbeta, float* dw_oihw, float* dgamma,
-                        int K, int C, int R, int S, void* stream);
+                        int K, int C, int R, int S, int splits, void* stream);
 
 /* ---------------------------------------------------------------- SAC tail (models/sac.py)
  * teacher logits -> pseudo labels; replaces SAC._refine + _update_running_conf + _avg_pool +

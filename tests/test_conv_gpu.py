@@ -141,7 +141,11 @@ def test_conv_wgrad(geom):
     F.conv2d(x, w, None, s, p, d).backward(g)
     ref = w.grad[:k_valid].permute(0, 2, 3, 1).reshape(k_valid, R * R, C)
     xh, xl = split(nhwc(x.float())); gh, gl = split(nhwc(g.float()))
-    dw = torch.zeros(k_valid, R * R, C, device="cuda")
-    L.conv_wgrad(xh, xl, gh, gl, dw, geom, k_valid=k_valid)
+    parts, n = L.conv_wgrad(xh, xl, gh, gl, lambda m: torch.full((m,), float("nan"), device="cuda"), geom, k_valid=k_valid)
     torch.cuda.synchronize()
+    dw = parts[:n * k_valid * R * R * C].view(n, k_valid, R * R, C).sum(0)
     assert relerr(dw, ref) < TOL
+    # deterministic split-K: a second run reproduces the partial planes bit for bit
+    parts2, n2 = L.conv_wgrad(xh, xl, gh, gl, lambda m: torch.empty(m, device="cuda"), geom, k_valid=k_valid)
+    torch.cuda.synchronize()
+    assert n2 == n and torch.equal(parts2[:parts.numel()], parts)
