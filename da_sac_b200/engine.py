@@ -20,6 +20,8 @@ from . import lib as L
 
 BN_EPS = 1e-5
 NUM_CLASSES = 19
+ASPP_JPAD = 768          # 4 convs x 9 taps x 19 classes = 684, padded to the GEMM N tile (sacb_aspp_jpad)
+ASPP_DIL = (C.c_int32 * 4)(6, 12, 18, 24)
 
 
 class ConvSpec(object):
@@ -133,13 +135,16 @@ class WeightPlanes(object):
         self.off = {}
         for name in net["order"]:
             s = net["specs"][name]
-            if s.C == 3:
+            if s.C == 3 or s.bn is None:       # stem runs on CUDA cores; the ASPP head uses the packed planes below
                 self.off[name] = (None, None, nsc)
             else:
                 self.off[name] = (nf, nt, nsc)
                 nf += s.R * s.R * s.Kf * s.C
                 nt += s.R * s.R * s.C * s.Kt
             nsc += s.Kf
+        self.aspp_off = (nf, nt)
+        self.aspp_n = ASPP_JPAD * net["aspp"][0].C
+        nf += self.aspp_n; nt += self.aspp_n
         bf = torch.bfloat16
         self.wf_hi = torch.empty(nf, device=device, dtype=bf); self.wf_lo = torch.empty(nf, device=device, dtype=bf)
         if with_dgrad:
@@ -154,6 +159,13 @@ class WeightPlanes(object):
         s = self.net["specs"][name]; o = self.off[name][1]; n = s.R * s.R * s.C * s.Kt
         return self.wt_hi[o:o + n], self.wt_lo[o:o + n]
 
+    def aspp(self):
+        of, ot = self.aspp_off
+        n = self.aspp_n
+        f = (self.wf_hi[of:of + n], self.wf_lo[of:of + n])
+        t = (self.wt_hi[ot:ot + n], self.wt_lo[ot:ot + n]) if self.with_dgrad else (None, None)
+        return f, t
+
     def affine(self, name):
         s = self.net["specs"][name]; o = self.off[name][2]
         return self.scale[o:o + s.Kf], self.shift[o:o + s.Kf]
@@ -167,15 +179,17 @@ class WeightPlanes(object):
                 L.check(lib.sacb_bn_fold(L.ptr(flat.view(s.bn + ".weight")), L.ptr(flat.view(s.bn + ".bias")),
                                          L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
                                          C.c_float(BN_EPS), L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
-            else:
-                sh[:s.K].copy_(flat.view(name + ".bias"))
-            if s.C == 3:
+            if s.C == 3 or s.bn is None:
                 continue
             fh, fl = self.wf(name)
             th, tl = self.wt(name) if self.with_dgrad else (None, None)
             L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc) if s.bn is not None else None,
                                          s.K, s.C, s.R, s.R, s.Kf, s.Kt, L.ptr(fh), L.ptr(fl), L.ptr(th), L.ptr(tl), st),
                     "sacb_prep_weight")
+        a = self.net["aspp"]
+        f, t = self.aspp()
+        L.check(lib.sacb_aspp_pack_weights(*[L.ptr(flat.view(x.name + ".weight")) for x in a], a[0].C,
+                                           L.ptr(f[0]), L.ptr(f[1]), L.ptr(t[0]), L.ptr(t[1]), st), "sacb_aspp_pack_weights")
 
 
 class Planes(object):
@@ -234,8 +248,7 @@ class ResNet101Engine(object):
         self.tpool_hi = BufferPool(max_elems, 5, bf, device); self.tpool_lo = BufferPool(max_elems, 5, bf, device)
         self.fpool = BufferPool(max_elems, 2, torch.float32, device)
         oh, ow = net["out_hw"]
-        self.head_acc = torch.empty(N * oh * ow * 32, device=device)
-        self.g5 = planes(N * oh * ow, 64)
+        self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)      # tap-unrolled ASPP partial outputs
         self.dwraw = torch.empty(max(s.Kt * s.R * s.R * s.C for s in net["specs"].values()), device=device)
 
     # ------------------------------------------------------------------ forward
@@ -279,13 +292,13 @@ class ResNet101Engine(object):
             if ds is not None: put(ds.name)
             put(xtag)
             a, xtag = o3, c3.name
-        # ASPP head: sum of 4 dilated 3x3 convs + biases (deeplabv2.py:112-116), accumulated in fp32
-        for i, s in enumerate(net["aspp"]):
-            fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
-            last = i == len(net["aspp"]) - 1
-            L.conv_gemm(a.hi, a.lo, fh, fl, s.geom(N), k_valid=s.K, scale=sc, shift=sh,
-                        add_f32=self.head_acc if i > 0 else None, out_f32=None if last else self.head_acc,
-                        out_nchw=logits_out if last else None)
+        # ASPP head (deeplabv2.py:112-116) as one tap-unrolled 1x1 GEMM + shift-and-add (csrc/sacb_aspp.cu)
+        asp = net["aspp"]
+        oh, ow = net["out_hw"]
+        (fh, fl), _ = wp.aspp()
+        L.conv_gemm(a.hi, a.lo, fh, fl, (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0), out_f32=self.zbuf)
+        L.check(lib.sacb_aspp_gather(L.ptr(self.zbuf), *[L.ptr(flat.view(x.name + ".bias")) for x in asp], ASPP_DIL,
+                                     L.ptr(logits_out), N, oh, ow, st), "sacb_aspp_gather")
         put(xtag)
         return logits_out
 
@@ -302,26 +315,25 @@ class ResNet101Engine(object):
         self.tpool_hi.reset(); self.tpool_lo.reset(); self.fpool.reset()
         oh, ow = net["out_hw"]
         M5 = N * oh * ow
-        # dlogits -> NHWC padded to 64 channels -> split planes
-        g = torch.zeros(M5, 64, device=self.device)
-        g[:, :NUM_CLASSES] = dlogits.permute(0, 2, 3, 1).reshape(M5, NUM_CLASSES)
-        L.check(lib.sacb_add_mask_split(L.ptr(g), None, None, L.ptr(self.g5.hi), L.ptr(self.g5.lo), C.c_int64(M5 * 64), st),
-                "sacb_add_mask_split")
-        dbias = torch.zeros(64, device=self.device)
-        L.check(lib.sacb_colsum(L.ptr(self.g5.hi), L.ptr(self.g5.lo), L.ptr(dbias), C.c_int64(M5), 64, st), "sacb_colsum")
+        # ASPP head backward: Gcol (shifted copies of dlogits) -> bias / filter / data gradients as plain GEMMs
+        asp = net["aspp"]
         blocks = net["blocks"]
         xlast = self.act[blocks[-1][3].name]
-        acc = self.fpool.get("acc", M5 * 2048)
-        gout = self._tplanes("gout", M5 * 2048)
-        for i, s in enumerate(net["aspp"]):
-            grad.view(s.name + ".bias").copy_(dbias[:NUM_CLASSES])
-            self._wgrad(flat, wp, s, xlast, self.g5, grad, dbeta=None)
-            th, tl = wp.wt(s.name)
-            last = i == len(net["aspp"]) - 1
-            L.conv_gemm(self.g5.hi, self.g5.lo, th, tl, s.geom_dgrad(N), add_f32=acc if i > 0 else None,
-                        out_f32=None if last else acc, mask_hi=xlast.hi if last else None,
-                        out_hi=gout.hi if last else None, out_lo=gout.lo if last else None)
-        self.fpool.put("acc")
+        gcol = self._tplanes("gcol", M5 * ASPP_JPAD)
+        L.check(lib.sacb_aspp_gcol(L.ptr(dlogits), ASPP_DIL, L.ptr(gcol.hi), L.ptr(gcol.lo), N, oh, ow, st), "sacb_aspp_gcol")
+        csum = self._dbeta(gcol, M5, ASPP_JPAD)
+        for i, s in enumerate(asp):                      # centre tap of conv i carries g itself: its column sum is d bias
+            o = (i * 9 + 4) * NUM_CLASSES
+            grad.view(s.name + ".bias").copy_(csum[o:o + NUM_CLASSES])
+        parts, splits = L.conv_wgrad(xlast.hi, xlast.lo, gcol.hi, gcol.lo, self._dw_workspace,
+                                     (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0))
+        L.check(lib.sacb_aspp_unpack_wgrad(L.ptr(parts), splits, asp[0].C, *[L.ptr(grad.view(x.name + ".weight")) for x in asp], st),
+                "sacb_aspp_unpack_wgrad")
+        gout = self._tplanes("gout", M5 * asp[0].C)
+        _, (th, tl) = wp.aspp()
+        L.conv_gemm(gcol.hi, gcol.lo, th, tl, (N, oh, ow, ASPP_JPAD, asp[0].C, 1, 1, 1, 0), mask_hi=xlast.hi,
+                    out_hi=gout.hi, out_lo=gout.lo)
+        self._tput("gcol")
         for bi in range(len(blocks) - 1, -1, -1):
             (p, c1, c2, c3, ds) = blocks[bi]
             xin = self.act[blocks[bi - 1][3].name] if bi > 0 else self.act["pool"]

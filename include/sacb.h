@@ -128,6 +128,22 @@ int sacb_wgrad_finalize(const float* dwraw, const float* w_oihw, const float* sc
                         const float* var, float eps, const float* dbeta, float* dw_oihw, float* dgamma,
                         int K, int C, int R, int S, int splits, void* stream);
 
+/* ---------------------------------------------------------------- ASPP head as a tap-unrolled 1x1 GEMM
+ * Classifier_Module (deeplabv2.py:101-116): sum of four 3x3 dilated convs 2048 -> 19 (+ biases).
+ *   Z[pix, (i*9 + r*3+s)*19 + k] = sum_c X[pix,c] * W_i[k,c,r,s]   via sacb_conv_gemm (1x1, K = sacb_aspp_jpad() = 768)
+ *   logits[n,k,p,q] = sum_i b_i[k] + sum_{i,r,s} Z[(n, p+(r-1)d_i, q+(s-1)d_i), (i*9+r*3+s)*19 + k]   (sacb_aspp_gather)
+ * backward: Gcol[pix, (i*9+rs)*19+k] = g[n,k,p-(r-1)d_i,q-(s-1)d_i] (sacb_aspp_gcol) feeds sacb_conv_gemm (data
+ * gradient, weights wt[c][j]) and sacb_conv_wgrad (filter gradient), unpacked by sacb_aspp_unpack_wgrad. */
+int sacb_aspp_jpad(void);
+int sacb_aspp_pack_weights(const float* w0, const float* w1, const float* w2, const float* w3, int C,
+                           void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, void* stream);
+int sacb_aspp_gather(const float* Z, const float* b0, const float* b1, const float* b2, const float* b3,
+                     const int32_t* dil4 /* host */, float* out_nchw, int N, int P, int Q, void* stream);
+int sacb_aspp_gcol(const float* g_nchw, const int32_t* dil4 /* host */, void* hi, void* lo, int N, int P, int Q,
+                   void* stream);
+int sacb_aspp_unpack_wgrad(const float* parts, int splits, int C, float* dw0, float* dw1, float* dw2, float* dw3,
+                           void* stream);
+
 /* ---------------------------------------------------------------- SAC tail (models/sac.py)
  * teacher logits -> pseudo labels; replaces SAC._refine + _update_running_conf + _avg_pool +
  * _pseudo_labels_probs (sac.py:104-117,151-187,238-313). */
