@@ -171,6 +171,57 @@ stem_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ g_hi
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem on the tensor cores: explicit im2col of the 3-channel image (147 taps, zero-padded to 192 columns) so the
+// 7x7 s2 conv becomes a 1x1 conv_gemm with C = 192 (and its filter gradient a plain conv_wgrad).
+// ------------------------------------------------------------------------------------------------
+constexpr int STEM_KP = 192;
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ a_hi, uint16_t* __restrict__ a_lo, int N, int H,
+                   int W, int P, int Q) {
+  const size_t total = (size_t)N * P * Q * (STEM_KP / 8);
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int jv = (int)(t % (STEM_KP / 8));
+    size_t pix = t / (STEM_KP / 8);
+    const int q = (int)(pix % Q); pix /= Q;
+    const int p = (int)(pix % P);
+    const int n = (int)(pix / P);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = jv * 8 + e;
+      float val = 0.f;
+      if (j < 147) {
+        const int c = j / 49, rs = j - c * 49;
+        const int r = rs / 7, ss = rs - r * 7;
+        const int hh = 2 * p - 3 + r, ww = 2 * q - 3 + ss;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((size_t)(n * 3 + c) * H + hh) * W + ww);
+      }
+      v[e] = val;
+    }
+    uint4 h, l;
+    split8(v, h, l);
+    reinterpret_cast<uint4*>(a_hi)[t] = h;
+    reinterpret_cast<uint4*>(a_lo)[t] = l;
+  }
+}
+// wf[k][j] (j < 192) from OIHW [64][147]
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * STEM_KP) return;
+  const int k = i / STEM_KP, j = i - k * STEM_KP;
+  st_split(hi, lo, i, j < 147 ? w[k * 147 + j] : 0.f);
+}
+// dwraw[k][j<147] = sum_split parts[split][k][j]  (parts rows are 192 wide)
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ parts, int splits, float* __restrict__ dwraw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 147) return;
+  const int k = i / 147, j = i - k * 147;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += parts[((size_t)sp * 64 + k) * STEM_KP + j];
+  dwraw[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // MaxPool2d(3, stride 2, pad 1, ceil_mode=True)   (deeplabv2.py:126)
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
@@ -467,6 +518,24 @@ extern "C" int sacb_stem_fwd(const float* x, const float* w, const float* scale,
 extern "C" int sacb_stem_wgrad(const float* x, const void* g_hi, const void* g_lo, float* dw, int N, int H, int W, int P,
                                int Q, void* stream) {
   stem_wgrad_kernel<<<148 * 2, 256, 0, ST>>>(x, (const uint16_t*)g_hi, (const uint16_t*)g_lo, dw, N, H, W, P, Q);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_stem_im2col(const float* x, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, void* stream) {
+  SACB_REQUIRE(P == (H + 6 - 7) / 2 + 1 && Q == (W + 6 - 7) / 2 + 1, "sacb_stem_im2col: bad output size");
+  const size_t total = (size_t)N * P * Q * (STEM_KP / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_stem_pack_weight(const float* w, void* hi, void* lo, void* stream) {
+  stem_pack_weight_kernel<<<(64 * STEM_KP + 255) / 256, 256, 0, ST>>>(w, (uint16_t*)hi, (uint16_t*)lo);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, void* stream) {
+  stem_unpack_wgrad_kernel<<<(64 * 147 + 255) / 256, 256, 0, ST>>>(parts, splits, dwraw);
   LAUNCHED();
   return 0;
 }

@@ -76,6 +76,20 @@ SACB_DEVINL void unpack8(const uint4& u, float* f) {
   f[6] = bf16_bits_to_float(u.w & 0xFFFF); f[7] = bf16_bits_to_float(u.w >> 16);
 }
 
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100a): one full 32-byte sector per lane
+SACB_DEVINL void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+SACB_DEVINL void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]),
+               "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+SACB_DEVINL void unpack16(const uint32_t (&u)[8], float* f) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16_bits_to_float(u[i] & 0xFFFF); f[2 * i + 1] = bf16_bits_to_float(u[i] >> 16); }
+}
+
 SACB_DEVINL void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
   const float2 hf = __bfloat1622float2(h);
@@ -101,20 +115,23 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
   }
   if (a.add_f32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(a.add_f32 + row) + i);
-      v[4 * i + 0] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+    for (int i = 0; i < 4; ++i) {
+      uint32_t t[8];
+      ldg256(a.add_f32 + row + 8 * i, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] += __uint_as_float(t[j]);
     }
   }
   if (a.add_hi) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 h = __ldg(reinterpret_cast<const uint4*>(a.add_hi + row) + i);
-      uint4 l = __ldg(reinterpret_cast<const uint4*>(a.add_lo + row) + i);
-      float fh[8], fl[8];
-      unpack8(h, fh); unpack8(l, fl);
+    for (int i = 0; i < 2; ++i) {
+      uint32_t h[8], l[8];
+      ldg256(a.add_hi + row + 16 * i, h);
+      ldg256(a.add_lo + row + 16 * i, l);
+      float fh[16], fl[16];
+      unpack16(h, fh); unpack16(l, fl);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 * i + j] += fh[j] + fl[j];
+      for (int j = 0; j < 16; ++j) v[16 * i + j] += fh[j] + fl[j];
     }
   }
   if (a.relu) {
@@ -123,28 +140,33 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
   }
   if (a.mask_hi) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 h = __ldg(reinterpret_cast<const uint4*>(a.mask_hi + row) + i);
-      float fh[8];
-      unpack8(h, fh);
+    for (int i = 0; i < 2; ++i) {
+      uint32_t h[8];
+      ldg256(a.mask_hi + row + 16 * i, h);
+      float fh[16];
+      unpack16(h, fh);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[8 * i + j] = fh[j] > 0.f ? v[8 * i + j] : 0.f;
+      for (int j = 0; j < 16; ++j) v[16 * i + j] = fh[j] > 0.f ? v[16 * i + j] : 0.f;
     }
   }
   if (a.out_hi) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t ph[4], pl[4];
+    for (int i = 0; i < 2; ++i) {
+      uint32_t ph[8], pl[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) split_pack(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], ph[j], pl[j]);
-      reinterpret_cast<uint4*>(a.out_hi + row)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-      reinterpret_cast<uint4*>(a.out_lo + row)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      for (int j = 0; j < 8; ++j) split_pack(v[16 * i + 2 * j], v[16 * i + 2 * j + 1], ph[j], pl[j]);
+      stg256(a.out_hi + row + 16 * i, ph);
+      stg256(a.out_lo + row + 16 * i, pl);
     }
   }
   if (a.out_f32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      reinterpret_cast<float4*>(a.out_f32 + row)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int i = 0; i < 4; ++i) {
+      uint32_t t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = __float_as_uint(v[8 * i + j]);
+      stg256(a.out_f32 + row + 8 * i, t);
+    }
   }
   if (a.out_nchw) {
     const int pq = a.P * a.Q;
@@ -276,13 +298,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       const int m = m_idx * BM + quad * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       uint32_t r[2][32];
-      if (half < CHUNKS) tmem_ld32(tbase + half * 32, r[0]);
+      const int ch0 = half * MY_CHUNKS;          // adjacent chunks: one warp covers MY_CHUNKS*32 contiguous channels
+      if (ch0 < CHUNKS) tmem_ld32(tbase + ch0 * 32, r[0]);
 #pragma unroll
       for (int j = 0; j < MY_CHUNKS; ++j) {
-        const int ch = half + 2 * j;
+        const int ch = ch0 + j;
         if (ch < CHUNKS) {
           tmem_ld_wait();
-          if (j + 1 < MY_CHUNKS && ch + 2 < CHUNKS) tmem_ld32(tbase + (ch + 2) * 32, r[(j + 1) & 1]);
+          if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
           if (m < a.M_total) epilogue_row(a, s_scale, s_shift, r[j & 1], m, n_idx * BN + ch * 32);
         }
       }

@@ -22,6 +22,7 @@ BN_EPS = 1e-5
 NUM_CLASSES = 19
 ASPP_JPAD = 768          # 4 convs x 9 taps x 19 classes = 684, padded to the GEMM N tile (sacb_aspp_jpad)
 ASPP_DIL = (C.c_int32 * 4)(6, 12, 18, 24)
+STEM_KP = 192            # 3*7*7 = 147 im2col columns of the stem, zero-padded to a multiple of 64
 
 
 class ConvSpec(object):
@@ -142,6 +143,8 @@ class WeightPlanes(object):
                 nf += s.R * s.R * s.Kf * s.C
                 nt += s.R * s.R * s.C * s.Kt
             nsc += s.Kf
+        self.stem_off = nf
+        nf += 64 * STEM_KP
         self.aspp_off = (nf, nt)
         self.aspp_n = ASPP_JPAD * net["aspp"][0].C
         nf += self.aspp_n; nt += self.aspp_n
@@ -158,6 +161,10 @@ class WeightPlanes(object):
     def wt(self, name):
         s = self.net["specs"][name]; o = self.off[name][1]; n = s.R * s.R * s.C * s.Kt
         return self.wt_hi[o:o + n], self.wt_lo[o:o + n]
+
+    def stem(self):
+        o = self.stem_off
+        return self.wf_hi[o:o + 64 * STEM_KP], self.wf_lo[o:o + 64 * STEM_KP]
 
     def aspp(self):
         of, ot = self.aspp_off
@@ -186,6 +193,9 @@ class WeightPlanes(object):
             L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc) if s.bn is not None else None,
                                          s.K, s.C, s.R, s.R, s.Kf, s.Kt, L.ptr(fh), L.ptr(fl), L.ptr(th), L.ptr(tl), st),
                     "sacb_prep_weight")
+        sh_, sl_ = self.stem()
+        L.check(lib.sacb_stem_pack_weight(L.ptr(flat.view(self.net["stem"].name + ".weight")), L.ptr(sh_), L.ptr(sl_), st),
+                "sacb_stem_pack_weight")
         a = self.net["aspp"]
         f, t = self.aspp()
         L.check(lib.sacb_aspp_pack_weights(*[L.ptr(flat.view(x.name + ".weight")) for x in a], a[0].C,
@@ -249,7 +259,9 @@ class ResNet101Engine(object):
         self.fpool = BufferPool(max_elems, 2, torch.float32, device)
         oh, ow = net["out_hw"]
         self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)      # tap-unrolled ASPP partial outputs
+        self.stem_a = planes(N * st.hout * st.wout, STEM_KP)                 # im2col matrix of the stem (kept for wgrad)
         self.dwraw = torch.empty(max(s.Kt * s.R * s.R * s.C for s in net["specs"].values()), device=device)
+        self.stem_dw = torch.empty(64 * 147, device=device)
 
     # ------------------------------------------------------------------ forward
     def _tplanes(self, tag, n):
@@ -268,8 +280,11 @@ class ResNet101Engine(object):
         put = (lambda tag: None) if keep else self._tput
         sc, sh = wp.affine(stem.name)
         a_stem = get("stem", N * stem.hout * stem.wout * 64)
-        L.check(lib.sacb_stem_fwd(L.ptr(x), L.ptr(flat.view(stem.name + ".weight")), L.ptr(sc), L.ptr(sh),
-                                  L.ptr(a_stem.hi), L.ptr(a_stem.lo), N, self.H, self.W, stem.hout, stem.wout, st), "sacb_stem_fwd")
+        L.check(lib.sacb_stem_im2col(L.ptr(x), L.ptr(self.stem_a.hi), L.ptr(self.stem_a.lo), N, self.H, self.W,
+                                     stem.hout, stem.wout, st), "sacb_stem_im2col")
+        wsh, wsl = wp.stem()
+        L.conv_gemm(self.stem_a.hi, self.stem_a.lo, wsh, wsl, (N, stem.hout, stem.wout, STEM_KP, 64, 1, 1, 1, 0),
+                    scale=sc, shift=sh, relu=True, out_hi=a_stem.hi, out_lo=a_stem.lo)
         a = get("pool", N * ph * pw * 64)
         L.check(lib.sacb_maxpool_fwd(L.ptr(a_stem.hi), L.ptr(a_stem.lo), L.ptr(a.hi), L.ptr(a.lo), L.ptr(self.pool_idx),
                                      N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_fwd")
@@ -399,10 +414,10 @@ class ResNet101Engine(object):
         L.check(lib.sacb_maxpool_bwd(L.ptr(gp), L.ptr(self.pool_idx), L.ptr(a_stem.hi), L.ptr(gs.hi), L.ptr(gs.lo),
                                      N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_bwd")
         dbeta = self._dbeta(gs, N * stem.hout * stem.wout, 64)
-        dwraw = self.dwraw[:64 * 147]
-        dwraw.zero_()
-        L.check(lib.sacb_stem_wgrad(L.ptr(x), L.ptr(gs.hi), L.ptr(gs.lo), L.ptr(dwraw), N, self.H, self.W, stem.hout, stem.wout, st),
-                "sacb_stem_wgrad")
+        parts, splits = L.conv_wgrad(self.stem_a.hi, self.stem_a.lo, gs.hi, gs.lo, self._dw_workspace,
+                                     (N, stem.hout, stem.wout, STEM_KP, 64, 1, 1, 1, 0))
+        dwraw = self.stem_dw
+        L.check(lib.sacb_stem_unpack_wgrad(L.ptr(parts), splits, L.ptr(dwraw), st), "sacb_stem_unpack_wgrad")
         self._finalize(flat, wp, stem, dwraw, grad, dbeta, C_eff=147, RS=1)
 
     def _dbeta(self, g, M, K):

@@ -97,6 +97,12 @@ int sacb_stem_fwd(const float* x_nchw, const float* w, const float* scale, const
 /* dW of the stem conv: g split planes [N,P,Q,64] (already masked by ReLU), x fp32 NCHW -> dw[64][3][7][7] (+=) */
 int sacb_stem_wgrad(const float* x_nchw, const void* g_hi, const void* g_lo, float* dw,
                     int N, int H, int W, int P, int Q, void* stream);
+/* Tensor-core stem: A[n,p,q, (c*7+r)*7+s] = x[n,c,2p-3+r,2q-3+s] (147 taps zero-padded to 192 columns) turns the
+ * 7x7 s2 conv into a 1x1 sacb_conv_gemm with C = 192 (weights from sacb_stem_pack_weight: [64][192]) and its filter
+ * gradient into a 1x1 sacb_conv_wgrad whose partial planes sacb_stem_unpack_wgrad sums into dwraw[64][147]. */
+int sacb_stem_im2col(const float* x_nchw, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, void* stream);
+int sacb_stem_pack_weight(const float* w, void* hi, void* lo, void* stream);
+int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, void* stream);
 /* MaxPool2d(3, 2, 1, ceil_mode=True) on split planes (deeplabv2.py:126); idx = argmax tap (uint8) for backward */
 int sacb_maxpool_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx,
                      int N, int H, int W, int C, int P, int Q, void* stream);

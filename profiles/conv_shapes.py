@@ -76,7 +76,10 @@ def main():
         seen.setdefault(key, [s, 0])[1] += 1
     print("%-34s %3s %9s %9s | %8s %7s | %8s %7s | %8s %7s" % ("shape", "cnt", "M", "GFLOP", "fprop us", "TF/s", "dgrad us", "TF/s", "wgrad us", "TF/s"))
     tot = {"fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    only = os.environ.get("SACB_ONLY")          # e.g. SACB_ONLY="C256 K1024,C1024 K256"
     for key, (s, cnt) in seen.items():
+        if only and not any(("C%d K%d " % (s.C, s.K)) == o.strip() + " " for o in only.split(",")):
+            continue
         d = make(s)
         fl = 2.0 * d["M"] * s.K * s.C * s.R * s.R
         res = []

@@ -141,8 +141,68 @@ def test_two_training_steps_match_reference_golden(net, golden):
                 g = g.flatten()[:60000] if g.numel() > 60000 else g
                 e = rel(g.reshape(golden[key].shape), golden[key])[0]
                 print("   grad", n, "rel-L2 %.2e" % e)
-                assert e < 1e-2, key
+                # end-to-end the only sizeable contribution is the handful of flipped pseudo-label pixels
+                # (2 of 65536 here => O(1e-2) on the deepest layers); the backward arithmetic itself is
+                # checked to 2e-3 in test_backward_matches_reference_given_golden_pseudo_labels
+                assert e < 3e-2, key
         if step == 0:
             optim.step()
             v = m.backbone.model.layer3[5].conv2.weight.detach().flatten()[:60000]
             assert rel(v, golden["s0_post_step::model.layer3.5.conv2.weight"])[1] < 1e-5
+
+
+def test_backward_matches_reference_given_golden_pseudo_labels(net, golden):
+    """Same two steps, but the pseudo labels / confidence / running_conf that feed the loss are overwritten with the
+    reference's golden values, so that every parameter gradient can be compared tightly (no label-flip noise)."""
+    from da_sac_b200 import synth
+    m, cfg = net
+    m.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    m.slow_init[0] = False
+    m.running_conf.zero_()
+    m.train()
+    optim = torch.optim.SGD(m.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    batch = synth.make_target_batch(N_GROUPS, K, HW, seed=0)
+    names = [str(n) for n in golden["grad_names"]]
+    params = dict(m.backbone.named_parameters())
+    orig_tail = m._tail
+    state = {"step": 0}
+
+    def tail_with_golden(*a, **k):
+        ws = orig_tail(*a, **k)
+        pre = "s%d_" % state["step"]
+        ws["labels"].copy_(torch.from_numpy(golden[pre + "teacher_labels"]).cuda())
+        conf = torch.from_numpy(golden[pre + "teacher_conf"]).cuda()
+        ws["conf"].copy_(conf)
+        ws["conf_mean"].copy_(conf.mean(0)[0])
+        m.running_conf.copy_(torch.from_numpy(golden[pre + "running_conf"]).cuda())
+        return ws
+
+    m._tail = tail_with_golden
+    try:
+        for step in (0, 1):
+            state["step"] = step
+            x, y, x2, A, Ai = [t.clone().cuda() for t in batch]
+            losses, outs = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=(step == 0), T=K)
+            optim.zero_grad()
+            (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+            torch.cuda.synchronize()
+            pre = "s%d_" % step
+            g = float(golden[pre + "self_ce"].reshape(-1)[0]); v = float(losses["self_ce"].detach().reshape(-1)[0])
+            assert abs(v - g) <= 5e-4 * abs(g), (v, g)
+            gn = golden[pre + "grad_norms"]
+            mine = np.array([params[n].grad.double().norm().item() for n in names])
+            relerr = np.abs(mine - gn) / np.maximum(gn, 1e-12)
+            print("step", step, "grad-norm max rel err %.2e (%s)" % (relerr.max(), names[int(relerr.argmax())]))
+            assert relerr.max() < 2e-3
+            for key in golden.files:
+                if key.startswith(pre + "grad::"):
+                    n = key.split("::")[1]
+                    gg = params[n].grad
+                    gg = gg.flatten()[:60000] if gg.numel() > 60000 else gg
+                    e = rel(gg.reshape(golden[key].shape), golden[key])[0]
+                    print("   grad", n, "rel-L2 %.2e" % e)
+                    assert e < 2e-3, key
+            if step == 0:
+                optim.step()
+    finally:
+        m._tail = orig_tail
