@@ -107,7 +107,10 @@ class SAC(SAC_Baseline):
     def _momentum_update(self, update=False):
         dev = self.running_conf.device
         fs, ft = self.backbone.ensure_flat(dev), self.slow_net.ensure_flat(dev)
-        if not self.slow_init[0]:
+        # the reference reads slow_init on the host every call (sac.py:75); while a CUDA graph is being captured the
+        # teacher is known to be initialised (capture only happens after eager warm-up steps)
+        initialised = True if torch.cuda.is_current_stream_capturing() else bool(self.slow_init[0])
+        if not initialised:
             self.running_conf.fill_(self.cfg.THRESHOLD_BETA)
             self.slow_init[0] = True
             ft.buf.copy_(fs.buf)                        # slow_net.load_state_dict(backbone.state_dict())
@@ -175,7 +178,7 @@ class SAC(SAC_Baseline):
         if reset_teacher:
             self.slow_init[0] = False
         y_raw = y.clone()                                                # keeps the -1 padding marker for the kernels
-        y[y == -1] = 255                                                 # in-place on the caller's tensor (sac.py:337-338)
+        y.masked_fill_(y == -1, 255)                                     # in-place on the caller's tensor (sac.py:337-338)
         losses = {}
         H, W = x.shape[-2:]
         if update_teacher:

@@ -103,7 +103,9 @@ class TargetStepper(object):
         self.optim = FusedSGD(net.backbone, groups, cfg_model.MOMENTUM)
         self.iter = 0
         self._pinned = None
-        self._host_losses = None
+        self._graph = None
+        self._static = None
+        self._graph_losses = None
 
     def stage_host(self, batch):
         """pinned host copies of a batch (what a DataLoader with pin_memory hands to train.py:183)"""
@@ -113,21 +115,54 @@ class TargetStepper(object):
     def h2d(self, host_batch):
         return tuple(t.to(self.device, non_blocking=True) for t in host_batch)
 
-    def step(self, batch, update_teacher=None, read_losses=False):
-        """one Trainer._step_target(train=True) on device-resident tensors; returns losses (tensors or floats)"""
-        if update_teacher is None:
-            update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)          # train.py:294
+    def _eager(self, batch, update_teacher):
         x, y, x2, A, Ai = batch
         losses, outs = self.net(x, y, x2, A, Ai, use_teacher=True, update_teacher=update_teacher, T=self.T)
         self.optim.zero_grad()                                                      # TARGET_ONLY (train.py:227-228)
         (self.cfg.LR_TARGET * losses["self_ce"].mean()).backward()                  # train.py:231-232
         allreduce_mean_(self.net.backbone._grad.buf)
         self.optim.step()                                                           # train.py:233
+        return torch.cat([losses["loss_ce"].detach(), losses["self_ce"].detach(), losses["teacher_diff"].detach()])
+
+    def capture(self, example_batch):
+        """Capture one steady-state step (no teacher update) into a CUDA graph: the whole step is a fixed kernel
+        schedule, so replaying it removes ~900 launches' worth of host work per step. Steps that update the
+        teacher (every NET_MOMENTUM_ITER) still run eagerly. Call after at least one eager step."""
+        assert self.iter > 0, "run an eager step first (teacher initialisation, workspace allocation)"
+        self._static = tuple(t.clone() for t in example_batch)
+        src = tuple(t.clone() for t in example_batch)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                for d, s_ in zip(self._static, src): d.copy_(s_)
+                self._eager(self._static, False)
+        torch.cuda.current_stream().wait_stream(side)
+        for d, s_ in zip(self._static, src): d.copy_(s_)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_losses = self._eager(self._static, False)
+        self._graph = g
+        self.iter += 2
+        return g
+
+    def step(self, batch, update_teacher=None, read_losses=False):
+        """one Trainer._step_target(train=True); ``batch`` may live on the device or in pinned host memory"""
+        if update_teacher is None:
+            update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)          # train.py:294
+        if self._graph is not None and not update_teacher:
+            for d, s_ in zip(self._static, batch):
+                d.copy_(s_, non_blocking=True)                                      # H2D when ``batch`` is pinned host memory
+            self._graph.replay()
+            v = self._graph_losses
+        else:
+            if not batch[0].is_cuda:
+                batch = self.h2d(batch)
+            v = self._eager(batch, update_teacher)
         self.iter += 1
         if read_losses:
-            v = torch.cat([losses["loss_ce"].detach(), losses["self_ce"].detach(), losses["teacher_diff"].detach()])
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(v); v /= dist.get_world_size()                      # train.py:243-245
+                v = v.clone(); dist.all_reduce(v); v /= dist.get_world_size()       # train.py:243-245
             host = v.cpu()                                                          # .item() host sync (train.py:246)
             return {"loss_ce": float(host[0]), "self_ce": float(host[1]), "teacher_diff": float(host[2])}
-        return losses
+        return {"loss_ce": v[0:1], "self_ce": v[1:2], "teacher_diff": v[2:3]}
