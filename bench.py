@@ -170,15 +170,24 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)              # max over ranks
         return float(ms)
 
+    def note(msg):
+        if rank == 0:
+            print("[bench] " + msg, file=sys.stderr, flush=True)
+
+    note("first eager step (teacher init, workspace allocation)")
     run(1, False)
-    if not args.no_graph:
+    use_graph = (not args.no_graph) and world == 1      # NCCL inside a captured graph is not used: eager launches at N>1
+    if use_graph:
+        note("capturing the steady-state step into a CUDA graph")
         stepper.capture(dev_batch)
+    note("warm-up x%d" % args.warmup)
     run(args.warmup, False)
+    note("timed region x%d" % args.steps)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = L.launch_count()
+    l0 = stepper.launches
     ms = timed(args.steps, False)
-    launches = L.launch_count() - l0
+    launches = stepper.launches - l0
     sampler.stop_flag = True
     sampler.join(timeout=2)
     run(1, True)
@@ -213,7 +222,7 @@ def main():
             "config": {"workload": "ResNet-101 DeepLabv2 SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % (args.groups, GROUP_SIZE, CROP[0], CROP[1]),
                        "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world,
                        "l2": "inputs larger than L2 (>20 GB of activations per step)",
-                       "launch": "eager" if args.no_graph else "CUDA graph replay of the whole step"},
+                       "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches"},
             "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}

@@ -106,6 +106,8 @@ class TargetStepper(object):
         self._graph = None
         self._static = None
         self._graph_losses = None
+        self._graph_launches = 0
+        self.launches = 0          # kernels of libsac_b200 launched (eagerly or through graph replays) by step()
 
     def stage_host(self, batch):
         """pinned host copies of a batch (what a DataLoader with pin_memory hands to train.py:183)"""
@@ -140,8 +142,10 @@ class TargetStepper(object):
         torch.cuda.current_stream().wait_stream(side)
         for d, s_ in zip(self._static, src): d.copy_(s_)
         g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(g):
             self._graph_losses = self._eager(self._static, False)
+        self._graph_launches = L.launch_count() - n0      # kernel nodes of ours inside the graph
         self._graph = g
         self.iter += 2
         return g
@@ -154,11 +158,14 @@ class TargetStepper(object):
             for d, s_ in zip(self._static, batch):
                 d.copy_(s_, non_blocking=True)                                      # H2D when ``batch`` is pinned host memory
             self._graph.replay()
+            self.launches += self._graph_launches
             v = self._graph_losses
         else:
             if not batch[0].is_cuda:
                 batch = self.h2d(batch)
+            n0 = L.launch_count()
             v = self._eager(batch, update_teacher)
+            self.launches += L.launch_count() - n0
         self.iter += 1
         if read_losses:
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
