@@ -277,31 +277,46 @@ __global__ void maxpool_fwd_kernel(const uint16_t* __restrict__ in_hi, const uin
 __global__ void maxpool_bwd_kernel(const float* __restrict__ g_out, const uint8_t* __restrict__ idx,
                                    const uint16_t* __restrict__ in_hi, uint16_t* __restrict__ gin_hi,
                                    uint16_t* __restrict__ gin_lo, int N, int H, int W, int C, int P, int Q) {
-  const size_t total = (size_t)N * H * W * C;
+  // thread = 8 channels of one input pixel; gathers from the (at most 4) pooling windows that cover it
+  const size_t total = (size_t)N * H * W * (C / 8);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    size_t t = i / C;
+    const int cv = (int)(i % (C / 8));
+    size_t t = i / (C / 8);
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
-    float acc = 0.f;
-    if (bf16_bits_to_float(in_hi[i]) > 0.f) {
-      const int pl = (h) / 2, ph = (h + 1) / 2;       // windows p with 2p-1 <= h <= 2p+1
-      const int ql = (w) / 2, qh = (w + 1) / 2;
-      for (int p = pl; p <= ph; ++p) {
-        if (p >= P) continue;
-        const int r = h - (2 * p - 1);
-        if (r < 0 || r > 2) continue;
-        for (int q = ql; q <= qh; ++q) {
-          if (q >= Q) continue;
-          const int s = w - (2 * q - 1);
-          if (s < 0 || s > 2) continue;
-          const size_t o = (((size_t)n * P + p) * Q + q) * C + c;
-          if (idx[o] == r * 3 + s) acc += g_out[o];
+    float acc[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    unpack8f(reinterpret_cast<const uint4*>(in_hi)[i], m);
+    const int pl = h / 2, ph = (h + 1) / 2;         // windows p with 2p-1 <= h <= 2p+1
+    const int ql = w / 2, qh = (w + 1) / 2;
+    for (int p = pl; p <= ph; ++p) {
+      if (p >= P) continue;
+      const int r = h - (2 * p - 1);
+      if (r < 0 || r > 2) continue;
+      for (int q = ql; q <= qh; ++q) {
+        if (q >= Q) continue;
+        const int sft = w - (2 * q - 1);
+        if (sft < 0 || sft > 2) continue;
+        const size_t o = (((size_t)n * P + p) * Q + q) * C + cv * 8;
+        const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
+        const float4 g0 = *reinterpret_cast<const float4*>(g_out + o), g1 = *reinterpret_cast<const float4*>(g_out + o + 4);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const int tap = r * 3 + sft;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int id = ((j < 4 ? iv.x : iv.y) >> ((j & 3) * 8)) & 0xFF;
+          if (id == tap) acc[j] += gv[j];
         }
       }
     }
-    st_split(gin_hi, gin_lo, i, acc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = m[j] > 0.f ? acc[j] : 0.f;      // ReLU mask of the stem output
+    uint4 hh, ll;
+    split8(acc, hh, ll);
+    reinterpret_cast<uint4*>(gin_hi)[i] = hh;
+    reinterpret_cast<uint4*>(gin_lo)[i] = ll;
   }
 }
 
@@ -555,7 +570,8 @@ extern "C" int sacb_maxpool_fwd(const void* in_hi, const void* in_lo, void* out_
 
 extern "C" int sacb_maxpool_bwd(const float* g_out, const uint8_t* idx, const void* in_hi, void* gin_hi, void* gin_lo,
                                 int N, int H, int W, int C, int P, int Q, void* stream) {
-  const size_t total = (size_t)N * H * W * C;
+  SACB_REQUIRE(C % 8 == 0, "sacb_maxpool_bwd: C %% 8");
+  const size_t total = (size_t)N * H * W * (C / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(g_out, idx, (const uint16_t*)in_hi, (uint16_t*)gin_hi,
                                                           (uint16_t*)gin_lo, N, H, W, C, P, Q);
   LAUNCHED();

@@ -32,7 +32,7 @@ template <int BN> struct TileCfg {
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 2 * MAX_AFFINE * sizeof(float);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
 };
 
 struct GemmArgs {
@@ -45,6 +45,7 @@ struct GemmArgs {
   const uint16_t* add_hi; const uint16_t* add_lo; const uint16_t* mask_hi;
   int relu;
   uint16_t* out_hi; uint16_t* out_lo; float* out_f32; float* out_nchw;
+  float* colsum;      // optional [N_total]: += column sums of the final values (BN d(beta) of the producer unit)
 };
 
 struct WgradArgs {
@@ -98,8 +99,47 @@ SACB_DEVINL void split_pack(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// column sums over the 32 rows (lanes) of a warp for 32 columns with 31 shuffles: after the exchange steps lane L holds
+// the sum of column L
+SACB_DEVINL float warp_colsum32(const float (&v)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const bool up = lane & 16;
+    const float send = up ? v[k] : v[k + 16];
+    const float keep = up ? v[k + 16] : v[k];
+    a16[k] = keep + __shfl_xor_sync(0xffffffff, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 8;
+    const float send = up ? a16[k] : a16[k + 8];
+    const float keep = up ? a16[k + 8] : a16[k];
+    a8[k] = keep + __shfl_xor_sync(0xffffffff, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 4;
+    const float send = up ? a8[k] : a8[k + 4];
+    const float keep = up ? a8[k + 4] : a8[k];
+    a4[k] = keep + __shfl_xor_sync(0xffffffff, send, 4);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 2;
+    const float send = up ? a4[k] : a4[k + 2];
+    const float keep = up ? a4[k + 2] : a4[k];
+    a2[k] = keep + __shfl_xor_sync(0xffffffff, send, 2);
+  }
+  const bool up = lane & 1;
+  const float send = up ? a2[0] : a2[1];
+  const float keep = up ? a2[1] : a2[0];
+  return keep + __shfl_xor_sync(0xffffffff, send, 1);
+}
+
 SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
-                              uint32_t (&r)[32], int m, int c0) {
+                              float* __restrict__ s_colsum, uint32_t (&r)[32], int m, int c0, int lane) {
+  const bool valid = m < a.M_total;       // rows past M (last tile) are not loaded / stored but still join the shuffles
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -113,7 +153,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
     }
   }
-  if (a.add_f32) {
+  if (a.add_f32 && valid) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t t[8];
@@ -122,7 +162,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       for (int j = 0; j < 8; ++j) v[8 * i + j] += __uint_as_float(t[j]);
     }
   }
-  if (a.add_hi) {
+  if (a.add_hi && valid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       uint32_t h[8], l[8];
@@ -138,7 +178,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  if (a.mask_hi) {
+  if (a.mask_hi && valid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       uint32_t h[8];
@@ -149,7 +189,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       for (int j = 0; j < 16; ++j) v[16 * i + j] = fh[j] > 0.f ? v[16 * i + j] : 0.f;
     }
   }
-  if (a.out_hi) {
+  if (a.out_hi && valid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       uint32_t ph[8], pl[8];
@@ -159,7 +199,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       stg256(a.out_lo + row + 16 * i, pl);
     }
   }
-  if (a.out_f32) {
+  if (a.out_f32 && valid) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint32_t t[8];
@@ -168,7 +208,7 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       stg256(a.out_f32 + row + 8 * i, t);
     }
   }
-  if (a.out_nchw) {
+  if (a.out_nchw && valid) {
     const int pq = a.P * a.Q;
     const int n_img = m / pq;
     const int rem = m - n_img * pq;
@@ -176,6 +216,14 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (c0 + i < a.n_valid) base[(size_t)(c0 + i) * pq] = v[i];
+  }
+  if (a.colsum) {                          // uniform across the warp: every lane takes part
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    const float cs = warp_colsum32(v, lane);
+    atomicAdd(&s_colsum[c0 + lane], cs);    // per-CTA accumulator in shared memory, flushed once at kernel end
   }
 }
 
@@ -198,6 +246,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES + 256);
   float* s_shift = s_scale + MAX_AFFINE;
+  float* s_colsum = s_shift + MAX_AFFINE;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,6 +255,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
   if (a.scale) {
     for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+  }
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -306,7 +358,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
         if (ch < CHUNKS) {
           tmem_ld_wait();
           if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
-          if (m < a.M_total) epilogue_row(a, s_scale, s_shift, r[j & 1], m, n_idx * BN + ch * 32);
+          epilogue_row(a, s_scale, s_shift, s_colsum, r[j & 1], m, n_idx * BN + ch * 32, lane);
         }
       }
       tc_fence_before();
@@ -317,6 +369,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
+      const float cs = s_colsum[i];
+      if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
+    }
+  }
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -642,6 +700,8 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.add_hi = (const uint16_t*)d->add_hi; a.add_lo = (const uint16_t*)d->add_lo; a.mask_hi = (const uint16_t*)d->mask_hi;
   a.relu = d->relu;
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
+  a.colsum = d->colsum;
+  SACB_REQUIRE(d->colsum == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged column-sum size", d->K);
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
   SACB_REQUIRE(d->scale == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged affine size", d->K);
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");

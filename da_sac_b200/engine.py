@@ -346,29 +346,33 @@ class ResNet101Engine(object):
                 "sacb_aspp_unpack_wgrad")
         gout = self._tplanes("gout", M5 * asp[0].C)
         _, (th, tl) = wp.aspp()
+        # d(beta) of every BN unit = column sums of the gradient arriving at it; they are accumulated by the epilogue of
+        # the GEMM that produces that gradient (colsum=...), into one zero-filled buffer
+        self._dbeta_pool = torch.zeros(sum(s.K for s in net["specs"].values() if s.bn is not None), device=self.device)
+        self._dbeta_off = 0
+        dbeta3 = self._new_dbeta(asp[0].C)
         L.conv_gemm(gcol.hi, gcol.lo, th, tl, (N, oh, ow, ASPP_JPAD, asp[0].C, 1, 1, 1, 0), mask_hi=xlast.hi,
-                    out_hi=gout.hi, out_lo=gout.lo)
+                    out_hi=gout.hi, out_lo=gout.lo, colsum=dbeta3)
         self._tput("gcol")
         for bi in range(len(blocks) - 1, -1, -1):
             (p, c1, c2, c3, ds) = blocks[bi]
             xin = self.act[blocks[bi - 1][3].name] if bi > 0 else self.act["pool"]
             o1, o2 = self.act[c1.name], self.act[c2.name]
             M = N * c3.hout * c3.wout
-            # conv3 + bn3 (no ReLU between bn3 and the residual sum): g3 = gout
-            dbeta3 = self._dbeta(gout, M, c3.K)
+            # conv3 + bn3 (no ReLU between bn3 and the residual sum): g3 = gout, its column sums are dbeta3
             self._wgrad(flat, wp, c3, o2, gout, grad, dbeta3)
             g2 = self._tplanes("g2", M * c2.K)
+            dbeta2 = self._new_dbeta(c2.K)
             th, tl = wp.wt(c3.name)
-            L.conv_gemm(gout.hi, gout.lo, th, tl, c3.geom_dgrad(N), mask_hi=o2.hi, out_hi=g2.hi, out_lo=g2.lo)
+            L.conv_gemm(gout.hi, gout.lo, th, tl, c3.geom_dgrad(N), mask_hi=o2.hi, out_hi=g2.hi, out_lo=g2.lo, colsum=dbeta2)
             # conv2 + bn2 + relu
-            dbeta2 = self._dbeta(g2, M, c2.K)
             self._wgrad(flat, wp, c2, o1, g2, grad, dbeta2)
             g1 = self._tplanes("g1", M * c1.K)
+            dbeta1 = self._new_dbeta(c1.K)
             th, tl = wp.wt(c2.name)
-            L.conv_gemm(g2.hi, g2.lo, th, tl, c2.geom_dgrad(N), mask_hi=o1.hi, out_hi=g1.hi, out_lo=g1.lo)
+            L.conv_gemm(g2.hi, g2.lo, th, tl, c2.geom_dgrad(N), mask_hi=o1.hi, out_hi=g1.hi, out_lo=g1.lo, colsum=dbeta1)
             self._tput("g2")
             # conv1 + bn1 + relu (and the downsample branch of the first block of a layer)
-            dbeta1 = self._dbeta(g1, M, c1.K)
             self._wgrad(flat, wp, c1, xin, g1, grad, dbeta1)
             if ds is not None:
                 self._wgrad(flat, wp, ds, xin, gout, grad, dbeta3)      # d beta of the downsample BN == d beta of bn3
@@ -384,14 +388,16 @@ class ResNet101Engine(object):
                 self._tput("g1"); self._tput("gout")
                 break
             gx = self._tplanes("gx", Min * c1.C)
+            dbeta3 = self._new_dbeta(c1.C)          # d beta of the previous block's bn3 (and of its downsample BN)
             if ds is None:
                 L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_hi=gout.hi, add_lo=gout.lo, mask_hi=xin.hi,
-                            out_hi=gx.hi, out_lo=gx.lo)
+                            out_hi=gx.hi, out_lo=gx.lo, colsum=dbeta3)
             elif c1.stride == 1:
                 thd, tld = wp.wt(ds.name)
                 tmp = self.fpool.get("tmp", Min * c1.C)
                 L.conv_gemm(gout.hi, gout.lo, thd, tld, ds.geom_dgrad(N), out_f32=tmp)
-                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_f32=tmp, mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo)
+                L.conv_gemm(g1.hi, g1.lo, th1, tl1, c1.geom_dgrad(N), add_f32=tmp, mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo,
+                            colsum=dbeta3)
                 self.fpool.put("tmp")
             else:
                 # stride-2 1x1 convs: compact data gradients on the 65x65 grid, scattered to the even pixels
@@ -401,6 +407,7 @@ class ResNet101Engine(object):
                 L.conv_gemm(gout.hi, gout.lo, thd, tld, ds.geom_dgrad(N), out_f32=tb)
                 L.check(lib.sacb_scatter2_mask_split(L.ptr(ta), L.ptr(tb), L.ptr(xin.hi), L.ptr(gx.hi), L.ptr(gx.lo),
                                                      N, c1.hin, c1.win, c1.C, c1.hout, c1.wout, st), "sacb_scatter2_mask_split")
+                L.check(lib.sacb_colsum(L.ptr(gx.hi), L.ptr(gx.lo), L.ptr(dbeta3), C.c_int64(Min), c1.C, st), "sacb_colsum")
                 self.fpool.put("tmp"); self.fpool.put("tmp2")
             self._tput("g1"); self._tput("gout")
             # rename gx -> gout for the next (earlier) block
@@ -419,6 +426,11 @@ class ResNet101Engine(object):
         dwraw = self.stem_dw
         L.check(lib.sacb_stem_unpack_wgrad(L.ptr(parts), splits, L.ptr(dwraw), st), "sacb_stem_unpack_wgrad")
         self._finalize(flat, wp, stem, dwraw, grad, dbeta, C_eff=147, RS=1)
+
+    def _new_dbeta(self, K):
+        o = self._dbeta_off
+        self._dbeta_off = o + K
+        return self._dbeta_pool[o:o + K]
 
     def _dbeta(self, g, M, K):
         d = torch.zeros(K, device=self.device)

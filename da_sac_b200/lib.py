@@ -68,7 +68,7 @@ class ConvGemm(C.Structure):
                 ("x_hi", _vp), ("x_lo", _vp), ("wt_hi", _vp), ("wt_lo", _vp),
                 ("scale", _vp), ("shift", _vp), ("add_f32", _vp), ("add_hi", _vp), ("add_lo", _vp), ("mask_hi", _vp),
                 ("relu", C.c_int32),
-                ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp)]
+                ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp), ("colsum", _vp)]
 
 
 class ConvWgrad(C.Structure):
@@ -134,13 +134,13 @@ def conv_out_hw(H, W, R, stride, dil, pad):
 
 
 def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift=None, add_f32=None, add_hi=None,
-              add_lo=None, mask_hi=None, relu=False, out_hi=None, out_lo=None, out_f32=None, out_nchw=None):
+              add_lo=None, mask_hi=None, relu=False, out_hi=None, out_lo=None, out_f32=None, out_nchw=None, colsum=None):
     """geom = (N, H, W, C, K, R, stride, dil, pad)"""
     N, H, W, Cc, K, R, s, d, p = geom
     P, Q = conv_out_hw(H, W, R, s, d, p)
     desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                     ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
-                    ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw))
+                    ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw), ptr(colsum))
     kind = "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))
     flops = 2.0 * N * P * Q * (K if k_valid is None else k_valid) * Cc * R * R
     _prof_wrap(kind, flops, lambda: check(lib().sacb_conv_gemm(C.byref(desc), stream()), "sacb_conv_gemm"))

@@ -47,6 +47,7 @@ int64_t sacb_launch_count(void);
  *   v          = max(v, 0)                             (if relu)
  *   v          = mask_hi[m*K+k] > 0 ? v : 0            (if mask_hi; ReLU backward)
  *   out_hi/out_lo[m*K+k] = split(v); out_f32[m*K+k] = v; out_nchw[((n*k_valid+k)*P+p)*Q+q] = v
+ *   colsum[k] += sum_m v                               (if colsum; caller zero-fills; fp32 atomics, one per CTA and k)
  * with m = (n*P + p)*Q + q.                                                          */
 typedef struct SacbConvGemm {
   uint32_t size;              /* sizeof(SacbConvGemm), ABI versioning */
@@ -65,6 +66,7 @@ typedef struct SacbConvGemm {
   void* out_hi; void* out_lo;             /* bf16 [M,K] or NULL */
   float* out_f32;                         /* [M,K] or NULL */
   float* out_nchw;                        /* [N,k_valid,P,Q] or NULL */
+  float* colsum;                          /* [K] or NULL: BN d(beta) of the unit that consumes this gradient */
 } SacbConvGemm;
 int sacb_conv_gemm(const SacbConvGemm* d, void* stream);
 

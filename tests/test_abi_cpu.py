@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header_layout():
     from da_sac_b200 import lib
     # natural alignment on LP64: 14 x int32 then pointers
-    assert ctypes.sizeof(lib.ConvGemm) == 14 * 4 + 10 * 8 + 8 + 4 * 8
+    assert ctypes.sizeof(lib.ConvGemm) == 14 * 4 + 10 * 8 + 8 + 5 * 8
     assert ctypes.sizeof(lib.ConvWgrad) == 14 * 4 + 5 * 8 + 8
 
 

@@ -95,9 +95,12 @@ def test_conv_fprop_mask_and_add_f32():
     ref = (F.conv2d(x.double(), w.double()).permute(0, 2, 3, 1) + add.double()) * (act > 0)
     xh, xl = split(nhwc(x)); wh, wl = wt_planes(w); mh, _ = split(act)
     out = torch.empty(N, H, W, K, device="cuda")
-    L.conv_gemm(xh, xl, wh, wl, geom, add_f32=add, mask_hi=mh, out_f32=out)
+    cs = torch.zeros(K, device="cuda")
+    L.conv_gemm(xh, xl, wh, wl, geom, add_f32=add, mask_hi=mh, out_f32=out, colsum=cs)
     torch.cuda.synchronize()
     assert relerr(out, ref) < TOL
+    # fused column sums (BN d beta) over all rows, including the ragged last tile (578 rows = 4.5 tiles)
+    assert relerr(cs, ref.sum((0, 1, 2))) < 1e-5
 
 
 def test_conv_aspp_head_nchw():
