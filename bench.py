@@ -39,6 +39,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.power = []
         self.max_mhz = None
 
     def run(self):
@@ -50,6 +51,10 @@ class ClockSampler(threading.Thread):
             names = {getattr(nv, n): n for n in dir(nv) if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason")}
             while not self.stop_flag:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 except Exception:
@@ -63,7 +68,9 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        p = sorted(self.power)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_median": p[len(p) // 2] if p else None, "power_w_max": p[-1] if p else None, "samples": len(s)}
 
 
 def run_reference(args, rank):

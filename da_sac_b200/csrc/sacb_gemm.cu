@@ -13,6 +13,7 @@
 #include <atomic>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
 #include "sacb_common.cuh"
 #include "../../include/sacb.h"
 
@@ -30,7 +31,7 @@ constexpr uint32_t A_BYTES = BM * BK * 2;   // one bf16 plane of the 128x64 (or 
 template <int BN> struct TileCfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);
+  static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : (BN == 64 ? 4 : 5));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
 };
@@ -137,8 +138,50 @@ SACB_DEVINL float warp_colsum32(const float (&v)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffff, send, 1);
 }
 
+// 4x4 transpose of 32-byte pieces among the 4 lanes of a quad-of-lanes (lanes 4g..4g+3): on entry lane 4g+i holds pieces
+// 0..3 (= 4 x 32 B = 64 consecutive bf16 channels) of ITS row; on exit it holds piece i of rows 4g+0..4g+3, so that a
+// warp-wide 256-bit store writes 8 rows x one full 128-byte line instead of touching 32 different lines.
+SACB_DEVINL void transpose4_pieces(uint32_t (&p)[4][8], int lane) {
+  const bool odd = lane & 1, hi2 = lane & 2;
+#pragma unroll
+  for (int a2 = 0; a2 < 2; ++a2) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t send = odd ? p[2 * a2][w] : p[2 * a2 + 1][w];
+      const uint32_t recv = __shfl_xor_sync(0xffffffff, send, 1);
+      if (odd) p[2 * a2][w] = recv; else p[2 * a2 + 1][w] = recv;
+    }
+  }
+  // now p[2a+b] = piece (2a + (lane&1)) of row (pair base + b); exchange the a-halves across lanes xor 2
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t send = hi2 ? p[b][w] : p[2 + b][w];
+      const uint32_t recv = __shfl_xor_sync(0xffffffff, send, 2);
+      // lanes 0,1 keep a=0 (rows 0,1) and receive rows 2,3; lanes 2,3 keep a=1 (rows 2,3) and receive rows 0,1
+      if (hi2) p[b][w] = recv; else p[2 + b][w] = recv;
+    }
+  }
+}
+
+// store one bf16 plane of a 32-row x 64-channel warp tile from transposed pieces: instruction k covers rows 4g+k
+SACB_DEVINL void store_plane_transposed(uint16_t* __restrict__ plane, uint32_t (&p)[4][8], int m_warp0, int c0, int lane,
+                                        int M_total, int ld) {
+  const int g = lane >> 2, i = lane & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = m_warp0 + 4 * g + k;
+    if (m < M_total) stg256(plane + (size_t)m * ld + c0 + 16 * i, p[k]);
+  }
+}
+
+// DEFER_E < 0: store the planes directly (one row per lane).  DEFER_E = 0/1: write the packed words into pieces
+// [2*DEFER_E, 2*DEFER_E+1] of dh/dl for the line-coalesced (transposed) store done by the caller.
+template <int DEFER_E>
 SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
-                              float* __restrict__ s_colsum, uint32_t (&r)[32], int m, int c0, int lane) {
+                              float* __restrict__ s_colsum, uint32_t (&r)[32], int m, int c0, int lane,
+                              uint32_t (&dh)[4][8], uint32_t (&dl)[4][8]) {
   const bool valid = m < a.M_total;       // rows past M (last tile) are not loaded / stored but still join the shuffles
   float v[32];
 #pragma unroll
@@ -189,14 +232,22 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       for (int j = 0; j < 16; ++j) v[16 * i + j] = fh[j] > 0.f ? v[16 * i + j] : 0.f;
     }
   }
-  if (a.out_hi && valid) {
+  if (a.out_hi) {
+    if constexpr (DEFER_E >= 0) {          // packed words go back to the caller for the line-coalesced (transposed) store
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint32_t ph[8], pl[8];
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) split_pack(v[16 * i + 2 * j], v[16 * i + 2 * j + 1], ph[j], pl[j]);
-      stg256(a.out_hi + row + 16 * i, ph);
-      stg256(a.out_lo + row + 16 * i, pl);
+        for (int j = 0; j < 8; ++j)
+          split_pack(v[16 * i + 2 * j], v[16 * i + 2 * j + 1], dh[2 * DEFER_E + i][j], dl[2 * DEFER_E + i][j]);
+    } else if (valid) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_pack(v[16 * i + 2 * j], v[16 * i + 2 * j + 1], ph[j], pl[j]);
+        stg256(a.out_hi + row + 16 * i, ph);
+        stg256(a.out_lo + row + 16 * i, pl);
+      }
     }
   }
   if (a.out_f32 && valid) {
@@ -230,8 +281,11 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
 // ------------------------------------------------------------------------------------------------
 // fprop / dgrad:  D[pixels, K] = sum_{taps, c} im2col(X)[pixels, c] * Wt[tap][K][c]     (both operands K-major)
 // ------------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// CL = 1: one CTA per output tile.  CL = 2: a cluster of two CTAs works on two adjacent N tiles of the same M tile; the
+// activation (A) tile they share is fetched once -- each CTA loads half of its pixels and TMA-multicasts them into both
+// CTAs' shared memory -- which cuts the L2->SM traffic per MMA from 64 KB to 48 KB per k-block (the binding resource).
+template <int BN, int CL>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> at most 168 registers/thread
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                  const GemmArgs a) {
@@ -261,7 +315,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      // a stage may be refilled once every CTA of the cluster has consumed it (the refill multicasts into all of them)
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
       fence_barrier_init();
     }
@@ -270,18 +325,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();       // peer barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = a.num_m_tiles * a.num_n_tiles;
   const int k_blocks = a.taps * a.kc_blocks;
+  // work unit = (m tile, group of CL adjacent n tiles); the CTAs of a cluster walk the same unit sequence
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = CL > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_step = CL > 1 ? (int)cluster_count_x() : (int)gridDim.x;
+  const int n_groups = a.num_n_tiles / CL;
+  const int total_units = a.num_m_tiles * n_groups;
 
   if (warp == 0) {
     if (lane == 0) {
       PipeState ps{0, 0};
       const int pq = a.P * a.Q;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_idx = tile / a.num_n_tiles, n_idx = tile - m_idx * a.num_n_tiles;
-        const int m0 = m_idx * BM;
+      constexpr int HALF_ROWS = BM / CL;                      // pixels of the A tile this CTA fetches
+      constexpr uint32_t HALF_BYTES = A_BYTES / CL;
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const int m_idx = unit / n_groups, n_idx = (unit - m_idx * n_groups) * CL + crank;
+        const int m0 = m_idx * BM + crank * HALF_ROWS;
         const int n_img = m0 / pq;
         const int rem = m0 - n_img * pq;
         const int p = rem / a.Q, q = rem - p * a.Q;
@@ -293,8 +356,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
             mbar_expect_tx(&full_bar[ps.stage], Cfg::STAGE_BYTES);
-            tma_load_im2col(&tmAh, &full_bar[ps.stage], st, cb * BK, w0, h0, n_img, ow, oh);
-            tma_load_im2col(&tmAl, &full_bar[ps.stage], st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            if constexpr (CL == 1) {
+              tma_load_im2col(&tmAh, &full_bar[ps.stage], st, cb * BK, w0, h0, n_img, ow, oh);
+              tma_load_im2col(&tmAl, &full_bar[ps.stage], st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            } else {
+              tma_load_im2col_mc(&tmAh, &full_bar[ps.stage], st + crank * HALF_BYTES, cb * BK, w0, h0, n_img, ow, oh,
+                                 (uint16_t)((1u << CL) - 1));
+              tma_load_im2col_mc(&tmAl, &full_bar[ps.stage], st + A_BYTES + crank * HALF_BYTES, cb * BK, w0, h0, n_img, ow, oh,
+                                 (uint16_t)((1u << CL) - 1));
+            }
             tma_load_3d(&tmBh, &full_bar[ps.stage], st + 2 * A_BYTES, cb * BK, n_idx * BN, tap);
             tma_load_3d(&tmBl, &full_bar[ps.stage], st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, n_idx * BN, tap);
             ps.advance<STAGES>();
@@ -307,7 +377,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
       PipeState ps{0, 0};
       int acc = 0; uint32_t acc_phase = 0;
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -330,7 +400,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
             accumulate = 1;
           }
-          tc_commit(&empty_bar[ps.stage]);
+          if constexpr (CL == 1) tc_commit(&empty_bar[ps.stage]);
+          else tc_commit_mc(&empty_bar[ps.stage], (uint16_t)((1u << CL) - 1));
           ps.advance<STAGES>();
         }
         tc_commit(&tfull_bar[acc]);
@@ -343,22 +414,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     constexpr int CHUNKS = BN / 32;
     constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_idx = tile / a.num_n_tiles, n_idx = tile - m_idx * a.num_n_tiles;
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
+      const int m_idx = unit / n_groups, n_idx = (unit - m_idx * n_groups) * CL + crank;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int m = m_idx * BM + quad * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      uint32_t r[2][32];
       const int ch0 = half * MY_CHUNKS;          // adjacent chunks: one warp covers MY_CHUNKS*32 contiguous channels
-      if (ch0 < CHUNKS) tmem_ld32(tbase + ch0 * 32, r[0]);
+      if constexpr (MY_CHUNKS % 2 == 0) {
+        // chunk pairs (64 channels = one 128-byte line per row and plane): math per chunk, stores transposed per pair
+        const int m_warp0 = m_idx * BM + quad * 32;
 #pragma unroll
-      for (int j = 0; j < MY_CHUNKS; ++j) {
-        const int ch = ch0 + j;
-        if (ch < CHUNKS) {
-          tmem_ld_wait();
-          if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
-          epilogue_row(a, s_scale, s_shift, s_colsum, r[j & 1], m, n_idx * BN + ch * 32, lane);
+        for (int jp = 0; jp < MY_CHUNKS / 2; ++jp) {
+          uint32_t ph[4][8], pl[4][8];
+          {
+            const int ch = ch0 + 2 * jp;
+            uint32_t r[32];                      // (register budget: 168/thread, so no TMEM-load double buffering here)
+            tmem_ld32(tbase + ch * 32, r);
+            tmem_ld_wait();
+            epilogue_row<0>(a, s_scale, s_shift, s_colsum, r, m, n_idx * BN + ch * 32, lane, ph, pl);
+            tmem_ld32(tbase + (ch + 1) * 32, r);
+            tmem_ld_wait();
+            epilogue_row<1>(a, s_scale, s_shift, s_colsum, r, m, n_idx * BN + (ch + 1) * 32, lane, ph, pl);
+          }
+          if (a.out_hi) {
+            const int c0 = n_idx * BN + (ch0 + 2 * jp) * 32;
+            transpose4_pieces(ph, lane);
+            store_plane_transposed(a.out_hi, ph, m_warp0, c0, lane, a.M_total, a.N_total);
+            transpose4_pieces(pl, lane);
+            store_plane_transposed(a.out_lo, pl, m_warp0, c0, lane, a.M_total, a.N_total);
+          }
+        }
+      } else {
+        uint32_t r[2][32];
+        if (ch0 < CHUNKS) tmem_ld32(tbase + ch0 * 32, r[0]);
+#pragma unroll
+        for (int j = 0; j < MY_CHUNKS; ++j) {
+          const int ch = ch0 + j;
+          if (ch < CHUNKS) {
+            tmem_ld_wait();
+            if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
+            uint32_t dh[4][8], dl[4][8];       // unused in the direct-store path
+            epilogue_row<-1>(a, s_scale, s_shift, s_colsum, r[j & 1], m, n_idx * BN + ch * 32, lane, dh, dl);
+          }
         }
       }
       tc_fence_before();
@@ -369,6 +467,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();       // nobody exits while a peer may still multicast / arrive into its smem
   if (a.colsum) {
     for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
       const float cs = s_colsum[i];
@@ -384,7 +483,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
 //   swap=1: rows = input channels (X, im2col map), cols = output channels (G, tiled map)
 // work item = (row tile, col tile, filter tap, K split); results accumulated with fp32 atomics.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                   const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
@@ -407,7 +506,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
       fence_barrier_init();
     }
@@ -416,15 +515,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_work = a.m_tiles * a.n_tiles * a.taps * a.splits;
+  // CL = 2: the two CTAs of a cluster take two adjacent column tiles of the same (row tile, tap, split); the row
+  // operand (two 64-channel boxes per plane) is fetched once, one box per CTA, and TMA-multicast to both.
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int unit0 = CL > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int unit_step = CL > 1 ? (int)cluster_count_x() : (int)gridDim.x;
+  const int n_groups = a.n_tiles / CL;
+  const int total_work = a.m_tiles * n_groups * a.taps * a.splits;
 
-  // work -> (split, tap, n_idx, m_idx); split fastest so that one (tile, tap)'s partial sums are in flight together
+  // work -> (split, tap, n group, m_idx); split fastest so that one (tile, tap)'s partial sums are in flight together
   auto decode = [&](int wk, int& m_idx, int& n_idx, int& tap, int& kb0, int& kb1) {
     const int split = wk % a.splits; wk /= a.splits;
     tap = wk % a.taps; wk /= a.taps;
-    n_idx = wk % a.n_tiles; m_idx = wk / a.n_tiles;
+    n_idx = (wk % n_groups) * CL + crank; m_idx = wk / n_groups;
     kb0 = split * a.blocks_per_split;
     kb1 = min(kb0 + a.blocks_per_split, a.num_pix_blocks);
   };
@@ -433,7 +539,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
     if (lane == 0) {
       PipeState ps{0, 0};
       const int pq = a.P * a.Q;
-      for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+      for (int wk = unit0; wk < total_work; wk += unit_step) {
         int m_idx, n_idx, tap, kb0, kb1;
         decode(wk, m_idx, n_idx, tap, kb0, kb1);
         const int r = tap / a.S, s = tap - r * a.S;
@@ -450,11 +556,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
           mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           uint8_t* sa_hi = st; uint8_t* sa_lo = st + A_BYTES;
           uint8_t* sb_hi = st + 2 * A_BYTES; uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
+          constexpr uint16_t MC = (uint16_t)((1u << CL) - 1);
           if (!a.swap) {
+            if constexpr (CL == 1) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              tma_load_2d(&tmGh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, m0);
-              tma_load_2d(&tmGl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+              for (int j = 0; j < 2; ++j) {
+                tma_load_2d(&tmGh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+                tma_load_2d(&tmGl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+              }
+            } else {
+              tma_load_2d_mc(&tmGh, fb, sa_hi + crank * BOX_BYTES, m_idx * BM + crank * 64, m0, MC);
+              tma_load_2d_mc(&tmGl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, m0, MC);
             }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
@@ -462,10 +574,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
               tma_load_im2col(&tmXl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
             }
           } else {
+            if constexpr (CL == 1) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              tma_load_im2col(&tmXh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
-              tma_load_im2col(&tmXl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+              for (int j = 0; j < 2; ++j) {
+                tma_load_im2col(&tmXh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+                tma_load_im2col(&tmXl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+              }
+            } else {
+              tma_load_im2col_mc(&tmXh, fb, sa_hi + crank * BOX_BYTES, m_idx * BM + crank * 64, w0, h0, n_img, ow, oh, MC);
+              tma_load_im2col_mc(&tmXl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, w0, h0, n_img, ow, oh, MC);
             }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
@@ -482,7 +599,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
       PipeState ps{0, 0};
       int acc = 0; uint32_t acc_phase = 0;
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);
-      for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+      for (int wk = unit0; wk < total_work; wk += unit_step) {
         int m_idx, n_idx, tap, kb0, kb1;
         decode(wk, m_idx, n_idx, tap, kb0, kb1);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -509,7 +626,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
             tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
             accumulate = 1;
           }
-          tc_commit(&empty_bar[ps.stage]);
+          if constexpr (CL == 1) tc_commit(&empty_bar[ps.stage]);
+          else tc_commit_mc(&empty_bar[ps.stage], (uint16_t)((1u << CL) - 1));
           ps.advance<STAGES>();
         }
         tc_commit(&tfull_bar[acc]);
@@ -521,7 +639,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
     const int half = (warp - 2) >> 2;
     constexpr int CHUNKS = BN / 32;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int wk = blockIdx.x; wk < total_work; wk += gridDim.x) {
+    for (int wk = unit0; wk < total_work; wk += unit_step) {
       int m_idx, n_idx, tap, kb0, kb1;
       decode(wk, m_idx, n_idx, tap, kb0, kb1);
       const int split = wk % a.splits;
@@ -559,6 +677,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
@@ -579,6 +698,10 @@ static int g_driver_version = 0;
 static int g_num_sms = 0;
 static std::once_flag g_once;
 static int g_init_status = 0;
+// SACB_CLUSTER=1: pair CTAs into clusters of 2 that share one operand tile by TMA multicast. Measured (profiles/): no gain,
+// because the limit is the per-SM shared-memory fill rate, not L2 bandwidth -- so it is off by default.
+static bool g_cluster = false;
+static bool g_no_bn256 = false;       // SACB_NO_BN256=1: cap the N tile at 128 (A/B comparison)
 
 static void init_once() {
   cudaDriverEntryPointQueryResult q;
@@ -593,6 +716,8 @@ static void init_once() {
   }
   g_im2col = reinterpret_cast<EncodeIm2colFn>(f);
   cudaDriverGetVersion(&g_driver_version);
+  if (const char* e = getenv("SACB_CLUSTER")) g_cluster = (e[0] == '1');
+  if (const char* e = getenv("SACB_NO_BN256")) g_no_bn256 = (e[0] == '1');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -634,37 +759,47 @@ static int make_tiled_map(CUtensorMap* m, const void* base, int rank, const cuui
   return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const GemmArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TileCfg<BN>::SMEM));
     attr_set = true;
   }
-  const int tiles = a.num_m_tiles * a.num_n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  conv_gemm_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, st>>>(ah, al, bh, bl, a);
+  const int units = a.num_m_tiles * (a.num_n_tiles / CL);
+  int grid = units * CL < g_num_sms ? units * CL : (g_num_sms / CL) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = TileCfg<BN>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, ah, al, bh, bl, a));
   g_launches++;
-  SACB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                         const WgradArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TileCfg<BN>::SMEM));
     attr_set = true;
   }
-  const int work = a.m_tiles * a.n_tiles * a.taps * a.splits;
-  const int grid = work < g_num_sms ? work : g_num_sms;
-  conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, TileCfg<BN>::SMEM, st>>>(gh, gl, xh, xl, a);
+  const int work = a.m_tiles * (a.n_tiles / CL) * a.taps * a.splits;
+  const int grid = work * CL < g_num_sms ? work * CL : (g_num_sms / CL) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = TileCfg<BN>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, CL>, gh, gl, xh, xl, a));
   g_launches++;
-  SACB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -682,10 +817,15 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   const int Q = (d->W + 2 * d->pad - (d->S - 1) * d->dil - 1) / d->stride + 1;
   SACB_REQUIRE(P == d->P && Q == d->Q, "sacb_conv_gemm: P,Q (%d,%d) inconsistent with geometry (%d,%d)", d->P, d->Q, P, Q);
   SACB_REQUIRE(d->pad <= 128 && (d->R - 1) * d->dil <= 255, "sacb_conv_gemm: pad/dilation outside im2col TMA limits");
-  const int BN = (d->K % 128 == 0) ? 128 : (d->K % 64 == 0 ? 64 : 32);
+  // Shared-memory bandwidth (128 B/clk/SM) is the binding resource of a single-CTA SS-mode MMA pipeline: per k16 step the
+  // tensor core reads A (4 KB) + B (BN*32 B) from smem while TMA writes the next stage into it. N = 256 lowers the total from
+  // 213 to 158 B/clk per MMA-clk; it is used when it still leaves >= 2 N tiles (measured: profiles/conv_shapes_r1*.txt).
+  const int BN = (d->K % 256 == 0 && d->K >= 512 && !g_no_bn256) ? 256 : (d->K % 128 == 0) ? 128 : (d->K % 64 == 0 ? 64 : 32);
+  // cluster of 2 (A tile shared by TMA multicast) whenever there are at least two N tiles to pair up
+  const int CL = (BN == 128 && (d->K / BN) % 2 == 0 && g_cluster) ? 2 : 1;
   CUtensorMap ah, al, bh, bl;
-  if (int e = make_im2col_map(&ah, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM)) return e;
-  if (int e = make_im2col_map(&al, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM)) return e;
+  if (int e = make_im2col_map(&ah, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
+  if (int e = make_im2col_map(&al, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
   cuuint64_t wd[3] = {(cuuint64_t)d->C, (cuuint64_t)d->K, (cuuint64_t)(d->R * d->S)};
   cuuint64_t ws[2] = {(cuuint64_t)d->C * 2, (cuuint64_t)d->C * d->K * 2};
   cuuint32_t wb[3] = {64, (cuuint32_t)BN, 1};
@@ -707,9 +847,10 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
-    case 128: return launch_gemm<128>(ah, al, bh, bl, a, st);
-    case 64: return launch_gemm<64>(ah, al, bh, bl, a, st);
-    default: return launch_gemm<32>(ah, al, bh, bl, a, st);
+    case 256: return launch_gemm<256, 1>(ah, al, bh, bl, a, st);
+    case 128: return CL == 2 ? launch_gemm<128, 2>(ah, al, bh, bl, a, st) : launch_gemm<128, 1>(ah, al, bh, bl, a, st);
+    case 64: return launch_gemm<64, 1>(ah, al, bh, bl, a, st);
+    default: return launch_gemm<32, 1>(ah, al, bh, bl, a, st);
   }
 }
 
@@ -728,7 +869,7 @@ static int plan_wgrad(const SacbConvWgrad* d, WgradArgs& a, int& BN) {
   a.dw = d->dw;
   // few valid output channels: put the wide input-channel dim on the 128 TMEM lanes
   a.swap = (d->k_valid <= 64 && d->C >= 128) ? 1 : 0;
-  if (!a.swap) { BN = (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
+  if (!a.swap) { BN = (d->C % 256 == 0 && !g_no_bn256) ? 256 : (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
   else { BN = 64; a.m_tiles = (d->C + BM - 1) / BM; a.n_tiles = d->K / 64; }
   int splits = d->splits;
   if (splits <= 0) {
@@ -763,6 +904,8 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
   if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
   if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 128) return launch_wgrad<128>(gh, gl, xh, xl, a, st);
-  return launch_wgrad<64>(gh, gl, xh, xl, a, st);
+  const bool pair = (a.n_tiles % 2 == 0) && g_cluster && BN != 256;     // two adjacent column tiles share the row operand
+  if (BN == 256) return launch_wgrad<256, 1>(gh, gl, xh, xl, a, st);
+  if (BN == 128) return pair ? launch_wgrad<128, 2>(gh, gl, xh, xl, a, st) : launch_wgrad<128, 1>(gh, gl, xh, xl, a, st);
+  return pair ? launch_wgrad<64, 2>(gh, gl, xh, xl, a, st) : launch_wgrad<64, 1>(gh, gl, xh, xl, a, st);
 }

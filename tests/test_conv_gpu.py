@@ -41,6 +41,8 @@ CASES = [
     (2, 17, 17, 512, 256, 1, 1, 1, 0),
     (1, 65, 65, 128, 128, 3, 1, 4, 4),
     (2, 20, 31, 64, 64, 3, 1, 1, 1),
+    (2, 20, 31, 128, 512, 1, 1, 1, 0),      # 4 N tiles -> cluster of 2 with multicast A, ragged last M tile
+    (1, 65, 65, 256, 256, 3, 1, 2, 2),      # 2 N tiles, 3x3 dilated, 33.01 M tiles
 ]
 
 
@@ -126,6 +128,8 @@ WG_CASES = [
     (3, 33, 33, 256, 128, 3, 1, 2, 2),
     (2, 33, 33, 64, 128, 1, 2, 1, 0),
     (2, 33, 33, 256, 64, 3, 1, 6, 6),     # ASPP-like: 19 valid output channels -> swapped roles
+    (2, 33, 33, 256, 128, 3, 1, 6, 6),    # swapped roles with two column tiles (cluster path)
+    (2, 17, 17, 512, 256, 1, 1, 1, 0),    # 4 column tiles -> clusters of 2 share the G operand
 ]
 
 
