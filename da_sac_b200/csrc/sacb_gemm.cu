@@ -278,6 +278,57 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
   }
 }
 
+// Epilogue of one 128-row x BN-column accumulator tile held in this CTA's TMEM at column `tcol0`.
+// quad = TMEM lane quadrant of the calling warp, half = which half of the column chunks it owns.
+template <int BN>
+SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
+                               float* __restrict__ s_colsum, uint32_t tcol0, int m_row0, int n_col0, int quad, int half,
+                               int lane) {
+  constexpr int CHUNKS = BN / 32;
+  constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
+  const int m = m_row0 + quad * 32 + lane;
+  const uint32_t tbase = tcol0 + ((uint32_t)(quad * 32) << 16);
+  const int ch0 = half * MY_CHUNKS;          // adjacent chunks: one warp covers MY_CHUNKS*32 contiguous channels
+  if constexpr (MY_CHUNKS % 2 == 0) {
+    // chunk pairs (64 channels = one 128-byte line per row and plane): math per chunk, stores transposed per pair
+    const int m_warp0 = m_row0 + quad * 32;
+#pragma unroll
+    for (int jp = 0; jp < MY_CHUNKS / 2; ++jp) {
+      uint32_t ph[4][8], pl[4][8];
+      {
+        const int ch = ch0 + 2 * jp;
+        uint32_t r[32];                      // (register budget: 168/thread, so no TMEM-load double buffering here)
+        tmem_ld32(tbase + ch * 32, r);
+        tmem_ld_wait();
+        epilogue_row<0>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + ch * 32, lane, ph, pl);
+        tmem_ld32(tbase + (ch + 1) * 32, r);
+        tmem_ld_wait();
+        epilogue_row<1>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + (ch + 1) * 32, lane, ph, pl);
+      }
+      if (a.out_hi) {
+        const int c0 = n_col0 + (ch0 + 2 * jp) * 32;
+        transpose4_pieces(ph, lane);
+        store_plane_transposed(a.out_hi, ph, m_warp0, c0, lane, a.M_total, a.N_total);
+        transpose4_pieces(pl, lane);
+        store_plane_transposed(a.out_lo, pl, m_warp0, c0, lane, a.M_total, a.N_total);
+      }
+    }
+  } else {
+    uint32_t r[2][32];
+    if (ch0 < CHUNKS) tmem_ld32(tbase + ch0 * 32, r[0]);
+#pragma unroll
+    for (int j = 0; j < MY_CHUNKS; ++j) {
+      const int ch = ch0 + j;
+      if (ch < CHUNKS) {
+        tmem_ld_wait();
+        if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
+        uint32_t dh[4][8], dl[4][8];       // unused in the direct-store path
+        epilogue_row<-1>(a, s_scale, s_shift, s_colsum, r[j & 1], m, n_col0 + ch * 32, lane, dh, dl);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fprop / dgrad:  D[pixels, K] = sum_{taps, c} im2col(X)[pixels, c] * Wt[tap][K][c]     (both operands K-major)
 // ------------------------------------------------------------------------------------------------
@@ -411,54 +462,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   } else {
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int half = (warp - 2) >> 2;          // the two warps of a quadrant split the column chunks
-    constexpr int CHUNKS = BN / 32;
-    constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int m_idx = unit / n_groups, n_idx = (unit - m_idx * n_groups) * CL + crank;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int m = m_idx * BM + quad * 32 + lane;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const int ch0 = half * MY_CHUNKS;          // adjacent chunks: one warp covers MY_CHUNKS*32 contiguous channels
-      if constexpr (MY_CHUNKS % 2 == 0) {
-        // chunk pairs (64 channels = one 128-byte line per row and plane): math per chunk, stores transposed per pair
-        const int m_warp0 = m_idx * BM + quad * 32;
-#pragma unroll
-        for (int jp = 0; jp < MY_CHUNKS / 2; ++jp) {
-          uint32_t ph[4][8], pl[4][8];
-          {
-            const int ch = ch0 + 2 * jp;
-            uint32_t r[32];                      // (register budget: 168/thread, so no TMEM-load double buffering here)
-            tmem_ld32(tbase + ch * 32, r);
-            tmem_ld_wait();
-            epilogue_row<0>(a, s_scale, s_shift, s_colsum, r, m, n_idx * BN + ch * 32, lane, ph, pl);
-            tmem_ld32(tbase + (ch + 1) * 32, r);
-            tmem_ld_wait();
-            epilogue_row<1>(a, s_scale, s_shift, s_colsum, r, m, n_idx * BN + (ch + 1) * 32, lane, ph, pl);
-          }
-          if (a.out_hi) {
-            const int c0 = n_idx * BN + (ch0 + 2 * jp) * 32;
-            transpose4_pieces(ph, lane);
-            store_plane_transposed(a.out_hi, ph, m_warp0, c0, lane, a.M_total, a.N_total);
-            transpose4_pieces(pl, lane);
-            store_plane_transposed(a.out_lo, pl, m_warp0, c0, lane, a.M_total, a.N_total);
-          }
-        }
-      } else {
-        uint32_t r[2][32];
-        if (ch0 < CHUNKS) tmem_ld32(tbase + ch0 * 32, r[0]);
-#pragma unroll
-        for (int j = 0; j < MY_CHUNKS; ++j) {
-          const int ch = ch0 + j;
-          if (ch < CHUNKS) {
-            tmem_ld_wait();
-            if (j + 1 < MY_CHUNKS && ch + 1 < CHUNKS) tmem_ld32(tbase + (ch + 1) * 32, r[(j + 1) & 1]);
-            uint32_t dh[4][8], dl[4][8];       // unused in the direct-store path
-            epilogue_row<-1>(a, s_scale, s_shift, s_colsum, r[j & 1], m, n_idx * BN + ch * 32, lane, dh, dl);
-          }
-        }
-      }
+      epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * BM, n_idx * BN, quad, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -475,6 +484,212 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
     }
   }
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop / dgrad on CTA PAIRS (tcgen05 cta_group::2):  one 256 x 256 output tile per pair.
+// Each CTA of the pair owns 128 rows of A and 128 of the 256 N rows of B in its own shared memory; the MMA (issued
+// by the leader CTA only, M = 256) reads A from both CTAs and B halves from both, so every CTA stages 64 KB per k-block
+// for twice the math of the single-CTA 128x128 tile: shared-memory traffic per MMA-clock drops from 213 to ~106 B/clk
+// (limit 128 B/clk/SM), which is what lets the tensor pipe run flat out.
+// Barrier protocol: both producers signal the LEADER's full barrier; tcgen05.commit multicasts to the empty / tmem-full
+// barriers of both CTAs; both CTAs' epilogue warps arrive (remotely) on the leader's tmem-empty barrier.
+// ------------------------------------------------------------------------------------------------
+SACB_DEVINL uint32_t leader_bar_addr(const uint64_t* bar) { return smem_u32(bar) & 0xFEFFFFFFu; }   // peer bit -> CTA 0
+SACB_DEVINL void tma2_load_im2col(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c, int w, int h, int n,
+                                  uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h)
+      : "memory");
+}
+SACB_DEVINL void tma2_load_3d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+SACB_DEVINL void tc2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+SACB_DEVINL void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+SACB_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+template <int COLS>
+SACB_DEVINL void tmem2_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+SACB_DEVINL void tmem2_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+constexpr int PAIR_BN = 256;              // N of the pair tile; each CTA stages PAIR_BN/2 rows of B
+struct PairCfg {
+  static constexpr uint32_t B_BYTES = (PAIR_BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;         // per CTA
+  static constexpr int STAGES = 3;
+  static constexpr int TMEM_COLS = 2 * PAIR_BN;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                      const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                      const GemmArgs a) {
+  using Cfg = PairCfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = PAIR_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES + 256);
+  float* s_shift = s_scale + MAX_AFFINE;
+  float* s_colsum = s_shift + MAX_AFFINE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+  }
+  if (a.scale) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+  }
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem2_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int k_blocks = a.taps * a.kc_blocks;
+  const int unit0 = (int)cluster_id_x(), unit_step = (int)cluster_count_x();
+  const int m_pairs = (a.M_total + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = a.N_total / BN;
+  const int total_units = m_pairs * n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const int pq = a.P * a.Q;
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+        const int m0 = m_idx * 2 * BM + crank * BM;            // this CTA's 128 rows of the 256-row tile
+        const int n_img = m0 / pq;
+        const int rem = m0 - n_img * pq;
+        const int p = rem / a.Q, q = rem - p * a.Q;
+        const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
+        const int brow = n_idx * BN + crank * (BN / 2);        // this CTA's half of the B rows
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int r = tap / a.S, s = tap - r * a.S;
+          const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
+          for (int cb = 0; cb < a.kc_blocks; ++cb) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+            const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * Cfg::STAGE_BYTES);     // bytes of BOTH CTAs
+            tma2_load_im2col(&tmAh, lbar, st, cb * BK, w0, h0, n_img, ow, oh);
+            tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            tma2_load_3d(&tmBh, lbar, st + 2 * A_BYTES, cb * BK, brow, tap);
+            tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
+            ps.advance<STAGES>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      PipeState ps{0, 0};
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 32, 16, 1024);
+            const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 32, 16, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 32, 16, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 32, 16, 1024);
+            tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+            tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+            tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            accumulate = 1;
+          }
+          tc2_commit_mc(&empty_bar[ps.stage], 0x3);          // frees the stage in both CTAs
+          ps.advance<STAGES>();
+        }
+        tc2_commit_mc(&tfull_bar[acc], 0x3);                 // accumulator ready in both CTAs' TMEM
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
+      const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM, n_idx * BN,
+                        quad, half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);      // the leader issues the MMAs for both CTAs
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
+      const float cs = s_colsum[i];
+      if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
+    }
+  }
+  if (warp == 1) tmem2_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -682,6 +897,174 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// wgrad on CTA pairs (cta_group::2): one 256 (G channels) x 256 (X channels) tile of one filter tap per pair and K split.
+// Each CTA stages 128 G channels (2 boxes) and 128 X channels (2 boxes) per 64-pixel k-block; same barrier protocol as
+// conv_gemm_pair_kernel.
+// ------------------------------------------------------------------------------------------------
+SACB_DEVINL void tma2_load_2d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
+                       const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+                       const WgradArgs a) {
+  using Cfg = PairCfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = PAIR_BN;
+  constexpr uint32_t BOX_BYTES = 64 * 64 * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmGh); prefetch_tmap(&tmGl); prefetch_tmap(&tmXh); prefetch_tmap(&tmXl);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem2_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int unit0 = (int)cluster_id_x(), unit_step = (int)cluster_count_x();
+  const int total_work = a.m_tiles * a.n_tiles * a.taps * a.splits;       // m_tiles / n_tiles count 256-wide tiles here
+
+  auto decode = [&](int wk, int& m_idx, int& n_idx, int& tap, int& split, int& kb0, int& kb1) {
+    split = wk % a.splits; wk /= a.splits;
+    tap = wk % a.taps; wk /= a.taps;
+    n_idx = wk % a.n_tiles; m_idx = wk / a.n_tiles;
+    kb0 = split * a.blocks_per_split;
+    kb1 = min(kb0 + a.blocks_per_split, a.num_pix_blocks);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const int pq = a.P * a.Q;
+      for (int wk = unit0; wk < total_work; wk += unit_step) {
+        int m_idx, n_idx, tap, split, kb0, kb1;
+        decode(wk, m_idx, n_idx, tap, split, kb0, kb1);
+        const int r = tap / a.S, s = tap - r * a.S;
+        const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
+        const int gch = m_idx * 2 * BM + crank * BM;          // this CTA's 128 G channels
+        const int xch = n_idx * BN + crank * (BN / 2);        // this CTA's 128 X channels
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int m0 = kb * 64;
+          const int n_img = m0 / pq;
+          const int rem = m0 - n_img * pq;
+          const int p = rem / a.Q, q = rem - p * a.Q;
+          const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
+          mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+          const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+          if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * Cfg::STAGE_BYTES);
+          uint8_t* sa_hi = st; uint8_t* sa_lo = st + A_BYTES;
+          uint8_t* sb_hi = st + 2 * A_BYTES; uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            tma2_load_2d(&tmGh, lbar, sa_hi + j * BOX_BYTES, gch + j * 64, m0);
+            tma2_load_2d(&tmGl, lbar, sa_lo + j * BOX_BYTES, gch + j * 64, m0);
+            tma2_load_im2col(&tmXh, lbar, sb_hi + j * BOX_BYTES, xch + j * 64, w0, h0, n_img, ow, oh);
+            tma2_load_im2col(&tmXl, lbar, sb_lo + j * BOX_BYTES, xch + j * 64, w0, h0, n_img, ow, oh);
+          }
+          ps.advance<STAGES>();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      PipeState ps{0, 0};
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 1, 1);
+      for (int wk = unit0; wk < total_work; wk += unit_step) {
+        int m_idx, n_idx, tap, split, kb0, kb1;
+        decode(wk, m_idx, n_idx, tap, split, kb0, kb1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < 64 / 16; ++k) {
+            const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 2048, BOX_BYTES, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 2048, BOX_BYTES, 1024);
+            tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+            tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+            tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            accumulate = 1;
+          }
+          tc2_commit_mc(&empty_bar[ps.stage], 0x3);
+          ps.advance<STAGES>();
+        }
+        tc2_commit_mc(&tfull_bar[acc], 0x3);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int CHUNKS = BN / 32;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int wk = unit0; wk < total_work; wk += unit_step) {
+      int m_idx, n_idx, tap, split, kb0, kb1;
+      decode(wk, m_idx, n_idx, tap, split, kb0, kb1);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_idx * 2 * BM + crank * BM + quad * 32 + lane;
+      float* part = a.dw + (size_t)split * a.k_valid * a.taps * a.C;
+#pragma unroll 1
+      for (int ch = half; ch < CHUNKS; ch += 2) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + ch * 32), r);
+        tmem_ld_wait();
+        if (row < a.k_valid) {
+          float4* dst = reinterpret_cast<float4*>(part + ((size_t)row * a.taps + tap) * a.C + n_idx * BN + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem2_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -701,6 +1084,7 @@ static int g_init_status = 0;
 // SACB_CLUSTER=1: pair CTAs into clusters of 2 that share one operand tile by TMA multicast. Measured (profiles/): no gain,
 // because the limit is the per-SM shared-memory fill rate, not L2 bandwidth -- so it is off by default.
 static bool g_cluster = false;
+static bool g_pair = true;            // SACB_PAIR=0 disables the CTA-pair (tcgen05 cta_group::2) 256x256 tile kernels
 static bool g_no_bn256 = false;       // SACB_NO_BN256=1: cap the N tile at 128 (A/B comparison)
 
 static void init_once() {
@@ -718,6 +1102,7 @@ static void init_once() {
   cudaDriverGetVersion(&g_driver_version);
   if (const char* e = getenv("SACB_CLUSTER")) g_cluster = (e[0] == '1');
   if (const char* e = getenv("SACB_NO_BN256")) g_no_bn256 = (e[0] == '1');
+  if (const char* e = getenv("SACB_PAIR")) g_pair = (e[0] != '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -781,6 +1166,46 @@ static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   return 0;
 }
 
+static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                            const GemmArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    attr_set = true;
+  }
+  const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
+  const int grid = units * 2 < g_num_sms ? units * 2 : (g_num_sms / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel, ah, al, bh, bl, a));
+  g_launches++;
+  return 0;
+}
+
+static int launch_wgrad_pair(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
+                             const WgradArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    attr_set = true;
+  }
+  const int work = a.m_tiles * a.n_tiles * a.taps * a.splits;
+  const int grid = work * 2 < g_num_sms ? work * 2 : (g_num_sms / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_pair_kernel, gh, gl, xh, xl, a));
+  g_launches++;
+  return 0;
+}
+
 template <int BN, int CL>
 static int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                         const WgradArgs& a, cudaStream_t st) {
@@ -823,17 +1248,19 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   const int BN = (d->K % 256 == 0 && d->K >= 512 && !g_no_bn256) ? 256 : (d->K % 128 == 0) ? 128 : (d->K % 64 == 0 ? 64 : 32);
   // cluster of 2 (A tile shared by TMA multicast) whenever there are at least two N tiles to pair up
   const int CL = (BN == 128 && (d->K / BN) % 2 == 0 && g_cluster) ? 2 : 1;
+  const bool pair = g_pair && d->K % PAIR_BN == 0;         // CTA-pair (cta_group::2) 256x256 tiles
   CUtensorMap ah, al, bh, bl;
   if (int e = make_im2col_map(&ah, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
   if (int e = make_im2col_map(&al, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
   cuuint64_t wd[3] = {(cuuint64_t)d->C, (cuuint64_t)d->K, (cuuint64_t)(d->R * d->S)};
   cuuint64_t ws[2] = {(cuuint64_t)d->C * 2, (cuuint64_t)d->C * d->K * 2};
-  cuuint32_t wb[3] = {64, (cuuint32_t)BN, 1};
+  cuuint32_t wb[3] = {64, (cuuint32_t)(pair ? PAIR_BN / 2 : BN), 1};
   if (int e = make_tiled_map(&bh, d->wt_hi, 3, wd, ws, wb)) return e;
   if (int e = make_tiled_map(&bl, d->wt_lo, 3, wd, ws, wb)) return e;
   GemmArgs a;
   a.M_total = d->N * P * Q; a.N_total = d->K; a.n_valid = d->k_valid;
   a.num_m_tiles = (a.M_total + BM - 1) / BM; a.num_n_tiles = d->K / BN;
+  a.colsum = d->colsum;
   a.taps = d->R * d->S; a.S = d->S; a.dil = d->dil; a.kc_blocks = d->C / 64;
   a.P = P; a.Q = Q; a.stride = d->stride; a.lower = -d->pad;
   a.scale = d->scale; a.shift = d->shift; a.add_f32 = d->add_f32;
@@ -846,6 +1273,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   SACB_REQUIRE(d->scale == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged affine size", d->K);
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair) return launch_gemm_pair(ah, al, bh, bl, a, st);
   switch (BN) {
     case 256: return launch_gemm<256, 1>(ah, al, bh, bl, a, st);
     case 128: return CL == 2 ? launch_gemm<128, 2>(ah, al, bh, bl, a, st) : launch_gemm<128, 1>(ah, al, bh, bl, a, st);
@@ -869,12 +1297,15 @@ static int plan_wgrad(const SacbConvWgrad* d, WgradArgs& a, int& BN) {
   a.dw = d->dw;
   // few valid output channels: put the wide input-channel dim on the 128 TMEM lanes
   a.swap = (d->k_valid <= 64 && d->C >= 128) ? 1 : 0;
-  if (!a.swap) { BN = (d->C % 256 == 0 && !g_no_bn256) ? 256 : (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
+  const bool pair = g_pair && !a.swap && d->K % 256 == 0 && d->C % 256 == 0;
+  if (pair) { BN = -256; a.m_tiles = d->K / 256; a.n_tiles = d->C / 256; }       // BN < 0 marks the CTA-pair kernel
+  else if (!a.swap) { BN = (d->C % 256 == 0 && !g_no_bn256) ? 256 : (d->C % 128 == 0) ? 128 : 64; a.m_tiles = (d->K + BM - 1) / BM; a.n_tiles = d->C / BN; }
   else { BN = 64; a.m_tiles = (d->C + BM - 1) / BM; a.n_tiles = d->K / 64; }
   int splits = d->splits;
   if (splits <= 0) {
     const int base = a.m_tiles * a.n_tiles * a.taps;
-    splits = (2 * g_num_sms + base - 1) / base;
+    // aim at ~2 work units per CTA (per CTA pair for the pair kernel), rounded down so the last wave stays full
+    splits = pair ? (g_num_sms / base) : (2 * g_num_sms + base - 1) / base;
     const int max_splits = a.num_pix_blocks / 8 > 0 ? a.num_pix_blocks / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -904,6 +1335,7 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
   if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
   if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  if (BN == -256) return launch_wgrad_pair(gh, gl, xh, xl, a, st);
   const bool pair = (a.n_tiles % 2 == 0) && g_cluster && BN != 256;     // two adjacent column tiles share the row operand
   if (BN == 256) return launch_wgrad<256, 1>(gh, gl, xh, xl, a, st);
   if (BN == 128) return pair ? launch_wgrad<128, 2>(gh, gl, xh, xl, a, st) : launch_wgrad<128, 1>(gh, gl, xh, xl, a, st);

@@ -129,7 +129,9 @@ WG_CASES = [
     (2, 33, 33, 64, 128, 1, 2, 1, 0),
     (2, 33, 33, 256, 64, 3, 1, 6, 6),     # ASPP-like: 19 valid output channels -> swapped roles
     (2, 33, 33, 256, 128, 3, 1, 6, 6),    # swapped roles with two column tiles (cluster path)
-    (2, 17, 17, 512, 256, 1, 1, 1, 0),    # 4 column tiles -> clusters of 2 share the G operand
+    (2, 17, 17, 512, 256, 1, 1, 1, 0),    # C, K multiples of 256 -> CTA-pair (cta_group::2) kernel
+    (3, 33, 33, 256, 256, 3, 1, 2, 2),    # CTA-pair kernel, 3x3 dilated, ragged last pixel block
+    (1, 20, 31, 256, 768, 1, 1, 1, 0),    # three 256-row tiles (the ASPP filter gradient shape)
 ]
 
 
