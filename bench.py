@@ -216,8 +216,13 @@ def main():
         a = by.setdefault(kind, [0.0, 0.0, 0]); a[0] += flops; a[1] += t; a[2] += 1
     dom = max(by, key=lambda k: by[k][1])
     achieved = by[dom][0] / (by[dom][1] * 1e-3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on its most frequent shape
+    # (3x3 d2 256->256, 23 layers x 3 passes), from the committed ncu --set full capture profiles/ncu_gemm_pair_r1k.txt
+    traffic = 106.904832e6 + 62.850816e6 if dom.startswith("conv_gemm_pair") else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["sustained"], "traffic": None, "launches": by[dom][2],
+                "frac": achieved / pk["sustained"], "traffic": traffic,
+                "traffic_note": "bytes per launch on the 3x3 d2 256->256 layer (algorithmic activations in+out 208 MB, weights 2.4 MB); per-launch FLOPs there: 119.6 GFLOP",
+                "launches": by[dom][2],
                 "share_of_step": by[dom][1] / (ms / args.steps),
                 "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3 split), so frac <= 1/3 by construction" % pk["src"],
                 "step_tensor_frac": value / world * TFLOP_PER_CROP / pk["sustained"],

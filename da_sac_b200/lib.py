@@ -141,7 +141,9 @@ def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift
     desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                     ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
                     ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw), ptr(colsum))
-    kind = "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))
+    # mirrors the dispatch in csrc/sacb_gemm.cu (sacb_conv_gemm)
+    pair = os.environ.get("SACB_PAIR", "1") != "0" and K % 256 == 0
+    kind = "conv_gemm_pair<256x256>" if pair else "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))
     flops = 2.0 * N * P * Q * (K if k_valid is None else k_valid) * Cc * R * R
     _prof_wrap(kind, flops, lambda: check(lib().sacb_conv_gemm(C.byref(desc), stream()), "sacb_conv_gemm"))
 
@@ -163,5 +165,6 @@ def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
     assert dw.numel() >= need, "split-K workspace too small: %d < %d" % (dw.numel(), need)
     desc.dw = ptr(dw)
     flops = 2.0 * N * P * Q * kv * Cc * R * R
-    _prof_wrap("conv_wgrad", flops, lambda: check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad"))
+    pair = os.environ.get("SACB_PAIR", "1") != "0" and K % 256 == 0 and Cc % 256 == 0 and not (kv <= 64 and Cc >= 128)
+    _prof_wrap("conv_wgrad_pair<256x256>" if pair else "conv_wgrad", flops, lambda: check(lib().sacb_conv_wgrad(C.byref(desc), stream()), "sacb_conv_wgrad"))
     return dw, n
