@@ -174,14 +174,15 @@ stem_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ g_hi
 // Stem on the tensor cores: explicit im2col of the 3-channel image (147 taps, zero-padded to 192 columns) so the
 // 7x7 s2 conv becomes a 1x1 conv_gemm with C = 192 (and its filter gradient a plain conv_wgrad).
 // ------------------------------------------------------------------------------------------------
-constexpr int STEM_KP = 192;
+// Generic for any 3-input-channel first conv: R x R taps, `stride`, `pad`; TAPS = 3*R*R columns padded to KP (multiple of 64).
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ a_hi, uint16_t* __restrict__ a_lo, int N, int H,
-                   int W, int P, int Q) {
-  const size_t total = (size_t)N * P * Q * (STEM_KP / 8);
+                   int W, int P, int Q, int R, int stride, int pad, int KP) {
+  const int RR = R * R, TAPS = 3 * RR;
+  const size_t total = (size_t)N * P * Q * (KP / 8);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int jv = (int)(t % (STEM_KP / 8));
-    size_t pix = t / (STEM_KP / 8);
+    const int jv = (int)(t % (KP / 8));
+    size_t pix = t / (KP / 8);
     const int q = (int)(pix % Q); pix /= Q;
     const int p = (int)(pix % P);
     const int n = (int)(pix / P);
@@ -190,10 +191,10 @@ stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ a_hi, uin
     for (int e = 0; e < 8; ++e) {
       const int j = jv * 8 + e;
       float val = 0.f;
-      if (j < 147) {
-        const int c = j / 49, rs = j - c * 49;
-        const int r = rs / 7, ss = rs - r * 7;
-        const int hh = 2 * p - 3 + r, ww = 2 * q - 3 + ss;
+      if (j < TAPS) {
+        const int c = j / RR, rs = j - c * RR;
+        const int r = rs / R, ss = rs - r * R;
+        const int hh = stride * p - pad + r, ww = stride * q - pad + ss;
         if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((size_t)(n * 3 + c) * H + hh) * W + ww);
       }
       v[e] = val;
@@ -204,21 +205,99 @@ stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ a_hi, uin
     reinterpret_cast<uint4*>(a_lo)[t] = l;
   }
 }
-// wf[k][j] (j < 192) from OIHW [64][147]
-__global__ void stem_pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+// wf[k][j] (j < KP) from OIHW [K][TAPS]
+__global__ void stem_pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                        int K, int TAPS, int KP) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 64 * STEM_KP) return;
-  const int k = i / STEM_KP, j = i - k * STEM_KP;
-  st_split(hi, lo, i, j < 147 ? w[k * 147 + j] : 0.f);
+  if (i >= K * KP) return;
+  const int k = i / KP, j = i - k * KP;
+  st_split(hi, lo, i, j < TAPS ? w[k * TAPS + j] : 0.f);
 }
-// dwraw[k][j<147] = sum_split parts[split][k][j]  (parts rows are 192 wide)
-__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ parts, int splits, float* __restrict__ dwraw) {
+// dwraw[k][j<TAPS] = sum_split parts[split][k][j]  (parts rows are KP wide)
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ parts, int splits, float* __restrict__ dwraw, int K,
+                                         int TAPS, int KP) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 64 * 147) return;
-  const int k = i / 147, j = i - k * 147;
+  if (i >= K * TAPS) return;
+  const int k = i / TAPS, j = i - k * TAPS;
   float s = 0.f;
-  for (int sp = 0; sp < splits; ++sp) s += parts[((size_t)sp * 64 + k) * STEM_KP + j];
+  for (int sp = 0; sp < splits; ++sp) s += parts[((size_t)sp * K + k) * KP + j];
   dwraw[i] = s;
+}
+
+// MaxPool2d(2, 2) on split planes (torchvision vgg16 features.6/13/23); idx = argmax tap 0..3 for backward
+__global__ void maxpool2_fwd_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo,
+                                    uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo,
+                                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int P, int Q) {
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (C / 8));
+    size_t t = i / (C / 8);
+    const int q = (int)(t % Q); t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float best[8]; uint32_t bhh[8], bll[8]; int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; bhh[j] = 0; bll[j] = 0; }
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int hh = 2 * p + (tap >> 1), ww = 2 * q + (tap & 1);
+      if (hh >= H || ww >= W) continue;
+      const size_t o = (((size_t)n * H + hh) * W + ww) * C + cv * 8;
+      const uint4 h = *reinterpret_cast<const uint4*>(in_hi + o);
+      const uint4 l = *reinterpret_cast<const uint4*>(in_lo + o);
+      float fh[8], fl[8];
+      unpack8f(h, fh); unpack8f(l, fl);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fh[j] + fl[j];
+        if (v > best[j]) {
+          best[j] = v; bi[j] = tap;
+          bhh[j] = (hw[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+          bll[j] = (lw[j >> 1] >> ((j & 1) * 16)) & 0xFFFF;
+        }
+      }
+    }
+    const size_t oo = (((size_t)n * P + p) * Q + q) * C + cv * 8;
+    *reinterpret_cast<uint4*>(out_hi + oo) = make_uint4(bhh[0] | (bhh[1] << 16), bhh[2] | (bhh[3] << 16), bhh[4] | (bhh[5] << 16), bhh[6] | (bhh[7] << 16));
+    *reinterpret_cast<uint4*>(out_lo + oo) = make_uint4(bll[0] | (bll[1] << 16), bll[2] | (bll[3] << 16), bll[4] | (bll[5] << 16), bll[6] | (bll[7] << 16));
+    *reinterpret_cast<uint2*>(idx + oo) = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24),
+                                                     bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+  }
+}
+// g_in[n,h,w,c] = (idx[n,h/2,w/2,c] == tap(h,w)) ? g_out[n,h/2,w/2,c] : 0, masked by in_hi > 0 -> split planes
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ g_out, const uint8_t* __restrict__ idx,
+                                    const uint16_t* __restrict__ in_hi, uint16_t* __restrict__ gin_hi,
+                                    uint16_t* __restrict__ gin_lo, int N, int H, int W, int C, int P, int Q) {
+  const size_t total = (size_t)N * H * W * (C / 8);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % (C / 8));
+    size_t t = i / (C / 8);
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    unpack8f(reinterpret_cast<const uint4*>(in_hi)[i], m);
+    const int p = h >> 1, q = w >> 1;
+    if (p < P && q < Q) {
+      const size_t o = (((size_t)n * P + p) * Q + q) * C + cv * 8;
+      const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
+      const float4 g0 = *reinterpret_cast<const float4*>(g_out + o), g1 = *reinterpret_cast<const float4*>(g_out + o + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const int tap = ((h & 1) << 1) | (w & 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int id = ((j < 4 ? iv.x : iv.y) >> ((j & 3) * 8)) & 0xFF;
+        if (id == tap && m[j] > 0.f) acc[j] = gv[j];
+      }
+    }
+    uint4 hh, ll;
+    split8(acc, hh, ll);
+    reinterpret_cast<uint4*>(gin_hi)[i] = hh;
+    reinterpret_cast<uint4*>(gin_lo)[i] = ll;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,22 +547,29 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, const float* __r
 
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+                               const float* __restrict__ conv_bias, float* __restrict__ scale,
+                               float* __restrict__ shift, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (!gamma) {                                   // conv + bias without BN: y = conv + bias
+    scale[c] = 1.f;
+    shift[c] = conv_bias ? conv_bias[c] : 0.f;
+    return;
+  }
   // same operation order as ATen's batch_norm inference path: invstd = 1/sqrt(var+eps)
   const float invstd = 1.0f / sqrtf(var[c] + eps);
   const float sc = gamma[c] * invstd;
   scale[c] = sc;
-  shift[c] = beta[c] - mean[c] * sc;
+  // y = gamma * (conv + bias - mean) * invstd + beta
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - mean[c]) * sc;
 }
 
 // block per output channel k
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ dwraw, const float* __restrict__ w, const float* __restrict__ scale,
                       const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                      const float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dgamma, int K,
-                      int C, int RS, int splits) {
+                      const float* __restrict__ dbeta, float* __restrict__ dw, float* __restrict__ dgamma,
+                      const float* __restrict__ conv_bias, float* __restrict__ dbias, int K, int C, int RS, int splits) {
   const int k = blockIdx.x;
   const float sc = scale ? scale[k] : 1.f;
   float dot = 0.f;
@@ -504,9 +590,12 @@ wgrad_finalize_kernel(const float* __restrict__ dwraw, const float* __restrict__
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int i = 0; i < 8; ++i) s += red[i];
-      dgamma[k] = (s - mean[k] * dbeta[k]) * (1.0f / sqrtf(var[k] + eps));
+      // z = conv + bias: sum g*z = <W, dW_raw> + bias * dbeta
+      const float b = conv_bias ? conv_bias[k] : 0.f;
+      dgamma[k] = (s + (b - mean[k]) * dbeta[k]) * (1.0f / sqrtf(var[k] + eps));
     }
   }
+  if (dbias && threadIdx.x == 0) dbias[k] = sc * dbeta[k];        // d(conv bias) = sum g * dy/dz = scale * d(beta)
 }
 
 static inline int grid_for(size_t n, int block) {
@@ -537,20 +626,40 @@ extern "C" int sacb_stem_wgrad(const float* x, const void* g_hi, const void* g_l
   return 0;
 }
 
-extern "C" int sacb_stem_im2col(const float* x, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, void* stream) {
-  SACB_REQUIRE(P == (H + 6 - 7) / 2 + 1 && Q == (W + 6 - 7) / 2 + 1, "sacb_stem_im2col: bad output size");
-  const size_t total = (size_t)N * P * Q * (STEM_KP / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q);
+extern "C" int sacb_stem_im2col(const float* x, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, int R,
+                                int stride, int pad, int KP, void* stream) {
+  SACB_REQUIRE(P == (H + 2 * pad - R) / stride + 1 && Q == (W + 2 * pad - R) / stride + 1, "sacb_stem_im2col: bad output size");
+  SACB_REQUIRE(KP % 64 == 0 && KP >= 3 * R * R, "sacb_stem_im2col: KP must be a multiple of 64 covering 3*R*R taps");
+  const size_t total = (size_t)N * P * Q * (KP / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q, R, stride, pad, KP);
   LAUNCHED();
   return 0;
 }
-extern "C" int sacb_stem_pack_weight(const float* w, void* hi, void* lo, void* stream) {
-  stem_pack_weight_kernel<<<(64 * STEM_KP + 255) / 256, 256, 0, ST>>>(w, (uint16_t*)hi, (uint16_t*)lo);
+extern "C" int sacb_stem_pack_weight(const float* w, void* hi, void* lo, int K, int taps, int KP, void* stream) {
+  stem_pack_weight_kernel<<<(K * KP + 255) / 256, 256, 0, ST>>>(w, (uint16_t*)hi, (uint16_t*)lo, K, taps, KP);
   LAUNCHED();
   return 0;
 }
-extern "C" int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, void* stream) {
-  stem_unpack_wgrad_kernel<<<(64 * 147 + 255) / 256, 256, 0, ST>>>(parts, splits, dwraw);
+extern "C" int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, int K, int taps, int KP, void* stream) {
+  stem_unpack_wgrad_kernel<<<(K * taps + 255) / 256, 256, 0, ST>>>(parts, splits, dwraw, K, taps, KP);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_maxpool2_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx, int N,
+                                 int H, int W, int C, int P, int Q, void* stream) {
+  SACB_REQUIRE(C % 8 == 0 && P == H / 2 && Q == W / 2, "sacb_maxpool2_fwd: C %% 8, P = H/2, Q = W/2");
+  const size_t total = (size_t)N * P * Q * (C / 8);
+  maxpool2_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint16_t*)in_hi, (const uint16_t*)in_lo,
+                                                           (uint16_t*)out_hi, (uint16_t*)out_lo, idx, N, H, W, C, P, Q);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_maxpool2_bwd(const float* g_out, const uint8_t* idx, const void* in_hi, void* gin_hi, void* gin_lo,
+                                 int N, int H, int W, int C, int P, int Q, void* stream) {
+  SACB_REQUIRE(C % 8 == 0, "sacb_maxpool2_bwd: C %% 8");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  maxpool2_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(g_out, idx, (const uint16_t*)in_hi, (uint16_t*)gin_hi,
+                                                           (uint16_t*)gin_lo, N, H, W, C, P, Q);
   LAUNCHED();
   return 0;
 }
@@ -619,16 +728,18 @@ extern "C" int sacb_prep_weight(const float* w, const float* scale, int K, int C
 }
 
 extern "C" int sacb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-                            float* scale, float* shift, int C, void* stream) {
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, mean, var, eps, scale, shift, C);
+                            const float* conv_bias, float* scale, float* shift, int C, void* stream) {
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, ST>>>(gamma, beta, mean, var, eps, conv_bias, scale, shift, C);
   LAUNCHED();
   return 0;
 }
 
 extern "C" int sacb_wgrad_finalize(const float* dwraw, const float* w, const float* scale, const float* mean,
-                                   const float* var, float eps, const float* dbeta, float* dw, float* dgamma, int K,
-                                   int C, int R, int S, int splits, void* stream) {
-  wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, K, C, R * S, splits);
+                                   const float* var, float eps, const float* dbeta, float* dw, float* dgamma,
+                                   const float* conv_bias, float* dbias, int K, int C, int R, int S, int splits,
+                                   void* stream) {
+  wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, conv_bias, dbias, K, C,
+                                          R * S, splits);
   LAUNCHED();
   return 0;
 }

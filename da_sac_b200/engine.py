@@ -26,11 +26,13 @@ STEM_KP = 192            # 3*7*7 = 147 im2col columns of the stem, zero-padded t
 
 
 class ConvSpec(object):
-    __slots__ = ("name", "bn", "K", "C", "R", "stride", "dil", "pad", "hin", "win", "hout", "wout", "Kf", "Kt")
+    __slots__ = ("name", "bn", "K", "C", "R", "stride", "dil", "pad", "hin", "win", "hout", "wout", "Kf", "Kt", "bias", "head")
 
-    def __init__(self, name, bn, K, Cc, R, stride, dil, pad):
+    def __init__(self, name, bn, K, Cc, R, stride, dil, pad, bias=False, head=False):
         self.name, self.bn, self.K, self.C, self.R = name, bn, K, Cc, R
         self.stride, self.dil, self.pad = stride, dil, pad
+        self.bias = bias            # conv has its own bias parameter (VGG convs, ASPP head)
+        self.head = head            # one of the four ASPP classifier convs (handled by the packed tap-unrolled GEMM)
         self.Kf = (K + 31) // 32 * 32       # rows of the fprop weight planes
         self.Kt = (K + 63) // 64 * 64       # reduction length of the dgrad weight planes
 
@@ -75,7 +77,44 @@ def build_resnet101(H, W):
             inplanes, h, w = planes * 4, c3.hout, c3.wout
     aspp = [add("model.layer5.conv2d_list.%d" % i, None, NUM_CLASSES, 2048, 3, 1, d, d, h, w)
             for i, d in enumerate((6, 12, 18, 24))]
-    return dict(specs=specs, order=order, stem=stem, pool_hw=(ph, pw), blocks=blocks, aspp=aspp, out_hw=(h, w))
+    for a_ in aspp:
+        a_.bias = True; a_.head = True
+    return dict(arch="resnet101", specs=specs, order=order, stem=stem, pool_hw=(ph, pw), blocks=blocks, aspp=aspp, out_hw=(h, w),
+                stem_kp=STEM_KP)
+
+
+VGG16_CONVS = ((0, 3, 64, 1), (3, 64, 64, 1), (7, 64, 128, 1), (10, 128, 128, 1), (14, 128, 256, 1), (17, 256, 256, 1),
+               (20, 256, 256, 1), (24, 256, 512, 1), (27, 512, 512, 1), (30, 512, 512, 1), (33, 512, 512, 2),
+               (36, 512, 512, 2), (39, 512, 512, 2))
+VGG16_POOL_AFTER = (3, 10, 20)          # features.6 / .13 / .23 follow these convs; pool4 / pool5 are removed
+
+
+def build_vgg16_deeplab(H, W):
+    """Layer table of DeepLabV2_VGG16(use_bn=True) (/root/reference/models/deeplabv2.py:229-312): torchvision
+    vgg16_bn features with conv5 dilated by 2, pool4/pool5 removed, fc6/fc7 as 3x3 dilation-4 convs, ASPP on 1024 ch."""
+    specs, order, seq = {}, [], []
+    h, w = H, W
+    for (idx, cin, cout, dil) in VGG16_CONVS:
+        s = ConvSpec("features.%d" % idx, "features.%d" % (idx + 1), cout, cin, 3, 1, dil, dil, bias=True)
+        s.hin, s.win, s.hout, s.wout = h, w, h, w
+        specs[s.name] = s; order.append(s.name); seq.append(("conv", s))
+        if idx in VGG16_POOL_AFTER:
+            seq.append(("pool", (h, w, h // 2, w // 2, cout, "pool%d" % idx)))
+            h, w = h // 2, w // 2
+    for (idx, cin, cout) in ((42, 512, 1024), (44, 1024, 1024)):
+        s = ConvSpec("features.%d" % idx, None, cout, cin, 3, 1, 4, 4, bias=True)
+        s.hin, s.win, s.hout, s.wout = h, w, h, w
+        specs[s.name] = s; order.append(s.name); seq.append(("conv", s))
+    aspp = []
+    for i, d in enumerate((6, 12, 18, 24)):
+        s = ConvSpec("classifier.conv2d_list.%d" % i, None, NUM_CLASSES, 1024, 3, 1, d, d, bias=True, head=True)
+        s.hin, s.win, s.hout, s.wout = h, w, h, w
+        specs[s.name] = s; order.append(s.name); aspp.append(s)
+    return dict(arch="vgg16", specs=specs, order=order, stem=seq[0][1], seq=seq, aspp=aspp, out_hw=(h, w), stem_kp=64)
+
+
+def build_net(arch, H, W):
+    return build_resnet101(H, W) if arch == "resnet101" else build_vgg16_deeplab(H, W)
 
 
 def param_layout(net):
@@ -85,9 +124,9 @@ def param_layout(net):
     for name in net["order"]:
         s = net["specs"][name]
         entries.append((name + ".weight", (s.K, s.C, s.R, s.R), True))
-        if s.bn is None:
+        if s.bias:
             entries.append((name + ".bias", (s.K,), True))
-        else:
+        if s.bn is not None:
             entries.append((s.bn + ".weight", (s.K,), True))
             entries.append((s.bn + ".bias", (s.K,), True))
             entries.append((s.bn + ".running_mean", (s.K,), False))
@@ -136,7 +175,7 @@ class WeightPlanes(object):
         self.off = {}
         for name in net["order"]:
             s = net["specs"][name]
-            if s.C == 3 or s.bn is None:       # stem runs on CUDA cores; the ASPP head uses the packed planes below
+            if s.C == 3 or s.head:             # first conv: packed im2col planes; ASPP head: packed tap-unrolled planes
                 self.off[name] = (None, None, nsc)
             else:
                 self.off[name] = (nf, nt, nsc)
@@ -144,7 +183,8 @@ class WeightPlanes(object):
                 nt += s.R * s.R * s.C * s.Kt
             nsc += s.Kf
         self.stem_off = nf
-        nf += 64 * STEM_KP
+        self.stem_n = net["stem"].K * net["stem_kp"]
+        nf += self.stem_n
         self.aspp_off = (nf, nt)
         self.aspp_n = ASPP_JPAD * net["aspp"][0].C
         nf += self.aspp_n; nt += self.aspp_n
@@ -164,7 +204,7 @@ class WeightPlanes(object):
 
     def stem(self):
         o = self.stem_off
-        return self.wf_hi[o:o + 64 * STEM_KP], self.wf_lo[o:o + 64 * STEM_KP]
+        return self.wf_hi[o:o + self.stem_n], self.wf_lo[o:o + self.stem_n]
 
     def aspp(self):
         of, ot = self.aspp_off
@@ -182,20 +222,26 @@ class WeightPlanes(object):
         for name in self.net["order"]:
             s = self.net["specs"][name]
             sc, sh = self.affine(name)
+            if s.head:
+                continue
+            cb = L.ptr(flat.view(name + ".bias")) if s.bias else None
             if s.bn is not None:
                 L.check(lib.sacb_bn_fold(L.ptr(flat.view(s.bn + ".weight")), L.ptr(flat.view(s.bn + ".bias")),
                                          L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
-                                         C.c_float(BN_EPS), L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
-            if s.C == 3 or s.bn is None:
+                                         C.c_float(BN_EPS), cb, L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
+            else:
+                L.check(lib.sacb_bn_fold(None, None, None, None, C.c_float(BN_EPS), cb, L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
+            if s.C == 3:
                 continue
             fh, fl = self.wf(name)
             th, tl = self.wt(name) if self.with_dgrad else (None, None)
-            L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc) if s.bn is not None else None,
+            L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc),
                                          s.K, s.C, s.R, s.R, s.Kf, s.Kt, L.ptr(fh), L.ptr(fl), L.ptr(th), L.ptr(tl), st),
                     "sacb_prep_weight")
         sh_, sl_ = self.stem()
-        L.check(lib.sacb_stem_pack_weight(L.ptr(flat.view(self.net["stem"].name + ".weight")), L.ptr(sh_), L.ptr(sl_), st),
-                "sacb_stem_pack_weight")
+        stem = self.net["stem"]
+        L.check(lib.sacb_stem_pack_weight(L.ptr(flat.view(stem.name + ".weight")), L.ptr(sh_), L.ptr(sl_), stem.K,
+                                          3 * stem.R * stem.R, self.net["stem_kp"], st), "sacb_stem_pack_weight")
         a = self.net["aspp"]
         f, t = self.aspp()
         L.check(lib.sacb_aspp_pack_weights(*[L.ptr(flat.view(x.name + ".weight")) for x in a], a[0].C,
@@ -231,45 +277,162 @@ class BufferPool(object):
         self.free = list(range(len(self.bufs))); self.used = {}
 
 
-class ResNet101Engine(object):
-    def __init__(self, N, H, W, device):
-        self.N, self.H, self.W, self.device = N, H, W, device
-        self.net = build_resnet101(H, W)
-        net = self.net
-        bf = torch.bfloat16
-        # student activations kept for backward
-        self.act = {}
-        st = net["stem"]
-        def planes(m, c):
-            return Planes(torch.empty(m * c, device=device, dtype=bf), torch.empty(m * c, device=device, dtype=bf))
-        self.act["stem"] = planes(N * st.hout * st.wout, 64)
-        ph, pw = net["pool_hw"]
-        self.act["pool"] = planes(N * ph * pw, 64)
-        self.pool_idx = torch.empty(N * ph * pw * 64, device=device, dtype=torch.uint8)
-        max_elems = N * st.hout * st.wout * 64
-        for (p, c1, c2, c3, ds) in net["blocks"]:
-            for c in (c1, c2, c3):
-                self.act[c.name] = planes(N * c.hout * c.wout, c.K)
-                max_elems = max(max_elems, N * c.hout * c.wout * c.K)
-            if ds is not None:
-                self.act[ds.name] = planes(N * ds.hout * ds.wout, ds.K)
-        self.max_elems = max_elems
-        # teacher ping-pong planes / gradient planes / fp32 scratch
-        self.tpool_hi = BufferPool(max_elems, 5, bf, device); self.tpool_lo = BufferPool(max_elems, 5, bf, device)
-        self.fpool = BufferPool(max_elems, 2, torch.float32, device)
-        oh, ow = net["out_hw"]
-        self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)      # tap-unrolled ASPP partial outputs
-        self.stem_a = planes(N * st.hout * st.wout, STEM_KP)                 # im2col matrix of the stem (kept for wgrad)
-        self.dwraw = torch.empty(max(s.Kt * s.R * s.R * s.C for s in net["specs"].values()), device=device)
-        self.stem_dw = torch.empty(64 * 147, device=device)
+class EngineBase(object):
+    """Buffers and building blocks shared by the backbone schedules: first conv through an explicit im2col GEMM,
+    conv+BN(+ReLU)(+residual) units, filter-gradient + finalisation, the tap-unrolled ASPP head."""
 
-    # ------------------------------------------------------------------ forward
+    def __init__(self, net, N, H, W, device):
+        self.net, self.N, self.H, self.W, self.device = net, N, H, W, device
+        self.act = {}
+        self.dwraw = torch.empty(1 << 20, device=device)
+        stem = net["stem"]
+        self.stem_a = self._planes(N * stem.hout * stem.wout, net["stem_kp"])     # im2col matrix of the first conv (kept for wgrad)
+        self.stem_dw = torch.empty(stem.K * 3 * stem.R * stem.R, device=device)
+        oh, ow = net["out_hw"]
+        self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)           # tap-unrolled ASPP partial outputs
+
+    def _planes(self, m, c):
+        bf = torch.bfloat16
+        return Planes(torch.empty(m * c, device=self.device, dtype=bf), torch.empty(m * c, device=self.device, dtype=bf))
+
+    def _make_pools(self, max_elems, n_planes, n_f32):
+        bf = torch.bfloat16
+        self.max_elems = max_elems
+        self.tpool_hi = BufferPool(max_elems, n_planes, bf, self.device); self.tpool_lo = BufferPool(max_elems, n_planes, bf, self.device)
+        self.fpool = BufferPool(max_elems, n_f32, torch.float32, self.device)
+
     def _tplanes(self, tag, n):
         return Planes(self.tpool_hi.get(tag, n), self.tpool_lo.get(tag, n))
 
     def _tput(self, tag):
         self.tpool_hi.put(tag); self.tpool_lo.put(tag)
 
+    def _rename(self, old, new):
+        self.tpool_hi.used[new] = self.tpool_hi.used.pop(old); self.tpool_lo.used[new] = self.tpool_lo.used.pop(old)
+
+    # ---- forward pieces
+    def _first_conv_fwd(self, flat, wp, x, out):
+        lib, st, N, stem = L.lib(), L.stream(), self.N, self.net["stem"]
+        kp = self.net["stem_kp"]
+        L.check(lib.sacb_stem_im2col(L.ptr(x), L.ptr(self.stem_a.hi), L.ptr(self.stem_a.lo), N, self.H, self.W,
+                                     stem.hout, stem.wout, stem.R, stem.stride, stem.pad, kp, st), "sacb_stem_im2col")
+        sc, sh = wp.affine(stem.name)
+        wsh, wsl = wp.stem()
+        L.conv_gemm(self.stem_a.hi, self.stem_a.lo, wsh, wsl, (N, stem.hout, stem.wout, kp, stem.K, 1, 1, 1, 0),
+                    scale=sc, shift=sh, relu=True, out_hi=out.hi, out_lo=out.lo)
+
+    def _unit(self, wp, s, xin, out, relu, res=None):
+        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+        L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), scale=sc, shift=sh,
+                    add_hi=None if res is None else res.hi, add_lo=None if res is None else res.lo,
+                    relu=relu, out_hi=out.hi, out_lo=out.lo)
+
+    def _aspp_fwd(self, flat, wp, a, logits_out):
+        """ASPP head (deeplabv2.py:112-116) as one tap-unrolled 1x1 GEMM + shift-and-add (csrc/sacb_aspp.cu)"""
+        lib, st, N, asp = L.lib(), L.stream(), self.N, self.net["aspp"]
+        oh, ow = self.net["out_hw"]
+        (fh, fl), _ = wp.aspp()
+        L.conv_gemm(a.hi, a.lo, fh, fl, (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0), out_f32=self.zbuf)
+        L.check(lib.sacb_aspp_gather(L.ptr(self.zbuf), *[L.ptr(flat.view(x.name + ".bias")) for x in asp], ASPP_DIL,
+                                     L.ptr(logits_out), N, oh, ow, st), "sacb_aspp_gather")
+
+    # ---- backward pieces
+    def _begin_backward(self):
+        self.tpool_hi.reset(); self.tpool_lo.reset(); self.fpool.reset()
+        # d(beta) of every BN unit (d(bias) of bias-only convs) = column sums of the gradient arriving at it; accumulated by
+        # the epilogue of the GEMM that produces that gradient (colsum=...), into one zero-filled buffer
+        self._dbeta_pool = torch.zeros(sum(s.K for s in self.net["specs"].values() if not s.head) + 64, device=self.device)
+        self._dbeta_off = 0
+
+    def _aspp_bwd(self, flat, wp, xlast, dlogits, grad):
+        """Gcol (shifted copies of dlogits) -> bias / filter / data gradients as plain GEMMs. Returns (gout, dbeta of xlast's unit)."""
+        lib, st, N, asp = L.lib(), L.stream(), self.N, self.net["aspp"]
+        oh, ow = self.net["out_hw"]
+        M5 = N * oh * ow
+        gcol = self._tplanes("gcol", M5 * ASPP_JPAD)
+        L.check(lib.sacb_aspp_gcol(L.ptr(dlogits), ASPP_DIL, L.ptr(gcol.hi), L.ptr(gcol.lo), N, oh, ow, st), "sacb_aspp_gcol")
+        csum = self._dbeta(gcol, M5, ASPP_JPAD)
+        for i, s in enumerate(asp):                      # centre tap of conv i carries g itself: its column sum is d bias
+            o = (i * 9 + 4) * NUM_CLASSES
+            grad.view(s.name + ".bias").copy_(csum[o:o + NUM_CLASSES])
+        parts, splits = L.conv_wgrad(xlast.hi, xlast.lo, gcol.hi, gcol.lo, self._dw_workspace,
+                                     (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0))
+        L.check(lib.sacb_aspp_unpack_wgrad(L.ptr(parts), splits, asp[0].C, *[L.ptr(grad.view(x.name + ".weight")) for x in asp], st),
+                "sacb_aspp_unpack_wgrad")
+        gout = self._tplanes("gout", M5 * asp[0].C)
+        _, (th, tl) = wp.aspp()
+        dbeta = self._new_dbeta(asp[0].C)
+        L.conv_gemm(gcol.hi, gcol.lo, th, tl, (N, oh, ow, ASPP_JPAD, asp[0].C, 1, 1, 1, 0), mask_hi=xlast.hi,
+                    out_hi=gout.hi, out_lo=gout.lo, colsum=dbeta)
+        self._tput("gcol")
+        return gout, dbeta
+
+    def _first_conv_bwd(self, flat, wp, gs, grad, dbeta):
+        lib, st, N, stem = L.lib(), L.stream(), self.N, self.net["stem"]
+        kp, taps = self.net["stem_kp"], 3 * stem.R * stem.R
+        parts, splits = L.conv_wgrad(self.stem_a.hi, self.stem_a.lo, gs.hi, gs.lo, self._dw_workspace,
+                                     (N, stem.hout, stem.wout, kp, stem.Kt, 1, 1, 1, 0), k_valid=stem.K)
+        L.check(lib.sacb_stem_unpack_wgrad(L.ptr(parts), splits, L.ptr(self.stem_dw), stem.K, taps, kp, st), "sacb_stem_unpack_wgrad")
+        self._finalize(flat, wp, stem, self.stem_dw, grad, dbeta, C_eff=taps, RS=1)
+
+    def _new_dbeta(self, K):
+        o = self._dbeta_off
+        self._dbeta_off = o + K
+        return self._dbeta_pool[o:o + K]
+
+    def _dbeta(self, g, M, K):
+        d = torch.zeros(K, device=self.device)
+        L.check(L.lib().sacb_colsum(L.ptr(g.hi), L.ptr(g.lo), L.ptr(d), C.c_int64(M), K, L.stream()), "sacb_colsum")
+        return d
+
+    def _dw_workspace(self, n):
+        if self.dwraw.numel() < n:
+            self.dwraw = torch.empty(n, device=self.device)
+        return self.dwraw
+
+    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
+        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, self._dw_workspace,
+                                     (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
+        self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R, splits=splits)
+
+    def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS, splits=1):
+        """dW (OIHW), d gamma, d beta and the conv-bias gradient of one unit from its raw filter gradient and d beta"""
+        lib, st = L.lib(), L.stream()
+        cb = L.ptr(flat.view(s.name + ".bias")) if s.bias else None
+        db = L.ptr(grad.view(s.name + ".bias")) if s.bias else None
+        if s.bn is not None:
+            sc, _ = wp.affine(s.name)
+            grad.view(s.bn + ".bias").copy_(dbeta)
+            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), L.ptr(sc),
+                                            L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
+                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")),
+                                            L.ptr(grad.view(s.bn + ".weight")), cb, db, s.K, C_eff, RS, 1, splits, st),
+                    "sacb_wgrad_finalize")
+        else:
+            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), None, None, None,
+                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")), None,
+                                            cb, db, s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")
+
+
+class ResNet101Engine(EngineBase):
+    def __init__(self, N, H, W, device):
+        EngineBase.__init__(self, build_resnet101(H, W), N, H, W, device)
+        net = self.net
+        st = net["stem"]
+        self.act["stem"] = self._planes(N * st.hout * st.wout, 64)
+        ph, pw = net["pool_hw"]
+        self.act["pool"] = self._planes(N * ph * pw, 64)
+        self.pool_idx = torch.empty(N * ph * pw * 64, device=device, dtype=torch.uint8)
+        max_elems = N * st.hout * st.wout * 64
+        for (p, c1, c2, c3, ds) in net["blocks"]:
+            for c in (c1, c2, c3):
+                self.act[c.name] = self._planes(N * c.hout * c.wout, c.K)
+                max_elems = max(max_elems, N * c.hout * c.wout * c.K)
+            if ds is not None:
+                self.act[ds.name] = self._planes(N * ds.hout * ds.wout, ds.K)
+        self._make_pools(max_elems, 5, 2)
+
+    # ------------------------------------------------------------------ forward
     def forward(self, flat, wp, x, logits_out, keep):
         """x: fp32 NCHW [N,3,H,W]; logits_out: fp32 NCHW [N,19,h,w]. keep=True stores activations for backward."""
         net, N, lib, st = self.net, self.N, L.lib(), L.stream()
@@ -278,13 +441,8 @@ class ResNet101Engine(object):
         self.tpool_hi.reset(); self.tpool_lo.reset()
         get = (lambda tag, n: self.act[tag]) if keep else self._tplanes
         put = (lambda tag: None) if keep else self._tput
-        sc, sh = wp.affine(stem.name)
         a_stem = get("stem", N * stem.hout * stem.wout * 64)
-        L.check(lib.sacb_stem_im2col(L.ptr(x), L.ptr(self.stem_a.hi), L.ptr(self.stem_a.lo), N, self.H, self.W,
-                                     stem.hout, stem.wout, st), "sacb_stem_im2col")
-        wsh, wsl = wp.stem()
-        L.conv_gemm(self.stem_a.hi, self.stem_a.lo, wsh, wsl, (N, stem.hout, stem.wout, STEM_KP, 64, 1, 1, 1, 0),
-                    scale=sc, shift=sh, relu=True, out_hi=a_stem.hi, out_lo=a_stem.lo)
+        self._first_conv_fwd(flat, wp, x, a_stem)
         a = get("pool", N * ph * pw * 64)
         L.check(lib.sacb_maxpool_fwd(L.ptr(a_stem.hi), L.ptr(a_stem.lo), L.ptr(a.hi), L.ptr(a.lo), L.ptr(self.pool_idx),
                                      N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_fwd")
@@ -307,53 +465,17 @@ class ResNet101Engine(object):
             if ds is not None: put(ds.name)
             put(xtag)
             a, xtag = o3, c3.name
-        # ASPP head (deeplabv2.py:112-116) as one tap-unrolled 1x1 GEMM + shift-and-add (csrc/sacb_aspp.cu)
-        asp = net["aspp"]
-        oh, ow = net["out_hw"]
-        (fh, fl), _ = wp.aspp()
-        L.conv_gemm(a.hi, a.lo, fh, fl, (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0), out_f32=self.zbuf)
-        L.check(lib.sacb_aspp_gather(L.ptr(self.zbuf), *[L.ptr(flat.view(x.name + ".bias")) for x in asp], ASPP_DIL,
-                                     L.ptr(logits_out), N, oh, ow, st), "sacb_aspp_gather")
+        self._aspp_fwd(flat, wp, a, logits_out)
         put(xtag)
         return logits_out
-
-    def _unit(self, wp, s, xin, out, relu, res=None):
-        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
-        L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), scale=sc, shift=sh,
-                    add_hi=None if res is None else res.hi, add_lo=None if res is None else res.lo,
-                    relu=relu, out_hi=out.hi, out_lo=out.lo)
 
     # ------------------------------------------------------------------ backward
     def backward(self, flat, wp, x, dlogits, grad):
         """dlogits fp32 NCHW [N,19,h,w]; writes every parameter gradient into ``grad`` (FlatParams layout)."""
         net, N, lib, st = self.net, self.N, L.lib(), L.stream()
-        self.tpool_hi.reset(); self.tpool_lo.reset(); self.fpool.reset()
-        oh, ow = net["out_hw"]
-        M5 = N * oh * ow
-        # ASPP head backward: Gcol (shifted copies of dlogits) -> bias / filter / data gradients as plain GEMMs
-        asp = net["aspp"]
+        self._begin_backward()
         blocks = net["blocks"]
-        xlast = self.act[blocks[-1][3].name]
-        gcol = self._tplanes("gcol", M5 * ASPP_JPAD)
-        L.check(lib.sacb_aspp_gcol(L.ptr(dlogits), ASPP_DIL, L.ptr(gcol.hi), L.ptr(gcol.lo), N, oh, ow, st), "sacb_aspp_gcol")
-        csum = self._dbeta(gcol, M5, ASPP_JPAD)
-        for i, s in enumerate(asp):                      # centre tap of conv i carries g itself: its column sum is d bias
-            o = (i * 9 + 4) * NUM_CLASSES
-            grad.view(s.name + ".bias").copy_(csum[o:o + NUM_CLASSES])
-        parts, splits = L.conv_wgrad(xlast.hi, xlast.lo, gcol.hi, gcol.lo, self._dw_workspace,
-                                     (N, oh, ow, asp[0].C, ASPP_JPAD, 1, 1, 1, 0))
-        L.check(lib.sacb_aspp_unpack_wgrad(L.ptr(parts), splits, asp[0].C, *[L.ptr(grad.view(x.name + ".weight")) for x in asp], st),
-                "sacb_aspp_unpack_wgrad")
-        gout = self._tplanes("gout", M5 * asp[0].C)
-        _, (th, tl) = wp.aspp()
-        # d(beta) of every BN unit = column sums of the gradient arriving at it; they are accumulated by the epilogue of
-        # the GEMM that produces that gradient (colsum=...), into one zero-filled buffer
-        self._dbeta_pool = torch.zeros(sum(s.K for s in net["specs"].values() if s.bn is not None), device=self.device)
-        self._dbeta_off = 0
-        dbeta3 = self._new_dbeta(asp[0].C)
-        L.conv_gemm(gcol.hi, gcol.lo, th, tl, (N, oh, ow, ASPP_JPAD, asp[0].C, 1, 1, 1, 0), mask_hi=xlast.hi,
-                    out_hi=gout.hi, out_lo=gout.lo, colsum=dbeta3)
-        self._tput("gcol")
+        gout, dbeta3 = self._aspp_bwd(flat, wp, self.act[blocks[-1][3].name], dlogits, grad)
         for bi in range(len(blocks) - 1, -1, -1):
             (p, c1, c2, c3, ds) = blocks[bi]
             xin = self.act[blocks[bi - 1][3].name] if bi > 0 else self.act["pool"]
@@ -411,7 +533,7 @@ class ResNet101Engine(object):
                 self.fpool.put("tmp"); self.fpool.put("tmp2")
             self._tput("g1"); self._tput("gout")
             # rename gx -> gout for the next (earlier) block
-            self.tpool_hi.used["gout"] = self.tpool_hi.used.pop("gx"); self.tpool_lo.used["gout"] = self.tpool_lo.used.pop("gx")
+            self._rename("gx", "gout")
             gout = gx
         # max-pool backward (+ ReLU mask of the stem) and the stem conv
         stem = net["stem"]
@@ -421,42 +543,92 @@ class ResNet101Engine(object):
         L.check(lib.sacb_maxpool_bwd(L.ptr(gp), L.ptr(self.pool_idx), L.ptr(a_stem.hi), L.ptr(gs.hi), L.ptr(gs.lo),
                                      N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_bwd")
         dbeta = self._dbeta(gs, N * stem.hout * stem.wout, 64)
-        parts, splits = L.conv_wgrad(self.stem_a.hi, self.stem_a.lo, gs.hi, gs.lo, self._dw_workspace,
-                                     (N, stem.hout, stem.wout, STEM_KP, 64, 1, 1, 1, 0))
-        dwraw = self.stem_dw
-        L.check(lib.sacb_stem_unpack_wgrad(L.ptr(parts), splits, L.ptr(dwraw), st), "sacb_stem_unpack_wgrad")
-        self._finalize(flat, wp, stem, dwraw, grad, dbeta, C_eff=147, RS=1)
+        self._first_conv_bwd(flat, wp, gs, grad, dbeta)
 
-    def _new_dbeta(self, K):
-        o = self._dbeta_off
-        self._dbeta_off = o + K
-        return self._dbeta_pool[o:o + K]
 
-    def _dbeta(self, g, M, K):
-        d = torch.zeros(K, device=self.device)
-        L.check(L.lib().sacb_colsum(L.ptr(g.hi), L.ptr(g.lo), L.ptr(d), C.c_int64(M), K, L.stream()), "sacb_colsum")
-        return d
+class VGG16Engine(EngineBase):
+    """DeepLabV2_VGG16(use_bn=True): 13 conv+bias+BN+ReLU units with three 2x2 max-pools, fc6/fc7 (conv+bias+ReLU), ASPP."""
 
-    def _dw_workspace(self, n):
-        if self.dwraw.numel() < n:
-            self.dwraw = torch.empty(n, device=self.device)
-        return self.dwraw
+    def __init__(self, N, H, W, device):
+        EngineBase.__init__(self, build_vgg16_deeplab(H, W), N, H, W, device)
+        max_elems = 0
+        self.pool_idx = {}
+        for kind, it in self.net["seq"]:
+            if kind == "conv":
+                self.act[it.name] = self._planes(N * it.hout * it.wout, it.K)
+                max_elems = max(max_elems, N * it.hout * it.wout * it.K)
+            else:
+                h, w, ph, pw, c, tag = it
+                self.act[tag] = self._planes(N * ph * pw, c)
+                self.pool_idx[tag] = torch.empty(N * ph * pw * c, device=device, dtype=torch.uint8)
+        self._make_pools(max_elems, 4, 2)
 
-    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
-        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, self._dw_workspace,
-                                     (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
-        self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R, splits=splits)
+    def forward(self, flat, wp, x, logits_out, keep):
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        self.tpool_hi.reset(); self.tpool_lo.reset()
+        get = (lambda tag, n: self.act[tag]) if keep else self._tplanes
+        put = (lambda tag: None) if keep else self._tput
+        a, atag = None, None
+        for kind, it in net["seq"]:
+            if kind == "conv":
+                o = get(it.name, N * it.hout * it.wout * it.K)
+                if a is None:
+                    self._first_conv_fwd(flat, wp, x, o)
+                else:
+                    self._unit(wp, it, a, o, relu=True)
+                    put(atag)
+                a, atag = o, it.name
+            else:
+                h, w, ph, pw, c, tag = it
+                o = get(tag, N * ph * pw * c)
+                L.check(lib.sacb_maxpool2_fwd(L.ptr(a.hi), L.ptr(a.lo), L.ptr(o.hi), L.ptr(o.lo), L.ptr(self.pool_idx[tag]),
+                                              N, h, w, c, ph, pw, st), "sacb_maxpool2_fwd")
+                put(atag)
+                a, atag = o, tag
+        self._aspp_fwd(flat, wp, a, logits_out)
+        put(atag)
+        return logits_out
 
-    def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS, splits=1):
-        lib, st = L.lib(), L.stream()
-        if s.bn is not None:
-            sc, _ = wp.affine(s.name)
-            grad.view(s.bn + ".bias").copy_(dbeta)
-            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), L.ptr(sc),
-                                            L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
-                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")),
-                                            L.ptr(grad.view(s.bn + ".weight")), s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")
-        else:
-            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), None, None, None,
-                                            C.c_float(BN_EPS), None, L.ptr(grad.view(s.name + ".weight")), None,
-                                            s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")
+    def backward(self, flat, wp, x, dlogits, grad):
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        self._begin_backward()
+        seq = net["seq"]
+        last = seq[-1][1]
+        g, dbeta = self._aspp_bwd(flat, wp, self.act[last.name], dlogits, grad)      # g = grad at fc7's output (masked)
+        i = len(seq) - 1
+        while i >= 0:
+            kind, s = seq[i]
+            assert kind == "conv"
+            if i == 0:
+                self._first_conv_bwd(flat, wp, g, grad, dbeta)
+                break
+            pkind, pit = seq[i - 1]
+            xin = self.act[pit.name] if pkind == "conv" else self.act[pit[5]]
+            self._wgrad(flat, wp, s, xin, g, grad, dbeta)
+            th, tl = wp.wt(s.name)
+            if pkind == "conv":
+                gx = self._tplanes("gx", N * s.hin * s.win * s.C)
+                dbeta = self._new_dbeta(s.C)
+                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo, colsum=dbeta)
+                self._tput("gout"); self._rename("gx", "gout")
+                g = gx
+                i -= 1
+            else:
+                # the conv's input is a max-pool output: un-masked fp32 gradient, routed through the pool to the conv before it
+                h, w, ph, pw, c, tag = pit
+                gp = self.fpool.get("gp", N * ph * pw * c)
+                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), out_f32=gp)
+                self._tput("gout")
+                src = seq[i - 2][1]                       # conv feeding the pool
+                gx = self._tplanes("gout", N * h * w * c)
+                L.check(lib.sacb_maxpool2_bwd(L.ptr(gp), L.ptr(self.pool_idx[tag]), L.ptr(self.act[src.name].hi), L.ptr(gx.hi),
+                                              L.ptr(gx.lo), N, h, w, c, ph, pw, st), "sacb_maxpool2_bwd")
+                self.fpool.put("gp")
+                dbeta = self._new_dbeta(c)
+                L.check(lib.sacb_colsum(L.ptr(gx.hi), L.ptr(gx.lo), L.ptr(dbeta), C.c_int64(N * h * w), c, st), "sacb_colsum")
+                g = gx
+                i -= 2
+
+
+def make_engine(arch, N, H, W, device):
+    return ResNet101Engine(N, H, W, device) if arch == "resnet101" else VGG16Engine(N, H, W, device)

@@ -4,12 +4,14 @@
 ``cfg.BASELINE``) wrapping a B200-native backbone and its momentum copy."""
 import os
 
-from .deeplabv2 import DeepLabV2_ResNet101
+from functools import partial
+
+from .deeplabv2 import DeepLabV2_ResNet101, DeepLabV2_VGG16
 from .sac import SAC, SAC_Baseline
 
 
 def get_model(cfg, rank, *args, **kwargs):
-    models = {"deeplabv2_resnet101": DeepLabV2_ResNet101}
+    models = {"deeplabv2_resnet101": DeepLabV2_ResNet101, "deeplabv2_vgg16_bn": partial(DeepLabV2_VGG16, use_bn=True)}
     arch = cfg.ARCH.lower()
     if arch not in models:
         raise NotImplementedError("libsac_b200: backbone '%s' is not built yet (SURVEY.md section 8(f)); available: %s"

@@ -80,18 +80,11 @@ class _BackboneFn(torch.autograd.Function):
         return (None, None, None) + tuple(net._grad.view(k) for k in net._param_keys)
 
 
-class DeepLabV2_ResNet101(BaseNet):
-    def __init__(self, num_classes=20, criterion=nn.CrossEntropyLoss(ignore_index=255, reduction="none"),
-                 pretrained=None, freeze_bn=False):
-        super().__init__()
-        assert num_classes == E.NUM_CLASSES, "libsac_b200 kernels are built for 19 classes"
-        self.model = _ResNetParams([3, 4, 23, 3], num_classes)
-        if pretrained is not None:
-            self.model.load_state_dict(torch.load(pretrained), strict=False)
-        if freeze_bn:
-            self._freeze_bn(self)
-        self._from_scratch(self.model.layer5)
-        self.criterion = criterion
+class _EngineBackbone(BaseNet):
+    """Shared machinery of the B200 backbones: flat fp32 parameter storage, bf16 weight planes, per-shape engines."""
+    ARCH = None
+
+    def _init_engine_state(self):
         self._flat = None
         self._grad = None
         self._wp = None
@@ -119,7 +112,7 @@ class DeepLabV2_ResNet101(BaseNet):
             ok = all(tensors[k].data_ptr() == self._flat.view(k).data_ptr() for k, _, _ in self._flat.entries)
             if ok:
                 return self._flat
-        net = E.build_resnet101(64, 64)
+        net = E.build_net(self.ARCH, 64, 64)
         flat = E.FlatParams(net, device)
         for k, _, _ in flat.entries:
             v = flat.view(k)
@@ -138,7 +131,7 @@ class DeepLabV2_ResNet101(BaseNet):
 
     def _planes(self, with_dgrad):
         if self._wp is None or self._wp.with_dgrad != with_dgrad:
-            self._wp = E.WeightPlanes(E.build_resnet101(64, 64), self._flat.buf.device, with_dgrad)
+            self._wp = E.WeightPlanes(E.build_net(self.ARCH, 64, 64), self._flat.buf.device, with_dgrad)
             self._wp_version = -1
         if self._wp_version != self._version:
             self._wp.prepare(self._flat)
@@ -146,10 +139,10 @@ class DeepLabV2_ResNet101(BaseNet):
         return self._wp
 
     def engine(self, N, H, W, shared=None):
-        key = (N, H, W)
+        key = (self.ARCH, N, H, W)
         cache = self._engines if shared is None else shared
         if key not in cache:
-            cache[key] = E.ResNet101Engine(N, H, W, self._flat.buf.device)
+            cache[key] = E.make_engine(self.ARCH, N, H, W, self._flat.buf.device)
         return cache[key]
 
     # ---------------------------------------------------------------- forward
@@ -177,6 +170,57 @@ class DeepLabV2_ResNet101(BaseNet):
             return logits, up
         ce = self.criterion(up, y)
         return {"loss_ce": ce.mean().view(1)}, {"logits_up": up, "logits": logits}
+
+
+class DeepLabV2_ResNet101(_EngineBackbone):
+    """/root/reference/models/deeplabv2.py:173-227"""
+    ARCH = "resnet101"
+
+    def __init__(self, num_classes=20, criterion=nn.CrossEntropyLoss(ignore_index=255, reduction="none"),
+                 pretrained=None, freeze_bn=False):
+        super().__init__()
+        assert num_classes == E.NUM_CLASSES, "libsac_b200 kernels are built for 19 classes"
+        self.model = _ResNetParams([3, 4, 23, 3], num_classes)
+        if pretrained is not None:
+            self.model.load_state_dict(torch.load(pretrained), strict=False)
+        if freeze_bn:
+            self._freeze_bn(self)
+        self._from_scratch(self.model.layer5)
+        self.criterion = criterion
+        self._init_engine_state()
+
+
+class DeepLabV2_VGG16(_EngineBackbone):
+    """/root/reference/models/deeplabv2.py:229-312 (use_bn=True): torchvision vgg16_bn features with conv5 dilated,
+    pool4/pool5 removed, fc6/fc7 as dilated 3x3 convs, ASPP on 1024 channels. Module indices inside ``features`` match
+    the reference so that checkpoints (``features.N.*``, ``classifier.conv2d_list.*``) load unchanged."""
+    ARCH = "vgg16"
+
+    def __init__(self, num_classes, criterion=None, pretrained=None, use_bn=False, freeze_bn=False):
+        super().__init__()
+        assert use_bn, "libsac_b200 implements the BN variant used by the reference configs (deeplabv2_vgg16_bn)"
+        assert num_classes == E.NUM_CLASSES, "libsac_b200 kernels are built for 19 classes"
+        self.criterion = criterion
+        layers = []
+        pool_after = set(E.VGG16_POOL_AFTER)
+        for (idx, cin, cout, dil) in E.VGG16_CONVS:
+            assert len(layers) == idx
+            layers += [nn.Conv2d(cin, cout, 3, padding=dil, dilation=dil), _bn(cout), nn.ReLU(inplace=True)]
+            if idx in pool_after:
+                layers.append(nn.MaxPool2d(2, 2))
+        fc6 = nn.Conv2d(512, 1024, 3, padding=4, dilation=4)
+        fc7 = nn.Conv2d(1024, 1024, 3, padding=4, dilation=4)
+        layers += [fc6, nn.ReLU(inplace=True), fc7, nn.ReLU(inplace=True)]
+        self.features = nn.Sequential(*layers)
+        if pretrained is not None:
+            raise NotImplementedError("loading torchvision vgg16_bn snapshots is done through load_state_dict on this module")
+        self.classifier = _Classifier(1024, (6, 12, 18, 24), num_classes)
+        if freeze_bn:
+            self._freeze_bn(self)
+        self._from_scratch(self.classifier)
+        self._from_scratch(fc6)
+        self._from_scratch(fc7)
+        self._init_engine_state()
 
 
 class _UpsampleFn(torch.autograd.Function):

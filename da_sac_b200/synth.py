@@ -72,6 +72,35 @@ def make_backbone_params(seed=123, num_classes=NUM_CLASSES, dtype=torch.float32)
     return OrderedDict((k, v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items())
 
 
+VGG16_CONVS = ((0, 3, 64, 1), (3, 64, 64, 1), (7, 64, 128, 1), (10, 128, 128, 1), (14, 128, 256, 1), (17, 256, 256, 1),
+               (20, 256, 256, 1), (24, 256, 512, 1), (27, 512, 512, 1), (30, 512, 512, 1), (33, 512, 512, 2),
+               (36, 512, 512, 2), (39, 512, 512, 2))
+
+
+def make_vgg16_params(seed=321, num_classes=NUM_CLASSES):
+    """Seeded DeepLabV2_VGG16(use_bn=True) state_dict (key layout of /root/reference/models/deeplabv2.py:229-312):
+    He fan-in conv weights, small random biases, BN gamma~U(0.8,1.2), beta/mean~N(0,0.1), var~U(0.8,1.2),
+    ASPP weights x3 so that the pseudo labels are discriminative."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for (idx, cin, cout, dil) in VGG16_CONVS:
+        sd["features.%d.weight" % idx] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        sd["features.%d.bias" % idx] = torch.randn(cout, generator=g) * 0.05
+        b = "features.%d" % (idx + 1)
+        sd[b + ".weight"] = torch.rand(cout, generator=g) * 0.4 + 0.8
+        sd[b + ".bias"] = torch.randn(cout, generator=g) * 0.1
+        sd[b + ".running_mean"] = torch.randn(cout, generator=g) * 0.1
+        sd[b + ".running_var"] = torch.rand(cout, generator=g) * 0.4 + 0.8
+        sd[b + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    for idx, cin, cout in ((42, 512, 1024), (44, 1024, 1024)):
+        sd["features.%d.weight" % idx] = torch.randn(cout, cin, 3, 3, generator=g) * math.sqrt(2.0 / (cin * 9))
+        sd["features.%d.bias" % idx] = torch.randn(cout, generator=g) * 0.05
+    for i in range(4):
+        sd["classifier.conv2d_list.%d.weight" % i] = torch.randn(num_classes, 1024, 3, 3, generator=g) * math.sqrt(2.0 / (1024 * 9)) * 3.0
+        sd["classifier.conv2d_list.%d.bias" % i] = torch.randn(num_classes, generator=g) * 0.05
+    return sd
+
+
 def affine_from_params(params, crop_hw):
     """Restates DataTarget._get_affine/_get_affine_inv
     (/root/reference/datasets/dataloader_target.py:220-262).

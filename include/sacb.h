@@ -99,12 +99,19 @@ int sacb_stem_fwd(const float* x_nchw, const float* w, const float* scale, const
 /* dW of the stem conv: g split planes [N,P,Q,64] (already masked by ReLU), x fp32 NCHW -> dw[64][3][7][7] (+=) */
 int sacb_stem_wgrad(const float* x_nchw, const void* g_hi, const void* g_lo, float* dw,
                     int N, int H, int W, int P, int Q, void* stream);
-/* Tensor-core stem: A[n,p,q, (c*7+r)*7+s] = x[n,c,2p-3+r,2q-3+s] (147 taps zero-padded to 192 columns) turns the
- * 7x7 s2 conv into a 1x1 sacb_conv_gemm with C = 192 (weights from sacb_stem_pack_weight: [64][192]) and its filter
- * gradient into a 1x1 sacb_conv_wgrad whose partial planes sacb_stem_unpack_wgrad sums into dwraw[64][147]. */
-int sacb_stem_im2col(const float* x_nchw, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, void* stream);
-int sacb_stem_pack_weight(const float* w, void* hi, void* lo, void* stream);
-int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, void* stream);
+/* Tensor-core first conv (3 input channels): A[n,p,q, (c*R+r)*R+s] = x[n,c,stride*p-pad+r,stride*q-pad+s] (3*R*R taps
+ * zero-padded to KP columns) turns the conv into a 1x1 sacb_conv_gemm with C = KP (weights from sacb_stem_pack_weight:
+ * [K][KP]) and its filter gradient into a 1x1 sacb_conv_wgrad whose partial planes sacb_stem_unpack_wgrad sums into
+ * dwraw[K][3*R*R]. ResNet stem: R=7, stride 2, pad 3, KP=192; VGG features.0: R=3, stride 1, pad 1, KP=64. */
+int sacb_stem_im2col(const float* x_nchw, void* a_hi, void* a_lo, int N, int H, int W, int P, int Q, int R, int stride,
+                     int pad, int KP, void* stream);
+int sacb_stem_pack_weight(const float* w, void* hi, void* lo, int K, int taps, int KP, void* stream);
+int sacb_stem_unpack_wgrad(const float* parts, int splits, float* dwraw, int K, int taps, int KP, void* stream);
+/* MaxPool2d(2, 2) of torchvision vgg16 (models/deeplabv2.py:238-260) on split planes, and its backward (+ReLU mask) */
+int sacb_maxpool2_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx,
+                      int N, int H, int W, int C, int P, int Q, void* stream);
+int sacb_maxpool2_bwd(const float* g_out, const uint8_t* idx, const void* in_hi, void* gin_hi, void* gin_lo,
+                      int N, int H, int W, int C, int P, int Q, void* stream);
 /* MaxPool2d(3, 2, 1, ceil_mode=True) on split planes (deeplabv2.py:126); idx = argmax tap (uint8) for backward */
 int sacb_maxpool_fwd(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, uint8_t* idx,
                      int N, int H, int W, int C, int P, int Q, void* stream);
@@ -124,17 +131,18 @@ int sacb_colsum(const void* hi, const void* lo, float* colsum, int64_t M, int C,
  * if wt_* != NULL, dgrad planes wt[R*S][C][Kt] = w[k][c][R-1-r][S-1-s] * scale[k] (scale NULL = 1; k >= K zero) */
 int sacb_prep_weight(const float* w_oihw, const float* scale, int K, int C, int R, int S, int Kf, int Kt,
                      void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, void* stream);
-/* BN fold (basenet.py:97-100 eval-mode statistics, trainable affine):
- * scale = gamma * rsqrt(var + eps), shift = beta - mean * scale */
+/* BN fold (basenet.py:97-100 eval-mode statistics, trainable affine), optionally with the conv bias of VGG convs:
+ * scale = gamma * rsqrt(var + eps), shift = beta + (conv_bias - mean) * scale; gamma == NULL: scale = 1, shift = conv_bias */
 int sacb_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-                 float* scale, float* shift, int C, void* stream);
+                 const float* conv_bias, float* scale, float* shift, int C, void* stream);
 /* finalize a conv+BN unit's parameter gradients from the raw filter gradient (DESIGN.md "BN backward"):
  * dwraw[k][rs][c] = sum over `splits` partial planes (plane stride K*R*S*C);
  * dw_oihw[k][c][r][s] = scale[k] * dwraw[k][rs][c];
- * dgamma[k] = (sum_{rs,c} w[k][c][r][s] * dwraw[k][rs][c] - mean[k] * dbeta[k]) * rsqrt(var[k]+eps) */
+ * dgamma[k] = (sum_{rs,c} w[k][c][r][s] * dwraw[k][rs][c] + (conv_bias[k] - mean[k]) * dbeta[k]) * rsqrt(var[k]+eps);
+ * dbias[k] = scale[k] * dbeta[k] (if dbias; scale NULL = 1) */
 int sacb_wgrad_finalize(const float* dwraw, const float* w_oihw, const float* scale, const float* mean,
                         const float* var, float eps, const float* dbeta, float* dw_oihw, float* dgamma,
-                        int K, int C, int R, int S, int splits, void* stream);
+                        const float* conv_bias, float* dbias, int K, int C, int R, int S, int splits, void* stream);
 
 /* ---------------------------------------------------------------- ASPP head as a tap-unrolled 1x1 GEMM
  * Classifier_Module (deeplabv2.py:101-116): sum of four 3x3 dilated convs 2048 -> 19 (+ biases).

@@ -80,9 +80,33 @@ def resnet101_logits(p, x, taps=None):
     return out
 
 
+VGG16_CONVS = ((0, 1), (3, 1), (7, 1), (10, 1), (14, 1), (17, 1), (20, 1), (24, 1), (27, 1), (30, 1), (33, 2), (36, 2), (39, 2))
+VGG16_POOL_AFTER = (3, 10, 20)
+
+
+def vgg16_deeplab_logits(p, x, taps=None):
+    """DeepLabV2_VGG16._backbone (deeplabv2.py:294-298): vgg16_bn features (conv5 dilation 2, pool4/5 removed,
+    :238-260), fc6/fc7 3x3 dilation 4 + ReLU (:262-265), Classifier_Module on 1024 channels (:270)."""
+    for idx, dil in VGG16_CONVS:
+        x = F.conv2d(x, p["features.%d.weight" % idx], p["features.%d.bias" % idx], 1, dil, dil)
+        x = F.relu(_bn_eval(x, p, "features.%d" % (idx + 1)))
+        if taps is not None: taps["features.%d" % idx] = x
+        if idx in VGG16_POOL_AFTER:
+            x = F.max_pool2d(x, 2, 2)
+    for idx in (42, 44):
+        x = F.relu(F.conv2d(x, p["features.%d.weight" % idx], p["features.%d.bias" % idx], 1, 4, 4))
+        if taps is not None: taps["features.%d" % idx] = x
+    out = None
+    for i, d in enumerate((6, 12, 18, 24)):
+        o = F.conv2d(x, p["classifier.conv2d_list.%d.weight" % i], p["classifier.conv2d_list.%d.bias" % i], 1, d, d)
+        out = o if out is None else out + o
+    return out
+
+
 def backbone_forward(p, im, y=None):
-    """DeepLabV2_ResNet101.forward (deeplabv2.py:213-227)."""
-    logits = resnet101_logits(p, im)
+    """DeepLabV2_ResNet101.forward / DeepLabV2_VGG16.forward (deeplabv2.py:213-227, 300-312); the architecture is
+    recognised from the state_dict keys."""
+    logits = resnet101_logits(p, im) if "model.conv1.weight" in p else vgg16_deeplab_logits(p, im)
     logits_up = F.interpolate(logits, im.shape[-2:], mode="bilinear", align_corners=True)
     if y is None:
         return logits, logits_up
@@ -276,7 +300,8 @@ def parameter_groups(student, lr, wd):
     for k, v in student.items():
         if not (k.endswith(".weight") or k.endswith(".bias")):
             continue
-        new = k.startswith("model.layer5.")
+        # from-scratch layers (deeplabv2.py:201, 285-287): ASPP head; for VGG also fc6 / fc7
+        new = k.startswith("model.layer5.") or k.startswith("classifier.") or k.startswith("features.42.") or k.startswith("features.44.")
         isw = k.endswith(".weight")
         groups[(2 if new else 0) + (0 if isw else 1)]["params"].append(v)
     return list(groups)

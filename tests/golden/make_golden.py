@@ -4,7 +4,9 @@ Run in the build container only (the GPU box has no /root/reference):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/sac_resnet101_tiny.npz.  Protocol (mirrors
+    python tests/golden/make_golden.py vgg16      # BASELINE.json configs[0]: VGG-16 DeepLabv2, 1 crop 256x256, K=1
+
+Writes tests/golden/sac_resnet101_tiny.npz (and sac_vgg16_cfg1.npz).  Protocol (mirrors
 /root/reference/train.py:266-298 with TRAIN.TARGET_ONLY=True):
 
   step 0: update_teacher=True  -> teacher := student, running_conf := beta
@@ -29,12 +31,16 @@ REF = "/root/reference"
 from da_sac_b200 import synth  # noqa: E402
 
 N_GROUPS, K, HW = 2, 2, (128, 128)
+ARCH = "resnet101"
+if len(sys.argv) > 1 and sys.argv[1] == "vgg16":
+    # BASELINE.json configs[0]: VGG-16 DeepLabv2, 1 target crop 256x256, K=1 (the reference's CPU-runnable plumbing case)
+    N_GROUPS, K, HW, ARCH = 1, 1, (256, 256), "vgg16"
 
 
 def build_reference_net():
     sys.path.insert(0, REF)
     from core.config import cfg, cfg_from_file, cfg_from_list
-    cfg_from_file(os.path.join(REF, "configs/deeplabv2_resnet101_train.yaml"))
+    cfg_from_file(os.path.join(REF, "configs/deeplabv2_resnet101_train.yaml" if ARCH == "resnet101" else "configs/deeplabv2_vgg16_train.yaml"))
     cfg_from_list(["TRAIN.GROUP_SIZE", str(K), "TRAIN.NUM_GROUPS", str(N_GROUPS),
                    "DATASET.CROP_SIZE", "(%d,%d)" % HW, "MODEL.INIT_MODEL", ""])
     from models import get_model
@@ -48,7 +54,7 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     net, cfg = build_reference_net()
-    sd = synth.make_backbone_params(seed=123)
+    sd = synth.make_backbone_params(seed=123) if ARCH == "resnet101" else synth.make_vgg16_params(seed=321)
     missing = net.backbone.load_state_dict(sd, strict=True)
     print("loaded", missing)
     net.train()
@@ -100,21 +106,28 @@ def main():
         out[pre + "grad_norms"] = np.array(norms)
         if step == 0:
             out["grad_names"] = np.array(names)
-        for k in ("model.conv1.weight", "model.bn1.weight", "model.bn1.bias", "model.layer1.0.conv1.weight",
-                  "model.layer2.0.downsample.0.weight", "model.layer3.5.bn2.weight", "model.layer3.5.bn2.bias",
-                  "model.layer3.5.conv2.weight", "model.layer4.2.conv3.weight",
-                  "model.layer5.conv2d_list.1.bias", "model.layer5.conv2d_list.3.weight"):
+        picks = ("model.conv1.weight", "model.bn1.weight", "model.bn1.bias", "model.layer1.0.conv1.weight",
+                 "model.layer2.0.downsample.0.weight", "model.layer3.5.bn2.weight", "model.layer3.5.bn2.bias",
+                 "model.layer3.5.conv2.weight", "model.layer4.2.conv3.weight",
+                 "model.layer5.conv2d_list.1.bias", "model.layer5.conv2d_list.3.weight") if ARCH == "resnet101" else \
+                ("features.0.weight", "features.0.bias", "features.1.weight", "features.1.bias", "features.10.weight",
+                 "features.18.weight", "features.24.bias", "features.36.weight", "features.42.weight", "features.44.bias",
+                 "classifier.conv2d_list.0.bias", "classifier.conv2d_list.2.weight")
+        for k in picks:
             g = dict(net.backbone.named_parameters())[k].grad
             if g.numel() > 60000:
                 g = g.flatten()[:60000]
             out[pre + "grad::" + k] = g.numpy().copy()
         if step == 0:
             optim.step()
-            out["s0_post_step::model.layer5.conv2d_list.1.bias"] = \
-                net.backbone.model.layer5.conv2d_list[1].bias.detach().numpy().copy()
-            out["s0_post_step::model.layer3.5.conv2.weight"] = \
-                net.backbone.model.layer3[5].conv2.weight.detach().flatten()[:60000].numpy().copy()
-    path = os.path.join(HERE, "sac_resnet101_tiny.npz")
+            if ARCH == "resnet101":
+                out["s0_post_step::model.layer5.conv2d_list.1.bias"] = \
+                    net.backbone.model.layer5.conv2d_list[1].bias.detach().numpy().copy()
+                out["s0_post_step::model.layer3.5.conv2.weight"] = \
+                    net.backbone.model.layer3[5].conv2.weight.detach().flatten()[:60000].numpy().copy()
+            else:
+                out["s0_post_step::features.44.bias"] = net.backbone.features[44].bias.detach().numpy().copy()
+    path = os.path.join(HERE, "sac_resnet101_tiny.npz" if ARCH == "resnet101" else "sac_vgg16_cfg1.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")
 

@@ -223,3 +223,54 @@ def test_backward_matches_reference_given_golden_pseudo_labels(net, golden):
                 optim.step()
     finally:
         m._tail = orig_tail
+
+
+def test_vgg16_config1_two_steps_match_reference_golden():
+    """BASELINE.json configs[0] (VGG-16 DeepLabv2, 1 crop 256x256, K=1) on the B200 path vs the reference's golden"""
+    import os
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_vgg16_cfg1.npz"))
+    cfg = synth.ModelCfg()
+    cfg.ARCH = "deeplabv2_vgg16_bn"
+    m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    m.backbone.load_state_dict(synth.make_vgg16_params(seed=321))
+    m.cuda().train()
+    optim = torch.optim.SGD(m.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    batch = synth.make_target_batch(1, 1, (256, 256), seed=0)
+    names = [str(n) for n in g["grad_names"]]
+    params = dict(m.backbone.named_parameters())
+    for step in (0, 1):
+        x, y, x2, A, Ai = [t.clone().cuda() for t in batch]
+        losses, outs = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=(step == 0), T=1)
+        optim.zero_grad()
+        (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+        torch.cuda.synchronize()
+        pre = "s%d_" % step
+        l2, mx = rel(outs["logits"].detach(), g[pre + "logits"])
+        print("vgg step", step, "logits rel-L2 %.2e max %.2e" % (l2, mx))
+        assert l2 < 1e-3 and mx < 1e-3
+        lab = outs["teacher_labels"].cpu().to(torch.uint8)
+        agree = (lab == torch.from_numpy(g[pre + "teacher_labels"])).float().mean().item()
+        print("vgg step", step, "pseudo-label agreement %.6f" % agree)
+        assert agree > 0.999
+        for k in ("self_ce", "loss_ce", "teacher_diff"):
+            gv = float(g[pre + k].reshape(-1)[0]); v = float(losses[k].detach().reshape(-1)[0])
+            print(k, v, gv)
+            assert abs(v - gv) <= 3e-3 * max(abs(gv), 1e-3), (k, v, gv)
+        gn = g[pre + "grad_norms"]
+        mine = np.array([params[n].grad.double().norm().item() for n in names])
+        relerr = np.abs(mine - gn) / np.maximum(gn, 1e-12)
+        print("vgg step", step, "grad-norm max rel err %.2e (%s)" % (relerr.max(), names[int(relerr.argmax())]))
+        assert relerr.max() < 2e-2
+        for key in g.files:
+            if key.startswith(pre + "grad::"):
+                n = key.split("::")[1]
+                gg = params[n].grad
+                gg = gg.flatten()[:60000] if gg.numel() > 60000 else gg
+                e = rel(gg.reshape(g[key].shape), g[key])[0]
+                print("   grad", n, "rel-L2 %.2e" % e)
+                assert e < 3e-2, key
+        if step == 0:
+            optim.step()
+            assert rel(m.backbone.features[44].bias.detach(), g["s0_post_step::features.44.bias"])[1] < 1e-4
