@@ -200,3 +200,10 @@ class ModelCfg(object):
     THRESHOLD_BETA = 1e-3
     OPT = "SGD"
     OPT_NESTEROV = False
+
+
+class ModelCfgVGG16(ModelCfg):
+    """cfg.MODEL of configs/deeplabv2_vgg16_train.yaml:22-33"""
+    ARCH = "deeplabv2_vgg16_bn"
+    LR_TARGET = 2.0
+    RUN_CONF_LOWER = 0.1

@@ -89,7 +89,7 @@ def test_oracle_vgg16_config1_matches_reference():
     import os
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_vgg16_cfg1.npz"))
     torch.set_num_threads(8)
-    cfg = synth.ModelCfg()
+    cfg = synth.ModelCfgVGG16()
     student = O.as_leaf_params(synth.make_vgg16_params(seed=321))
     groups = O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY)
     assert [len(x["params"]) for x in groups] == [26, 26, 6, 6]

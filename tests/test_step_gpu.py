@@ -231,8 +231,7 @@ def test_vgg16_config1_two_steps_match_reference_golden():
     from da_sac_b200 import synth
     from da_sac_b200.models import get_model
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_vgg16_cfg1.npz"))
-    cfg = synth.ModelCfg()
-    cfg.ARCH = "deeplabv2_vgg16_bn"
+    cfg = synth.ModelCfgVGG16()
     m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
     m.backbone.load_state_dict(synth.make_vgg16_params(seed=321))
     m.cuda().train()
