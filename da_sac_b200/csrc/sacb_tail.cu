@@ -355,9 +355,11 @@ __global__ void loss_finalize_kernel(const double* __restrict__ scratch, float* 
 // one warp per low-resolution logit pixel (b, yy, xx); lanes sweep the up-sampled pixels that touch it.
 template <int C_>
 __global__ void __launch_bounds__(256)
-loss_bwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const float* __restrict__ conf_mean,
-                const float* __restrict__ running_conf, float focal_p, float coef, float* __restrict__ dlogits, int BT,
-                int C, int h, int w, int H, int W) {
+loss_bwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const int64_t* __restrict__ y,
+                const float* __restrict__ conf_mean, const float* __restrict__ running_conf, float focal_p, float coef,
+                float* __restrict__ dlogits, int BT, int C, int h, int w, int H, int W) {
+  // labels != NULL: gradient of self_ce (pseudo labels, focal weight, batch-mean confidence; sac.py:134-149)
+  // labels == NULL: gradient of the plain loss_ce against y (deeplabv2.py:223-224; used by the source-domain pass)
   const int wid = (blockIdx.x * 256 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= BT * h * w) return;
@@ -383,7 +385,9 @@ loss_bwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ la
     const float wx = (cx.i0 == xx ? cx.l0 : 0.f) + (cx.i1 == xx ? cx.l1 : 0.f);
     const float wgt = wy * wx;
     if (wgt == 0.f) continue;
-    const int lab = labels[(size_t)b * HW + i * W + j];
+    int lab;
+    if (labels) lab = labels[(size_t)b * HW + i * W + j];
+    else { const long long t = y[(size_t)b * HW + i * W + j]; lab = (t >= 0 && t < C) ? (int)t : 255; }
     if (lab >= C) continue;
     float v[C_];
     up_logits<C_>(L, C, h, w, cy, cx, v);
@@ -393,9 +397,12 @@ loss_bwd_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ la
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) { v[c] = expf(v[c] - mx); sum += v[c]; }
-    const float base = 1.f - fmaxf(running_conf[lab], 0.f);
-    const float fw = (focal_p == 3.f) ? base * base * base : powf(base, focal_p);
-    const float k = coef * fw * conf_mean[i * W + j] * wgt;
+    float k = coef * wgt;
+    if (labels) {
+      const float base = 1.f - fmaxf(running_conf[lab], 0.f);
+      const float fw = (focal_p == 3.f) ? base * base * base : powf(base, focal_p);
+      k *= fw * conf_mean[i * W + j];
+    }
     const float inv = 1.f / sum;
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) acc[c] += k * (v[c] * inv - (c == lab ? 1.f : 0.f));
@@ -541,7 +548,7 @@ extern "C" int sacb_student_loss_bwd(const SacbLoss* d, void* stream) {
   const int HW = d->H * d->W;
   const float coef = d->grad_scale / (float)((double)d->BT * HW);
   const size_t warps = (size_t)d->BT * d->h * d->w;
-  loss_bwd_kernel<19><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ST>>>(d->logits, d->labels, d->conf_mean,
+  loss_bwd_kernel<19><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ST>>>(d->logits, d->labels, d->y, d->conf_mean,
                                                                           d->running_conf, d->focal_p, coef, d->dlogits,
                                                                           d->BT, d->C, d->h, d->w, d->H, d->W);
   LAUNCHED();

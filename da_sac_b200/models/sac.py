@@ -61,22 +61,31 @@ class SAC_Baseline(BaseNet):
 
 
 class _StudentLossFn(torch.autograd.Function):
-    """(loss_ce, self_ce) = fused upsample + log-softmax + NLL (deeplabv2.py:217-224, sac.py:134-149)"""
+    """(loss_ce, self_ce) = fused upsample + log-softmax + NLL (deeplabv2.py:217-224, sac.py:134-149).
+    Two outputs with un-materialised gradients: the backward kernel only runs for the loss that is actually
+    back-propagated (self_ce on the target step, train.py:231; loss_ce on the source step, train.py:133)."""
 
     @staticmethod
     def forward(ctx, sac, logits, y, tail):
         desc, keep = sac._loss_desc(logits, y, tail, 0.0, None)
         L.check(L.lib().sacb_student_loss_fwd(C.byref(desc), L.stream()), "sacb_student_loss_fwd")
         ctx.sac, ctx.logits, ctx.y, ctx.tail = sac, logits, y, tail
-        return keep["losses"].clone()
+        ctx.set_materialize_grads(False)
+        both = keep["losses"].clone()
+        return both[0:1], both[1:2]
 
     @staticmethod
-    def backward(ctx, g):
-        # only self_ce is differentiated on the target step (train.py:231); loss_ce is monitoring (sac.py:340)
-        dlogits = torch.empty_like(ctx.logits)
-        desc, keep = ctx.sac._loss_desc(ctx.logits, ctx.y, ctx.tail, 1.0, dlogits)
-        L.check(L.lib().sacb_student_loss_bwd(C.byref(desc), L.stream()), "sacb_student_loss_bwd")
-        return None, dlogits * g[1], None, None
+    def backward(ctx, g_ce, g_self):
+        total = None
+        for g, use_labels in ((g_self, True), (g_ce, False)):
+            if g is None:
+                continue
+            dl = torch.empty_like(ctx.logits)
+            desc, keep = ctx.sac._loss_desc(ctx.logits, ctx.y, ctx.tail, 1.0, dl, use_labels=use_labels)
+            L.check(L.lib().sacb_student_loss_bwd(C.byref(desc), L.stream()), "sacb_student_loss_bwd")
+            dl = dl * g
+            total = dl if total is None else total + dl
+        return None, total, None, None
 
 
 class SAC(SAC_Baseline):
@@ -155,11 +164,11 @@ class SAC(SAC_Baseline):
         L.check(L.lib().sacb_teacher_tail(C.byref(d), L.stream()), "sacb_teacher_tail")
         return ws
 
-    def _loss_desc(self, logits, y, tail, grad_scale, dlogits):
+    def _loss_desc(self, logits, y, tail, grad_scale, dlogits, use_labels=True):
         BT, Cn, h, w = logits.shape
         H, W = y.shape[-2:]
         keep = tail
-        d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), L.ptr(tail["labels"]),
+        d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), L.ptr(tail["labels"]) if use_labels else None,
                    L.ptr(tail["conf_mean"]), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
                    L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits))
         return d, keep
@@ -194,13 +203,13 @@ class SAC(SAC_Baseline):
             BT = x.shape[0]
             tail = self._workspace(BT, 1, H, W, dev)
             tail["labels"].fill_(255); tail["conf_mean"].zero_()
-        both = _StudentLossFn.apply(self, s_logits, y_raw, tail)
-        losses["loss_ce"] = both[0:1]
+        loss_ce, self_ce = _StudentLossFn.apply(self, s_logits, y_raw, tail)
+        losses["loss_ce"] = loss_ce
         outs = LazyOuts(logits=s_logits)
         from .deeplabv2 import upsample
         outs.lazy("logits_up", lambda: upsample(s_logits.detach(), H, W))
         if use_teacher:
-            losses["self_ce"] = both[1:2]                                # sac.py:360-361
+            losses["self_ce"] = self_ce                                  # sac.py:360-361
             outs["teacher_conf"] = tail["conf"]
             outs["running_conf"] = self.running_conf
             outs.lazy("teacher_labels", lambda: tail["labels"].long())

@@ -208,6 +208,7 @@ typedef struct SacbLoss {
   float* dlogits;                /* [BT,C,h,w] or NULL */
 } SacbLoss;
 int sacb_student_loss_fwd(const SacbLoss* d, void* stream);
+/* dlogits = grad_scale * d(self_ce)/d(logits); with d->labels == NULL: grad_scale * d(loss_ce)/d(logits) (CE against y) */
 int sacb_student_loss_bwd(const SacbLoss* d, void* stream);
 /* bilinear align_corners=True upsample [B,C,h,w] -> [B,C,H,W] (F.interpolate, deeplabv2.py:217) */
 int sacb_upsample(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream);

@@ -273,3 +273,31 @@ def test_vgg16_config1_two_steps_match_reference_golden():
         if step == 0:
             optim.step()
             assert rel(m.backbone.features[44].bias.detach(), g["s0_post_step::features.44.bias"])[1] < 1e-4
+
+
+def test_source_pass_loss_ce_backward_matches_oracle(net):
+    """Trainer.step(train=True) semantics (train.py:119-138): net(image, gt) -> loss_ce.backward(). The plain CE against y
+    goes through the same fused loss kernels (labels == NULL mode)."""
+    from da_sac_b200 import synth
+    from oracle import sac_oracle as O
+    m, cfg = net
+    sd = synth.make_backbone_params(seed=123)
+    m.backbone.load_state_dict(sd)
+    m.train()
+    x, y, _, _, _ = synth.make_target_batch(N_GROUPS, K, HW, seed=3)
+    y = y.clone(); y[y == -1] = 255
+    for p in m.backbone.parameters():
+        p.grad = None
+    losses, outs = m(x.cuda(), y.clone().cuda())
+    assert "self_ce" not in losses
+    losses["loss_ce"].mean().backward()
+    torch.cuda.synchronize()
+    student = O.as_leaf_params(sd)
+    ref_losses, _ = O.backbone_forward(student, x, y)
+    ref_losses["loss_ce"].mean().backward()
+    assert abs(float(losses["loss_ce"].detach().reshape(-1)[0]) - float(ref_losses["loss_ce"].detach().reshape(-1)[0])) < 2e-4 * float(ref_losses["loss_ce"].detach().reshape(-1)[0])
+    params = dict(m.backbone.named_parameters())
+    for n in ("model.layer5.conv2d_list.0.weight", "model.layer4.1.conv2.weight", "model.layer3.10.bn2.weight", "model.layer1.0.conv1.weight"):
+        e = rel(params[n].grad, student[n].grad)[0]
+        print("   source-pass grad", n, "rel-L2 %.2e" % e)
+        assert e < grad_tol(n), n
