@@ -428,6 +428,79 @@ __global__ void upsample_kernel(const float* __restrict__ in, float* __restrict_
   }
 }
 
+// out = up(in) (+ addend): bilinear, align_corners=True, [BC,h,w] -> [BC,H,W]  (fcn.py:107-109 up_x2 and score fusion :111-134)
+__global__ void upsample_add_kernel(const float* __restrict__ in, const float* __restrict__ addend, float* __restrict__ out,
+                                    int BC, int h, int w, int H, int W) {
+  const size_t total = (size_t)BC * H * W;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % W);
+    const int i = (int)((t / W) % H);
+    const size_t bc = t / ((size_t)W * H);
+    const UpCoef cy = up_coef(i, h, H), cx = up_coef(j, w, W);
+    const float* p = in + bc * h * w;
+    float v = cy.l0 * (cx.l0 * p[cy.i0 * w + cx.i0] + cx.l1 * p[cy.i0 * w + cx.i1]) +
+              cy.l1 * (cx.l0 * p[cy.i1 * w + cx.i0] + cx.l1 * p[cy.i1 * w + cx.i1]);
+    if (addend) v += addend[t];
+    out[t] = v;
+  }
+}
+// adjoint of the bilinear align_corners=True upsample: g_in[bc,y,x] = sum_{(i,j)} wy(i,y) wx(j,x) g_out[bc,i,j]  (gather form)
+__global__ void upsample_bwd_kernel(const float* __restrict__ g_out, float* __restrict__ g_in, int BC, int h, int w, int H,
+                                    int W) {
+  const size_t total = (size_t)BC * h * w;
+  const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(t % w);
+    const int yy = (int)((t / w) % h);
+    const size_t bc = t / ((size_t)w * h);
+    const int i_lo = sy > 0.f ? max(0, (int)floorf((float)(yy - 1) / sy) - 1) : 0;
+    const int i_hi = sy > 0.f ? min(H - 1, (int)ceilf((float)(yy + 1) / sy) + 1) : H - 1;
+    const int j_lo = sx > 0.f ? max(0, (int)floorf((float)(xx - 1) / sx) - 1) : 0;
+    const int j_hi = sx > 0.f ? min(W - 1, (int)ceilf((float)(xx + 1) / sx) + 1) : W - 1;
+    const float* g = g_out + bc * H * W;
+    float acc = 0.f;
+    for (int i = i_lo; i <= i_hi; ++i) {
+      const UpCoef cy = up_coef(i, h, H);
+      const float wy = (cy.i0 == yy ? cy.l0 : 0.f) + (cy.i1 == yy ? cy.l1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int j = j_lo; j <= j_hi; ++j) {
+        const UpCoef cx = up_coef(j, w, W);
+        const float wx = (cx.i0 == xx ? cx.l0 : 0.f) + (cx.i1 == xx ? cx.l1 : 0.f);
+        if (wx != 0.f) acc += wy * wx * g[i * W + j];
+      }
+    }
+    g_in[t] = acc;
+  }
+}
+// fp32 NCHW [N,C,P,Q] -> split planes NHWC [N,P,Q,Cp] (channels >= C zero): feeds the GEMM gradients of the 19-class score convs
+__global__ void nchw_to_planes_kernel(const float* __restrict__ g, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int N,
+                                      int C, int PQ, int Cp) {
+  const size_t total = (size_t)N * PQ * Cp;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % Cp);
+    const size_t pix = t / Cp;
+    const int n = (int)(pix / PQ);
+    const int r = (int)(pix - (size_t)n * PQ);
+    const float v = c < C ? g[((size_t)n * C + c) * PQ + r] : 0.f;
+    const uint16_t h = float_to_bf16_bits(v);
+    hi[t] = h;
+    lo[t] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+  }
+}
+// Dropout2d (fcn.py:52,56) on split planes: x[n,p,q,c] *= m[n,c]   (m = 0 or 1/(1-p), drawn by the caller)
+__global__ void channel_scale_kernel(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, const float* __restrict__ m, int N,
+                                     int PQ, int C) {
+  const size_t total = (size_t)N * PQ * C;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const int n = (int)(t / ((size_t)PQ * C));
+    const float v = (bf16_bits_to_float(hi[t]) + bf16_bits_to_float(lo[t])) * m[(size_t)n * C + c];
+    const uint16_t h = float_to_bf16_bits(v);
+    hi[t] = h;
+    lo[t] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+  }
+}
+
 // ---------------------------------------------------------------- multi-tensor EMA / norm and SGD
 constexpr int SEG_CHUNKS = 16;
 __global__ void __launch_bounds__(256)
@@ -558,6 +631,32 @@ extern "C" int sacb_student_loss_bwd(const SacbLoss* d, void* stream) {
 extern "C" int sacb_upsample(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream) {
   const size_t total = (size_t)B * C * H * W;
   upsample_kernel<<<grid1(total, 256), 256, 0, ST>>>(in, out, B * C, h, w, H, W);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_upsample_add(const float* in, const float* addend, float* out, int B, int C, int h, int w, int H, int W,
+                                 void* stream) {
+  const size_t total = (size_t)B * C * H * W;
+  upsample_add_kernel<<<grid1(total, 256), 256, 0, ST>>>(in, addend, out, B * C, h, w, H, W);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_upsample_bwd(const float* g_out, float* g_in, int B, int C, int h, int w, int H, int W, void* stream) {
+  const size_t total = (size_t)B * C * h * w;
+  upsample_bwd_kernel<<<grid1(total, 256), 256, 0, ST>>>(g_out, g_in, B * C, h, w, H, W);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_nchw_to_planes(const float* g, void* hi, void* lo, int N, int C, int P, int Q, int Cp, void* stream) {
+  const size_t total = (size_t)N * P * Q * Cp;
+  nchw_to_planes_kernel<<<grid1(total, 256), 256, 0, ST>>>(g, (uint16_t*)hi, (uint16_t*)lo, N, C, P * Q, Cp);
+  LAUNCHED();
+  return 0;
+}
+extern "C" int sacb_channel_scale(void* hi, void* lo, const float* m, int N, int P, int Q, int C, void* stream) {
+  const size_t total = (size_t)N * P * Q * C;
+  channel_scale_kernel<<<grid1(total, 256), 256, 0, ST>>>((uint16_t*)hi, (uint16_t*)lo, m, N, P * Q, C);
   LAUNCHED();
   return 0;
 }

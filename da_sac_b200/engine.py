@@ -113,8 +113,51 @@ def build_vgg16_deeplab(H, W):
     return dict(arch="vgg16", specs=specs, order=order, stem=seq[0][1], seq=seq, aspp=aspp, out_hw=(h, w), stem_kp=64)
 
 
+FCN_BLOCKS = (("block1", ((0, 3, 64), (3, 64, 64), (7, 64, 128), (10, 128, 128), (14, 128, 256), (17, 256, 256), (20, 256, 256)), (3, 10, 20)),
+              ("block2", ((24, 256, 512), (27, 512, 512), (30, 512, 512)), (30,)),
+              ("block3", ((34, 512, 512), (37, 512, 512), (40, 512, 512)), (40,)))
+
+
+def build_vgg16_fcn(H, W):
+    """Layer table of VGG16_FCN8s(use_bn=True) (/root/reference/models/fcn.py:10-149): vgg16_bn features split into
+    block1 (.. pool3), block2 (.. pool4), block3 (.. pool5); head = 7x7 conv 512->4096 + BN + ReLU + Dropout2d, 1x1
+    4096->4096 + BN + ReLU + Dropout2d, 1x1 4096->19; score_pool4 / score_pool3 1x1 convs; bilinear x2 fusion."""
+    specs, order, seq = {}, [], []
+    h, w = H, W
+
+    def add(name, bn, K, Cc, R, dil, pad):
+        s = ConvSpec(name, bn, K, Cc, R, 1, dil, pad, bias=True)
+        s.hin, s.win, s.hout, s.wout = h, w, h, w
+        specs[name] = s; order.append(name)
+        return s
+
+    taps = {}
+    for blk, convs, pools in FCN_BLOCKS:
+        for (idx, cin, cout) in convs:
+            s = add("%s.%d" % (blk, idx), "%s.%d" % (blk, idx + 1), cout, cin, 3, 1, 1)
+            seq.append(("conv", s))
+            if idx in pools:
+                tag = "pool%d" % idx
+                seq.append(("pool", (h, w, h // 2, w // 2, cout, tag)))
+                h, w = h // 2, w // 2
+                taps[tag] = (h, w, cout)
+    head0 = add("vgg_head.0", "vgg_head.1", 4096, 512, 7, 1, 3)
+    head4 = add("vgg_head.4", "vgg_head.5", 4096, 4096, 1, 1, 0)
+    head8 = add("vgg_head.8", None, NUM_CLASSES, 4096, 1, 1, 0)
+    h16, w16, _ = taps["pool30"]
+    h8, w8, _ = taps["pool20"]
+    sp4 = ConvSpec("score_pool4", None, NUM_CLASSES, 512, 1, 1, 1, 0, bias=True)
+    sp4.hin, sp4.win, sp4.hout, sp4.wout = h16, w16, h16, w16
+    sp3 = ConvSpec("score_pool3", None, NUM_CLASSES, 256, 1, 1, 1, 0, bias=True)
+    sp3.hin, sp3.win, sp3.hout, sp3.wout = h8, w8, h8, w8
+    for s_ in (sp4, sp3):
+        specs[s_.name] = s_; order.append(s_.name)
+    return dict(arch="fcn", specs=specs, order=order, stem=seq[0][1], seq=seq, aspp=[], out_hw=(h8, w8), stem_kp=64,
+                head=(head0, head4, head8), score=(sp4, sp3), hw32=(h, w), hw16=(h16, w16))
+
+
 def build_net(arch, H, W):
-    return build_resnet101(H, W) if arch == "resnet101" else build_vgg16_deeplab(H, W)
+    return {"resnet101": build_resnet101, "vgg16": build_vgg16_deeplab, "fcn": build_vgg16_fcn}[arch](H, W)
 
 
 def param_layout(net):
@@ -186,7 +229,7 @@ class WeightPlanes(object):
         self.stem_n = net["stem"].K * net["stem_kp"]
         nf += self.stem_n
         self.aspp_off = (nf, nt)
-        self.aspp_n = ASPP_JPAD * net["aspp"][0].C
+        self.aspp_n = ASPP_JPAD * net["aspp"][0].C if net["aspp"] else 0
         nf += self.aspp_n; nt += self.aspp_n
         bf = torch.bfloat16
         self.wf_hi = torch.empty(nf, device=device, dtype=bf); self.wf_lo = torch.empty(nf, device=device, dtype=bf)
@@ -243,6 +286,8 @@ class WeightPlanes(object):
         L.check(lib.sacb_stem_pack_weight(L.ptr(flat.view(stem.name + ".weight")), L.ptr(sh_), L.ptr(sl_), stem.K,
                                           3 * stem.R * stem.R, self.net["stem_kp"], st), "sacb_stem_pack_weight")
         a = self.net["aspp"]
+        if not a:
+            return
         f, t = self.aspp()
         L.check(lib.sacb_aspp_pack_weights(*[L.ptr(flat.view(x.name + ".weight")) for x in a], a[0].C,
                                            L.ptr(f[0]), L.ptr(f[1]), L.ptr(t[0]), L.ptr(t[1]), st), "sacb_aspp_pack_weights")
@@ -289,7 +334,8 @@ class EngineBase(object):
         self.stem_a = self._planes(N * stem.hout * stem.wout, net["stem_kp"])     # im2col matrix of the first conv (kept for wgrad)
         self.stem_dw = torch.empty(stem.K * 3 * stem.R * stem.R, device=device)
         oh, ow = net["out_hw"]
-        self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)           # tap-unrolled ASPP partial outputs
+        if net["aspp"]:
+            self.zbuf = torch.empty(N * oh * ow * ASPP_JPAD, device=device)       # tap-unrolled ASPP partial outputs
 
     def _planes(self, m, c):
         bf = torch.bfloat16
@@ -374,6 +420,49 @@ class EngineBase(object):
                                      (N, stem.hout, stem.wout, kp, stem.Kt, 1, 1, 1, 0), k_valid=stem.K)
         L.check(lib.sacb_stem_unpack_wgrad(L.ptr(parts), splits, L.ptr(self.stem_dw), stem.K, taps, kp, st), "sacb_stem_unpack_wgrad")
         self._finalize(flat, wp, stem, self.stem_dw, grad, dbeta, C_eff=taps, RS=1)
+
+    def _trunk_backward(self, flat, wp, seq, i, g, dbeta, gp, grad, inject=None):
+        """Backward through a plain conv / 2x2-max-pool chain seq[0..i] (VGG trunks).
+        Entering at a conv: ``g`` = masked gradient planes at its output (pool tag "gout"), ``dbeta`` their column sums.
+        Entering at a pool: ``gp`` = un-masked fp32 gradient at the pool output. ``inject[tag]`` (fp32) is added to the
+        gradient arriving at pool ``tag`` (FCN score branches)."""
+        lib, st, N = L.lib(), L.stream(), self.N
+        inject = inject or {}
+        while i >= 0:
+            kind, it = seq[i]
+            if kind == "pool":
+                h, w, ph, pw, c, tag = it
+                src = seq[i - 1][1]                       # conv feeding the pool (its output is a ReLU output)
+                gx = self._tplanes("gout", N * h * w * c)
+                L.check(lib.sacb_maxpool2_bwd(L.ptr(gp), L.ptr(self.pool_idx[tag]), L.ptr(self.act[src.name].hi), L.ptr(gx.hi),
+                                              L.ptr(gx.lo), N, h, w, c, ph, pw, st), "sacb_maxpool2_bwd")
+                self.fpool.put("gp")
+                dbeta = self._new_dbeta(c)
+                L.check(lib.sacb_colsum(L.ptr(gx.hi), L.ptr(gx.lo), L.ptr(dbeta), C.c_int64(N * h * w), c, st), "sacb_colsum")
+                g = gx
+                i -= 1
+                continue
+            s = it
+            if i == 0:
+                self._first_conv_bwd(flat, wp, g, grad, dbeta)
+                self._tput("gout")
+                return
+            pkind, pit = seq[i - 1]
+            xin = self.act[pit.name] if pkind == "conv" else self.act[pit[5]]
+            self._wgrad(flat, wp, s, xin, g, grad, dbeta)
+            th, tl = wp.wt(s.name)
+            if pkind == "conv":
+                gx = self._tplanes("gx", N * s.hin * s.win * s.C)
+                dbeta = self._new_dbeta(s.C)
+                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo, colsum=dbeta)
+                self._tput("gout"); self._rename("gx", "gout")
+                g = gx
+            else:
+                # the conv's input is a max-pool output: un-masked fp32 gradient, routed through the pool afterwards
+                gp = self.fpool.get("gp", N * s.hin * s.win * s.C)
+                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), add_f32=inject.get(pit[5]), out_f32=gp)
+                self._tput("gout")
+            i -= 1
 
     def _new_dbeta(self, K):
         o = self._dbeta_off
@@ -595,40 +684,130 @@ class VGG16Engine(EngineBase):
         seq = net["seq"]
         last = seq[-1][1]
         g, dbeta = self._aspp_bwd(flat, wp, self.act[last.name], dlogits, grad)      # g = grad at fc7's output (masked)
-        i = len(seq) - 1
-        while i >= 0:
-            kind, s = seq[i]
-            assert kind == "conv"
-            if i == 0:
-                self._first_conv_bwd(flat, wp, g, grad, dbeta)
-                break
-            pkind, pit = seq[i - 1]
-            xin = self.act[pit.name] if pkind == "conv" else self.act[pit[5]]
-            self._wgrad(flat, wp, s, xin, g, grad, dbeta)
-            th, tl = wp.wt(s.name)
-            if pkind == "conv":
-                gx = self._tplanes("gx", N * s.hin * s.win * s.C)
-                dbeta = self._new_dbeta(s.C)
-                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), mask_hi=xin.hi, out_hi=gx.hi, out_lo=gx.lo, colsum=dbeta)
-                self._tput("gout"); self._rename("gx", "gout")
-                g = gx
-                i -= 1
+        self._trunk_backward(flat, wp, seq, len(seq) - 1, g, dbeta, None, grad)
+
+
+class FCN8sEngine(EngineBase):
+    """VGG16_FCN8s(use_bn=True) (/root/reference/models/fcn.py): VGG trunk with five 2x2 pools, 7x7 / 1x1 head with
+    channel dropout, three 19-class 1x1 score convs fused by bilinear x2 up-sampling (align_corners=True)."""
+
+    def __init__(self, N, H, W, device):
+        EngineBase.__init__(self, build_vgg16_fcn(H, W), N, H, W, device)
+        net = self.net
+        max_elems = 0
+        self.pool_idx = {}
+        for kind, it in net["seq"]:
+            if kind == "conv":
+                self.act[it.name] = self._planes(N * it.hout * it.wout, it.K)
+                max_elems = max(max_elems, N * it.hout * it.wout * it.K)
             else:
-                # the conv's input is a max-pool output: un-masked fp32 gradient, routed through the pool to the conv before it
-                h, w, ph, pw, c, tag = pit
-                gp = self.fpool.get("gp", N * ph * pw * c)
-                L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), out_f32=gp)
-                self._tput("gout")
-                src = seq[i - 2][1]                       # conv feeding the pool
-                gx = self._tplanes("gout", N * h * w * c)
-                L.check(lib.sacb_maxpool2_bwd(L.ptr(gp), L.ptr(self.pool_idx[tag]), L.ptr(self.act[src.name].hi), L.ptr(gx.hi),
-                                              L.ptr(gx.lo), N, h, w, c, ph, pw, st), "sacb_maxpool2_bwd")
-                self.fpool.put("gp")
-                dbeta = self._new_dbeta(c)
-                L.check(lib.sacb_colsum(L.ptr(gx.hi), L.ptr(gx.lo), L.ptr(dbeta), C.c_int64(N * h * w), c, st), "sacb_colsum")
-                g = gx
-                i -= 2
+                h, w, ph, pw, c, tag = it
+                self.act[tag] = self._planes(N * ph * pw, c)
+                self.pool_idx[tag] = torch.empty(N * ph * pw * c, device=device, dtype=torch.uint8)
+        h32, w32 = net["hw32"]; h16, w16 = net["hw16"]; h8, w8 = net["out_hw"]
+        head0, head4, head8 = net["head"]
+        for hd in (head0, head4):
+            self.act[hd.name] = self._planes(N * h32 * w32, hd.K)
+        max_elems = max(max_elems, N * h32 * w32 * 4096)
+        self._make_pools(max_elems, 4, 2)
+        f32 = dict(device=device, dtype=torch.float32)
+        self.s32 = torch.empty(N, NUM_CLASSES, h32, w32, **f32)
+        self.s4 = torch.empty(N, NUM_CLASSES, h16, w16, **f32); self.t16 = torch.empty_like(self.s4)
+        self.s3 = torch.empty(N, NUM_CLASSES, h8, w8, **f32)
+        self.d16 = torch.empty_like(self.s4); self.d32 = torch.empty_like(self.s32)
+        self.gsc = {8: self._planes(N * h8 * w8, 64), 16: self._planes(N * h16 * w16, 64), 32: self._planes(N * h32 * w32, 64)}
+        self.inj3 = torch.empty(N * h8 * w8 * 256, **f32); self.inj4 = torch.empty(N * h16 * w16 * 512, **f32)
+        self.dropout = None          # (mask0 [N,4096], mask4 [N,4096]) of Dropout2d scale factors, or None (eval / p = 0)
+
+    def _score(self, wp, s, xin, out_nchw):
+        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+        L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), k_valid=s.K, scale=sc, shift=sh, out_nchw=out_nchw)
+
+    def forward(self, flat, wp, x, logits_out, keep):
+        # teacher and student both use the persistent activation set: the (no-grad) teacher pass always precedes the
+        # student pass of the same step, and the score convs need pool3 / pool4 after the trunk has moved on
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        a = None
+        for kind, it in net["seq"]:
+            if kind == "conv":
+                o = self.act[it.name]
+                if a is None: self._first_conv_fwd(flat, wp, x, o)
+                else: self._unit(wp, it, a, o, relu=True)
+                a = o
+            else:
+                h, w, ph, pw, c, tag = it
+                o = self.act[tag]
+                L.check(lib.sacb_maxpool2_fwd(L.ptr(a.hi), L.ptr(a.lo), L.ptr(o.hi), L.ptr(o.lo), L.ptr(self.pool_idx[tag]),
+                                              N, h, w, c, ph, pw, st), "sacb_maxpool2_fwd")
+                a = o
+        head0, head4, head8 = net["head"]
+        sp4, sp3 = net["score"]
+        h32, w32 = net["hw32"]; h16, w16 = net["hw16"]; h8, w8 = net["out_hw"]
+        for j, hd in enumerate((head0, head4)):
+            o = self.act[hd.name]
+            self._unit(wp, hd, a, o, relu=True)
+            if self.dropout is not None:                  # Dropout2d after the ReLU (fcn.py:52,56)
+                L.check(lib.sacb_channel_scale(L.ptr(o.hi), L.ptr(o.lo), L.ptr(self.dropout[j]), N, h32, w32, hd.K, st), "sacb_channel_scale")
+            a = o
+        self._score(wp, head8, a, self.s32)
+        self._score(wp, sp4, self.act["pool30"], self.s4)
+        self._score(wp, sp3, self.act["pool20"], self.s3)
+        Cn = NUM_CLASSES                                   # score fusion (fcn.py:111-134)
+        L.check(lib.sacb_upsample_add(L.ptr(self.s32), L.ptr(self.s4), L.ptr(self.t16), N, Cn, h32, w32, h16, w16, st), "sacb_upsample_add")
+        L.check(lib.sacb_upsample_add(L.ptr(self.t16), L.ptr(self.s3), L.ptr(logits_out), N, Cn, h16, w16, h8, w8, st), "sacb_upsample_add")
+        return logits_out
+
+    def _score_bwd(self, flat, wp, s, xin, d_nchw, res, grad, out_f32=None, mask=None, out=None, colsum=None):
+        """19-class 1x1 conv: d bias, filter gradient, data gradient (fp32 for pool inputs, masked planes for the head)"""
+        lib, st, N = L.lib(), L.stream(), self.N
+        g = self.gsc[res]
+        L.check(lib.sacb_nchw_to_planes(L.ptr(d_nchw), L.ptr(g.hi), L.ptr(g.lo), N, NUM_CLASSES, s.hout, s.wout, 64, st), "sacb_nchw_to_planes")
+        db = self._dbeta(g, N * s.hout * s.wout, 64)
+        self._wgrad(flat, wp, s, xin, g, grad, db)         # no BN: finalize copies scale(=1) * db into the bias gradient
+        th, tl = wp.wt(s.name)
+        L.conv_gemm(g.hi, g.lo, th, tl, s.geom_dgrad(N), out_f32=out_f32, mask_hi=mask,
+                    out_hi=None if out is None else out.hi, out_lo=None if out is None else out.lo, colsum=colsum)
+
+    def backward(self, flat, wp, x, dlogits, grad):
+        net, N, lib, st = self.net, self.N, L.lib(), L.stream()
+        self._begin_backward()
+        head0, head4, head8 = net["head"]
+        sp4, sp3 = net["score"]
+        h32, w32 = net["hw32"]; h16, w16 = net["hw16"]; h8, w8 = net["out_hw"]
+        Cn = NUM_CLASSES
+        p3, p4, p5 = self.act["pool20"], self.act["pool30"], self.act["pool40"]
+        a0, a4 = self.act[head0.name], self.act[head4.name]
+        # score branches (adjoints of the two bilinear x2 fusions)
+        self._score_bwd(flat, wp, sp3, p3, dlogits, 8, grad, out_f32=self.inj3)
+        L.check(lib.sacb_upsample_bwd(L.ptr(dlogits), L.ptr(self.d16), N, Cn, h16, w16, h8, w8, st), "sacb_upsample_bwd")
+        self._score_bwd(flat, wp, sp4, p4, self.d16, 16, grad, out_f32=self.inj4)
+        L.check(lib.sacb_upsample_bwd(L.ptr(self.d16), L.ptr(self.d32), N, Cn, h32, w32, h16, w16, st), "sacb_upsample_bwd")
+        # head: 4096->19, then the two conv+BN+ReLU(+dropout) units
+        M32 = N * h32 * w32
+        drop = self.dropout is not None
+        g4 = self._tplanes("gout", M32 * head4.K)
+        db4 = self._new_dbeta(head4.K)
+        self._score_bwd(flat, wp, head8, a4, self.d32, 32, grad, mask=a4.hi, out=g4, colsum=None if drop else db4)
+        if drop:
+            L.check(lib.sacb_channel_scale(L.ptr(g4.hi), L.ptr(g4.lo), L.ptr(self.dropout[1]), N, h32, w32, head4.K, st), "sacb_channel_scale")
+            L.check(lib.sacb_colsum(L.ptr(g4.hi), L.ptr(g4.lo), L.ptr(db4), C.c_int64(M32), head4.K, st), "sacb_colsum")
+        self._wgrad(flat, wp, head4, a0, g4, grad, db4)
+        g0 = self._tplanes("gx", M32 * head0.K)
+        db0 = self._new_dbeta(head0.K)
+        th, tl = wp.wt(head4.name)
+        L.conv_gemm(g4.hi, g4.lo, th, tl, head4.geom_dgrad(N), mask_hi=a0.hi, out_hi=g0.hi, out_lo=g0.lo, colsum=None if drop else db0)
+        if drop:
+            L.check(lib.sacb_channel_scale(L.ptr(g0.hi), L.ptr(g0.lo), L.ptr(self.dropout[0]), N, h32, w32, head0.K, st), "sacb_channel_scale")
+            L.check(lib.sacb_colsum(L.ptr(g0.hi), L.ptr(g0.lo), L.ptr(db0), C.c_int64(M32), head0.K, st), "sacb_colsum")
+        self._tput("gout"); self._rename("gx", "gout")
+        self._wgrad(flat, wp, head0, p5, g0, grad, db0)
+        gp = self.fpool.get("gp", M32 * head0.C)
+        th, tl = wp.wt(head0.name)
+        L.conv_gemm(g0.hi, g0.lo, th, tl, head0.geom_dgrad(N), out_f32=gp)
+        self._tput("gout")
+        seq = net["seq"]
+        self._trunk_backward(flat, wp, seq, len(seq) - 1, None, None, gp, grad, inject={"pool30": self.inj4, "pool20": self.inj3})
 
 
 def make_engine(arch, N, H, W, device):
-    return ResNet101Engine(N, H, W, device) if arch == "resnet101" else VGG16Engine(N, H, W, device)
+    return {"resnet101": ResNet101Engine, "vgg16": VGG16Engine, "fcn": FCN8sEngine}[arch](N, H, W, device)

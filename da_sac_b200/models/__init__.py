@@ -7,11 +7,13 @@ import os
 from functools import partial
 
 from .deeplabv2 import DeepLabV2_ResNet101, DeepLabV2_VGG16
+from .fcn import VGG16_FCN8s
 from .sac import SAC, SAC_Baseline
 
 
 def get_model(cfg, rank, *args, **kwargs):
-    models = {"deeplabv2_resnet101": DeepLabV2_ResNet101, "deeplabv2_vgg16_bn": partial(DeepLabV2_VGG16, use_bn=True)}
+    models = {"deeplabv2_resnet101": DeepLabV2_ResNet101, "deeplabv2_vgg16_bn": partial(DeepLabV2_VGG16, use_bn=True),
+              "fcn_vgg16_bn": partial(VGG16_FCN8s, use_bn=True)}
     arch = cfg.ARCH.lower()
     if arch not in models:
         raise NotImplementedError("libsac_b200: backbone '%s' is not built yet (SURVEY.md section 8(f)); available: %s"

@@ -69,6 +69,7 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, eng, x, *params):
         logits = torch.empty(x.shape[0], E.NUM_CLASSES, *eng.net["out_hw"], device=x.device)
+        net._pre_forward(eng, x, True)
         eng.forward(net._flat, net._planes(True), x, logits, keep=True)
         ctx.net, ctx.eng, ctx.x = net, eng, x
         return logits
@@ -129,6 +130,10 @@ class _EngineBackbone(BaseNet):
     def mark_dirty(self):
         self._version += 1
 
+    def _pre_forward(self, eng, x, with_grad):
+        """hook for per-forward engine state (FCN dropout masks)"""
+        return None
+
     def _planes(self, with_dgrad):
         if self._wp is None or self._wp.with_dgrad != with_dgrad:
             self._wp = E.WeightPlanes(E.build_net(self.ARCH, 64, 64), self._flat.buf.device, with_dgrad)
@@ -158,6 +163,7 @@ class _EngineBackbone(BaseNet):
         if trainable and torch.is_grad_enabled():
             return _BackboneFn.apply(self, eng, im, *self._params)
         out = torch.empty(im.shape[0], E.NUM_CLASSES, *eng.net["out_hw"], device=im.device)
+        self._pre_forward(eng, im, False)
         eng.forward(self._flat, self._planes(trainable), im, out, keep=False)
         return out
 

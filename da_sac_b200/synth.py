@@ -207,3 +207,44 @@ class ModelCfgVGG16(ModelCfg):
     ARCH = "deeplabv2_vgg16_bn"
     LR_TARGET = 2.0
     RUN_CONF_LOWER = 0.1
+
+
+FCN_CONVS = (("block1", (0, 3, 64)), ("block1", (3, 64, 64)), ("block1", (7, 64, 128)), ("block1", (10, 128, 128)),
+             ("block1", (14, 128, 256)), ("block1", (17, 256, 256)), ("block1", (20, 256, 256)),
+             ("block2", (24, 256, 512)), ("block2", (27, 512, 512)), ("block2", (30, 512, 512)),
+             ("block3", (34, 512, 512)), ("block3", (37, 512, 512)), ("block3", (40, 512, 512)))
+
+
+def make_fcn_params(seed=213, num_classes=NUM_CLASSES):
+    """Seeded VGG16_FCN8s(use_bn=True) state_dict (key layout of /root/reference/models/fcn.py:23-98)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+
+    def bn(prefix, c):
+        sd[prefix + ".weight"] = torch.rand(c, generator=g) * 0.4 + 0.8
+        sd[prefix + ".bias"] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[prefix + ".running_var"] = torch.rand(c, generator=g) * 0.4 + 0.8
+        sd[prefix + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def conv(name, cout, cin, k, gain=1.0):
+        sd[name + ".weight"] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k)) * gain
+        sd[name + ".bias"] = torch.randn(cout, generator=g) * 0.05
+
+    for blk, (idx, cin, cout) in FCN_CONVS:
+        conv("%s.%d" % (blk, idx), cout, cin, 3)
+        bn("%s.%d" % (blk, idx + 1), cout)
+    conv("vgg_head.0", 4096, 512, 7); bn("vgg_head.1", 4096)
+    conv("vgg_head.4", 4096, 4096, 1); bn("vgg_head.5", 4096)
+    conv("vgg_head.8", num_classes, 4096, 1, gain=4.0)
+    conv("score_pool4", num_classes, 512, 1, gain=2.0)
+    conv("score_pool3", num_classes, 256, 1, gain=2.0)
+    return sd
+
+
+class ModelCfgFCN(ModelCfg):
+    """cfg.MODEL of configs/fcn_vgg16_train.yaml"""
+    ARCH = "fcn_vgg16_bn"
+    LR = 5e-4
+    LR_TARGET = 2.0
+    RUN_CONF_LOWER = 0.1

@@ -213,6 +213,13 @@ int sacb_student_loss_bwd(const SacbLoss* d, void* stream);
 /* bilinear align_corners=True upsample [B,C,h,w] -> [B,C,H,W] (F.interpolate, deeplabv2.py:217) */
 int sacb_upsample(const float* in, float* out, int B, int C, int h, int w, int H, int W, void* stream);
 
+/* FCN-8s score fusion (fcn.py:107-134): out = bilinear_up(in, align_corners=True) (+ addend); its adjoint; the
+ * NCHW fp32 -> NHWC split-plane conversion that feeds the 19-class score convs' gradients; Dropout2d on split planes */
+int sacb_upsample_add(const float* in, const float* addend, float* out, int B, int C, int h, int w, int H, int W, void* stream);
+int sacb_upsample_bwd(const float* g_out, float* g_in, int B, int C, int h, int w, int H, int W, void* stream);
+int sacb_nchw_to_planes(const float* g_nchw, void* hi, void* lo, int N, int C, int P, int Q, int Cpad, void* stream);
+int sacb_channel_scale(void* hi, void* lo, const float* m /* [N,C] */, int N, int P, int Q, int C, void* stream);
+
 /* ---------------------------------------------------------------- optimiser-side multi-tensor kernels
  * flat fp32 buffers with a segment table: seg_ranges[2*i], seg_ranges[2*i+1] = [begin, end) of tensor i. */
 /* SAC._momentum_update (sac.py:83-102): out[0] = sum_seg ||slow-fast||_2 ; if update: slow = m*slow+(1-m)*fast */

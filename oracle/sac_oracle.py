@@ -103,10 +103,35 @@ def vgg16_deeplab_logits(p, x, taps=None):
     return out
 
 
+FCN_TRUNK = (("block1", (0, 3, 7, 10, 14, 17, 20), (3, 10, 20)), ("block2", (24, 27, 30), (30,)), ("block3", (34, 37, 40), (40,)))
+
+
+def vgg16_fcn8s_logits(p, x):
+    """VGG16_FCN8s._backbone (fcn.py:111-137) with drop_rate = 0 (Dropout2d is the identity): pool3/4/5 features, 7x7 /
+    1x1 head, score_pool4 / score_pool3, bilinear x2 (align_corners=True) fusion -> scores at 1/8 resolution."""
+    feats = {}
+    for blk, convs, pools in FCN_TRUNK:
+        for idx in convs:
+            x = F.conv2d(x, p["%s.%d.weight" % (blk, idx)], p["%s.%d.bias" % (blk, idx)], 1, 1)
+            x = F.relu(_bn_eval(x, p, "%s.%d" % (blk, idx + 1)))
+            if idx in pools:
+                x = F.max_pool2d(x, 2, 2)
+        feats[blk] = x
+    h = F.relu(_bn_eval(F.conv2d(feats["block3"], p["vgg_head.0.weight"], p["vgg_head.0.bias"], 1, 3), p, "vgg_head.1"))
+    h = F.relu(_bn_eval(F.conv2d(h, p["vgg_head.4.weight"], p["vgg_head.4.bias"]), p, "vgg_head.5"))
+    score = F.conv2d(h, p["vgg_head.8.weight"], p["vgg_head.8.bias"])
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)       # fcn.py:107-109
+    score = up(score) + F.conv2d(feats["block2"], p["score_pool4.weight"], p["score_pool4.bias"])
+    score = up(score) + F.conv2d(feats["block1"], p["score_pool3.weight"], p["score_pool3.bias"])
+    return score
+
+
 def backbone_forward(p, im, y=None):
     """DeepLabV2_ResNet101.forward / DeepLabV2_VGG16.forward (deeplabv2.py:213-227, 300-312); the architecture is
     recognised from the state_dict keys."""
-    logits = resnet101_logits(p, im) if "model.conv1.weight" in p else vgg16_deeplab_logits(p, im)
+    if "model.conv1.weight" in p: logits = resnet101_logits(p, im)
+    elif "vgg_head.0.weight" in p: logits = vgg16_fcn8s_logits(p, im)
+    else: logits = vgg16_deeplab_logits(p, im)
     logits_up = F.interpolate(logits, im.shape[-2:], mode="bilinear", align_corners=True)
     if y is None:
         return logits, logits_up
@@ -301,7 +326,7 @@ def parameter_groups(student, lr, wd):
         if not (k.endswith(".weight") or k.endswith(".bias")):
             continue
         # from-scratch layers (deeplabv2.py:201, 285-287): ASPP head; for VGG also fc6 / fc7
-        new = k.startswith("model.layer5.") or k.startswith("classifier.") or k.startswith("features.42.") or k.startswith("features.44.")
+        new = k.startswith(("model.layer5.", "classifier.", "features.42.", "features.44.", "vgg_head.", "score_pool"))
         isw = k.endswith(".weight")
         groups[(2 if new else 0) + (0 if isw else 1)]["params"].append(v)
     return list(groups)

@@ -37,15 +37,23 @@ if len(sys.argv) > 1 and sys.argv[1] == "vgg16":
     N_GROUPS, K, HW, ARCH = 1, 1, (256, 256), "vgg16"
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "fcn":
+    # VGG-16 FCN-8s (BASELINE.json configs[3] architecture) at a CPU-sized crop; Dropout2d disabled (drop_rate=0) so that
+    # the comparison does not depend on the RNG stream
+    N_GROUPS, K, HW, ARCH = 1, 2, (128, 128), "fcn"
+
+
 def build_reference_net():
     sys.path.insert(0, REF)
     from core.config import cfg, cfg_from_file, cfg_from_list
-    cfg_from_file(os.path.join(REF, "configs/deeplabv2_resnet101_train.yaml" if ARCH == "resnet101" else "configs/deeplabv2_vgg16_train.yaml"))
+    cfg_from_file(os.path.join(REF, {"resnet101": "configs/deeplabv2_resnet101_train.yaml", "vgg16": "configs/deeplabv2_vgg16_train.yaml",
+                                     "fcn": "configs/fcn_vgg16_train.yaml"}[ARCH]))
     cfg_from_list(["TRAIN.GROUP_SIZE", str(K), "TRAIN.NUM_GROUPS", str(N_GROUPS),
                    "DATASET.CROP_SIZE", "(%d,%d)" % HW, "MODEL.INIT_MODEL", ""])
     from models import get_model
+    extra = {"drop_rate": 0.0} if ARCH == "fcn" else {}
     net = get_model(cfg.MODEL, 0, num_classes=19,
-                    criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+                    criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"), **extra)
     sys.path.remove(REF)
     return net, cfg
 
@@ -54,7 +62,8 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     net, cfg = build_reference_net()
-    sd = synth.make_backbone_params(seed=123) if ARCH == "resnet101" else synth.make_vgg16_params(seed=321)
+    sd = {"resnet101": lambda: synth.make_backbone_params(seed=123), "vgg16": lambda: synth.make_vgg16_params(seed=321),
+          "fcn": lambda: synth.make_fcn_params(seed=213)}[ARCH]()
     missing = net.backbone.load_state_dict(sd, strict=True)
     print("loaded", missing)
     net.train()
@@ -69,7 +78,11 @@ def main():
         optim.zero_grad()
         (cfg.MODEL.LR_TARGET * losses["self_ce"].mean()).backward()
         pre = "s%d_" % step
-        out[pre + "logits"] = outs["logits"].detach().numpy()
+        if "logits" in outs:
+            out[pre + "logits"] = outs["logits"].detach().numpy()
+        else:                                   # VGG16_FCN8s exposes logits_up only (fcn.py:149)
+            with torch.no_grad():
+                out[pre + "logits"] = net.backbone._backbone(x).numpy()
         with torch.no_grad():
             tl, _ = net.slow_net(x2)
         out[pre + "teacher_logits"] = tl.numpy()
@@ -97,7 +110,7 @@ def main():
         valid = (lab != 255).float().mean().item()
         ncls = len(torch.unique(lab[lab != 255]))
         print("step", step, {k: float(v) for k, v in losses.items()}, "valid frac %.3f" % valid,
-              "classes", ncls, "ambiguous", int(amb.sum()), "logits absmax %.2f" % outs["logits"].abs().max().item())
+              "classes", ncls, "ambiguous", int(amb.sum()), "logits absmax %.2f" % float(np.abs(out[pre + "logits"]).max()))
         assert 0.1 <= valid <= 0.9 and ncls >= 5, "fixture not discriminative"
         # gradients
         names, norms = [], []
@@ -110,6 +123,9 @@ def main():
                  "model.layer2.0.downsample.0.weight", "model.layer3.5.bn2.weight", "model.layer3.5.bn2.bias",
                  "model.layer3.5.conv2.weight", "model.layer4.2.conv3.weight",
                  "model.layer5.conv2d_list.1.bias", "model.layer5.conv2d_list.3.weight") if ARCH == "resnet101" else \
+                ("block1.0.weight", "block1.1.bias", "block1.17.weight", "block2.27.weight", "block2.28.weight", "block3.40.bias",
+                 "vgg_head.0.weight", "vgg_head.1.weight", "vgg_head.4.weight", "vgg_head.5.bias", "vgg_head.8.weight",
+                 "vgg_head.8.bias", "score_pool4.weight", "score_pool3.weight", "score_pool3.bias") if ARCH == "fcn" else \
                 ("features.0.weight", "features.0.bias", "features.1.weight", "features.1.bias", "features.10.weight",
                  "features.18.weight", "features.24.bias", "features.36.weight", "features.42.weight", "features.44.bias",
                  "classifier.conv2d_list.0.bias", "classifier.conv2d_list.2.weight")
@@ -125,9 +141,11 @@ def main():
                     net.backbone.model.layer5.conv2d_list[1].bias.detach().numpy().copy()
                 out["s0_post_step::model.layer3.5.conv2.weight"] = \
                     net.backbone.model.layer3[5].conv2.weight.detach().flatten()[:60000].numpy().copy()
-            else:
+            elif ARCH == "vgg16":
                 out["s0_post_step::features.44.bias"] = net.backbone.features[44].bias.detach().numpy().copy()
-    path = os.path.join(HERE, "sac_resnet101_tiny.npz" if ARCH == "resnet101" else "sac_vgg16_cfg1.npz")
+            else:
+                out["s0_post_step::vgg_head.8.bias"] = net.backbone.vgg_head[8].bias.detach().numpy().copy()
+    path = os.path.join(HERE, {"resnet101": "sac_resnet101_tiny.npz", "vgg16": "sac_vgg16_cfg1.npz", "fcn": "sac_fcn8s_tiny.npz"}[ARCH])
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) / 1e6, "MB")
 

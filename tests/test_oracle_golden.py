@@ -115,3 +115,35 @@ def test_oracle_vgg16_config1_matches_reference():
             optim.step()
             assert rel(student["features.44.bias"].detach(), g["s0_post_step::features.44.bias"])[1] < 1e-4
             optim.zero_grad()
+
+
+def test_oracle_fcn8s_matches_reference():
+    """VGG-16 FCN-8s (BASELINE.json configs[3] architecture, Dropout2d off) -- oracle vs golden of the real reference"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_fcn8s_tiny.npz"))
+    torch.set_num_threads(8)
+    cfg = synth.ModelCfgFCN()
+    student = O.as_leaf_params(synth.make_fcn_params(seed=213))
+    groups = O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY)
+    assert [len(x["params"]) for x in groups] == [26, 26, 7, 7]
+    optim = torch.optim.SGD(groups, momentum=cfg.MOMENTUM)
+    batch = synth.make_target_batch(1, 2, (128, 128), seed=0)
+    teacher = {k: v.detach().clone() for k, v in student.items()}
+    rc = torch.full((19,), cfg.THRESHOLD_BETA)
+    names = [str(n) for n in g["grad_names"]]
+    for step in (0, 1):
+        losses, outs, rc = O.sac_target_step(student, teacher, rc, batch, 2, cfg, optim=None)
+        pre = "s%d_" % step
+        assert rel(outs["logits"].detach(), g[pre + "logits"])[1] < 1e-4
+        lab = outs["teacher_labels"].to(torch.uint8)
+        assert ((lab != torch.from_numpy(g[pre + "teacher_labels"])) & ~torch.from_numpy(g[pre + "ambiguous"])).sum().item() <= 2
+        for k in ("self_ce", "loss_ce", "teacher_diff"):
+            gv = float(g[pre + k].reshape(-1)[0]); v = float(losses[k].detach().reshape(-1)[0])
+            assert abs(v - gv) <= 2e-4 * max(abs(gv), 1e-3), (k, v, gv)
+        gn = g[pre + "grad_norms"]
+        mine = np.array([student[n].grad.double().norm().item() for n in names])
+        assert np.all(np.abs(mine - gn) <= 2e-3 * np.maximum(gn, 1e-12))
+        if step == 0:
+            optim.step()
+            assert rel(student["vgg_head.8.bias"].detach(), g["s0_post_step::vgg_head.8.bias"])[1] < 1e-4
+            optim.zero_grad()

@@ -301,3 +301,69 @@ def test_source_pass_loss_ce_backward_matches_oracle(net):
         e = rel(params[n].grad, student[n].grad)[0]
         print("   source-pass grad", n, "rel-L2 %.2e" % e)
         assert e < grad_tol(n), n
+
+
+def test_fcn8s_two_steps_match_reference_golden():
+    """VGG-16 FCN-8s (BASELINE.json configs[3] architecture; Dropout2d off for RNG-independent parity) vs the reference"""
+    import os
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sac_fcn8s_tiny.npz"))
+    cfg = synth.ModelCfgFCN()
+    m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"), drop_rate=0.0)
+    m.backbone.load_state_dict(synth.make_fcn_params(seed=213))
+    m.cuda().train()
+    optim = torch.optim.SGD(m.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    batch = synth.make_target_batch(1, 2, (128, 128), seed=0)
+    names = [str(n) for n in g["grad_names"]]
+    params = dict(m.backbone.named_parameters())
+    for step in (0, 1):
+        x, y, x2, A, Ai = [t.clone().cuda() for t in batch]
+        losses, outs = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=(step == 0), T=2)
+        optim.zero_grad()
+        (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+        torch.cuda.synchronize()
+        pre = "s%d_" % step
+        l2, mx = rel(outs["logits"].detach(), g[pre + "logits"])
+        print("fcn step", step, "logits rel-L2 %.2e max %.2e" % (l2, mx))
+        assert l2 < 1e-3 and mx < 1e-3
+        lab = outs["teacher_labels"].cpu().to(torch.uint8)
+        agree = (lab == torch.from_numpy(g[pre + "teacher_labels"])).float().mean().item()
+        print("fcn step", step, "pseudo-label agreement %.6f" % agree)
+        assert agree > 0.999
+        for k in ("self_ce", "loss_ce", "teacher_diff"):
+            gv = float(g[pre + k].reshape(-1)[0]); v = float(losses[k].detach().reshape(-1)[0])
+            print(k, v, gv)
+            assert abs(v - gv) <= 5e-3 * max(abs(gv), 1e-3), (k, v, gv)
+        gn = g[pre + "grad_norms"]
+        mine = np.array([params[n].grad.double().norm().item() for n in names])
+        relerr = np.abs(mine - gn) / np.maximum(gn, 1e-12)
+        print("fcn step", step, "grad-norm max rel err %.2e (%s)" % (relerr.max(), names[int(relerr.argmax())]))
+        assert relerr.max() < 3e-2
+        for key in g.files:
+            if key.startswith(pre + "grad::"):
+                n = key.split("::")[1]
+                gg = params[n].grad
+                gg = gg.flatten()[:60000] if gg.numel() > 60000 else gg
+                e = rel(gg.reshape(g[key].shape), g[key])[0]
+                print("   grad", n, "rel-L2 %.2e" % e)
+                assert e < 3e-2, key
+        if step == 0:
+            optim.step()
+            assert rel(m.backbone.vgg_head[8].bias.detach(), g["s0_post_step::vgg_head.8.bias"])[1] < 1e-4
+
+
+def test_fcn8s_dropout_train_mode_runs():
+    """Dropout2d active (default drop_rate): the step runs, losses are finite, every parameter receives a gradient"""
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    cfg = synth.ModelCfgFCN()
+    m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    m.backbone.load_state_dict(synth.make_fcn_params(seed=213))
+    m.cuda().train()
+    x, y, x2, A, Ai = [t.cuda() for t in synth.make_target_batch(1, 2, (128, 128), seed=0)]
+    losses, outs = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=True, T=2)
+    (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() for v in losses.values())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.backbone.parameters())
