@@ -358,11 +358,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
   }
-  if (a.scale) {
-    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
-  }
-  if (a.colsum) {
-    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+  // per-channel vectors are staged in shared memory when they fit (N_total <= MAX_AFFINE); wider layers (FCN head, 4096
+  // channels) read scale/shift from global memory and accumulate the column sums with global atomics instead
+  const bool staged = a.N_total <= MAX_AFFINE;
+  if (staged) {
+    if (a.scale) {
+      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+    }
+    if (a.colsum) {
+      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+    }
+  } else {
+    s_scale = const_cast<float*>(a.scale); s_shift = const_cast<float*>(a.shift); s_colsum = a.colsum;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -477,7 +484,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();       // nobody exits while a peer may still multicast / arrive into its smem
-  if (a.colsum) {
+  if (a.colsum && staged) {
     for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
       const float cs = s_colsum[i];
       if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
@@ -574,11 +581,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
   }
-  if (a.scale) {
-    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
-  }
-  if (a.colsum) {
-    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+  // per-channel vectors are staged in shared memory when they fit (N_total <= MAX_AFFINE); wider layers (FCN head, 4096
+  // channels) read scale/shift from global memory and accumulate the column sums with global atomics instead
+  const bool staged = a.N_total <= MAX_AFFINE;
+  if (staged) {
+    if (a.scale) {
+      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+    }
+    if (a.colsum) {
+      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+    }
+  } else {
+    s_scale = const_cast<float*>(a.scale); s_shift = const_cast<float*>(a.shift); s_colsum = a.colsum;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -683,7 +697,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (a.colsum) {
+  if (a.colsum && staged) {
     for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
       const float cs = s_colsum[i];
       if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
@@ -1268,9 +1282,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.relu = d->relu;
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
   a.colsum = d->colsum;
-  SACB_REQUIRE(d->colsum == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged column-sum size", d->K);
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
-  SACB_REQUIRE(d->scale == nullptr || d->K <= MAX_AFFINE, "sacb_conv_gemm: K=%d exceeds the staged affine size", d->K);
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) return launch_gemm_pair(ah, al, bh, bl, a, st);
