@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--groups", type=int, default=NUM_GROUPS, help="view-groups per GPU (default: configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-p2p", action="store_true", help="N>1: NCCL all-reduce + SGD instead of the fused peer-memory kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -146,6 +147,22 @@ def main():
     net.backbone.load_state_dict(synth.make_backbone_params(seed=123))
     net.to(dev).train()
     stepper = TargetStepper(net, cfg, GROUP_SIZE, dev)
+    exchange = "none (1 GPU)"
+    if world > 1:
+        exchange = "NCCL all-reduce of the flat gradient + SGD kernel"
+        if not args.no_p2p:
+            # gradient mean + SGD + weight broadcast as ONE kernel over NVLink peer memory (no NCCL on the data path)
+            ok = torch.ones(1, device=dev)
+            try:
+                stepper.enable_p2p()
+            except Exception as e:          # peer access unavailable: every rank must agree before changing path
+                print("[bench] rank %d: peer-memory setup failed (%r); using NCCL" % (rank, e), file=sys.stderr, flush=True)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) > 0:
+                exchange = "fused peer-memory all-reduce + SGD kernel (sacb_allreduce_sgd, no NCCL)"
+            else:
+                stepper.optim.p2p = None
     host = stepper.stage_host(synth.make_target_batch(args.groups, GROUP_SIZE, CROP, seed=rank))
     dev_batch = stepper.h2d(host)
     crops_per_step = args.groups * GROUP_SIZE * world
@@ -183,7 +200,8 @@ def main():
 
     note("first eager step (teacher init, workspace allocation)")
     run(1, False)
-    use_graph = (not args.no_graph) and world == 1      # NCCL inside a captured graph is not used: eager launches at N>1
+    # the fused exchange kernel makes the whole step NCCL-free, so it is captured at any N; with NCCL: eager launches
+    use_graph = (not args.no_graph) and (world == 1 or stepper.optim.p2p is not None)
     if use_graph:
         note("capturing the steady-state step into a CUDA graph")
         stepper.capture(dev_batch)
@@ -232,7 +250,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (bf16 hi/lo split operands, fp32 TMEM accumulation; fp32-equivalent)", "data": "synthetic",
             "config": {"workload": "ResNet-101 DeepLabv2 SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % (args.groups, GROUP_SIZE, CROP[0], CROP[1]),
-                       "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world,
+                       "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world, "gradient_exchange": exchange,
                        "l2": "inputs larger than L2 (>20 GB of activations per step)",
                        "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches"},
             "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

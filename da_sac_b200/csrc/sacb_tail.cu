@@ -155,7 +155,7 @@ tail_running_conf_kernel(const float* __restrict__ part_sums, int nparts, int C,
 template <int C_>
 __global__ void __launch_bounds__(256)
 tail_pool_kernel(const float* __restrict__ probs, const float* __restrict__ affine, const float* __restrict__ affine_inv,
-                 float* __restrict__ pooled, int T, int C, int CP, int CP2, int H, int W) {
+                 float* __restrict__ pooled, int T, int C, int CP, int CP2, int H, int W, int partial) {
   const int g = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int HW = H * W;
@@ -193,12 +193,38 @@ tail_pool_kernel(const float* __restrict__ probs, const float* __restrict__ affi
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) S[c] += A[c] * V;        // sac.py:305 aligned * valid, summed over T
   }
+  float* dst = pooled + ((size_t)g * HW + pix) * CP2;
+  if (partial) {
+    // fractional group (sac.py:198-216,243-245): this rank holds only T of the group's views; the un-normalised sums
+    // are exchanged (sum over the ranks that share the group) and tail_pool_finalize_kernel normalises them
+#pragma unroll
+    for (int c = 0; c < C_; ++c) if (c < C) dst[c] = S[c];
+    dst[C] = 0.f;
+    return;
+  }
   float Z = 0.f;
 #pragma unroll
   for (int c = 0; c < C_; ++c) if (c < C) Z += S[c];
   const float mask = Z > 0.1f ? 1.f : 0.f;                           // sac.py:258
   const float denom = fmaxf(Z, 1e-3f);                               // sac.py:261
-  float* dst = pooled + ((size_t)g * HW + pix) * CP2;
+#pragma unroll
+  for (int c = 0; c < C_; ++c) if (c < C) dst[c] = S[c] / denom;
+  dst[C] = mask;
+}
+
+// second half of T2 for fractional groups: pooled holds the summed S over ALL views of the group (after the exchange)
+template <int C_>
+__global__ void __launch_bounds__(256)
+tail_pool_finalize_kernel(float* __restrict__ pooled, int C, int CP2, size_t npix) {
+  const size_t pix = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= npix) return;
+  float* dst = pooled + pix * CP2;
+  float S[C_];
+  float Z = 0.f;
+#pragma unroll
+  for (int c = 0; c < C_; ++c) if (c < C) { S[c] = dst[c]; Z += S[c]; }
+  const float mask = Z > 0.1f ? 1.f : 0.f;                           // sac.py:258
+  const float denom = fmaxf(Z, 1e-3f);                               // sac.py:261
 #pragma unroll
   for (int c = 0; c < C_; ++c) if (c < C) dst[c] = S[c] / denom;
   dst[C] = mask;
@@ -579,15 +605,24 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   const int C = d->C, HW = d->H * d->W, CP = (C + 3) / 4 * 4, CP2 = (C + 1 + 3) / 4 * 4;
   const int nb = (HW + 255) / 256;
   dim3 gridB(nb, d->BT), gridG(nb, d->BT / d->T);
-  tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
-  LAUNCHED();
-  if (d->training) {
-    tail_running_conf_kernel<<<1, dim3(32, 32), 0, ST>>>(d->part_sums, nb * d->BT, C, 1.0 / ((double)d->BT * HW), d->beta,
-                                              d->stat_momentum, d->running_conf);
+  SACB_REQUIRE(d->phase >= 0 && d->phase <= 2, "sacb_teacher_tail: phase must be 0, 1 or 2");
+  if (d->phase != 2) {
+    tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
+    LAUNCHED();
+    if (d->training) {
+      tail_running_conf_kernel<<<1, dim3(32, 32), 0, ST>>>(d->part_sums, nb * d->BT, C, 1.0 / ((double)d->BT * HW), d->beta,
+                                                d->stat_momentum, d->running_conf);
+      LAUNCHED();
+    }
+    tail_pool_kernel<C_><<<gridG, 256, 0, ST>>>(d->probs, d->affine, d->affine_inv, d->pooled, d->T, C, CP, CP2, d->H, d->W,
+                                               d->phase == 1);
+    LAUNCHED();
+    if (d->phase == 1) return 0;          // caller sums `pooled` over the ranks that share the group, then phase 2
+  } else {
+    const size_t npix = (size_t)(d->BT / d->T) * HW;
+    tail_pool_finalize_kernel<C_><<<(unsigned)((npix + 255) / 256), 256, 0, ST>>>(d->pooled, C, CP2, npix);
     LAUNCHED();
   }
-  tail_pool_kernel<C_><<<gridG, 256, 0, ST>>>(d->probs, d->affine, d->affine_inv, d->pooled, d->T, C, CP, CP2, d->H, d->W);
-  LAUNCHED();
   SACB_CHECK_CUDA(cudaMemsetAsync(d->peaks, 0, sizeof(float) * d->BT * C, ST));
   tail_refine_kernel<C_><<<gridB, 256, 0, ST>>>(d->pooled, d->affine_inv, d->conf, d->idx, reinterpret_cast<int*>(d->peaks),
                                                d->refined, d->T, C, CP2, d->H, d->W);

@@ -77,6 +77,7 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         net, eng = ctx.net, ctx.eng
+        net._select_grad_buffer()
         eng.backward(net._flat, net._planes(True), ctx.x, dlogits.contiguous(), net._grad)
         return (None, None, None) + tuple(net._grad.view(k) for k in net._param_keys)
 
@@ -129,6 +130,28 @@ class _EngineBackbone(BaseNet):
 
     def mark_dirty(self):
         self._version += 1
+
+    def _select_grad_buffer(self):
+        """The engine WRITES a whole backward pass into the flat buffer ``_grad`` and autograd receives views of it, so
+        after the first backward ``p.grad`` aliases that buffer.  A second backward without ``zero_grad`` in between
+        (train.py:128-138 then :231-232: the source pass and the target pass accumulate into one optimiser step) must
+        therefore not overwrite it: switch to the alternate flat buffer, autograd then adds the two."""
+        g = self._grad
+        lo, hi = g.buf.data_ptr(), g.buf.data_ptr() + g.buf.numel() * 4
+        held = getattr(self, "_grad_held", False) or \
+            any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self._params)
+        if held:
+            if getattr(self, "_grad_alt", None) is None:
+                self._grad_alt = E.FlatParams(E.build_net(self.ARCH, 64, 64), g.buf.device)
+            self._grad, self._grad_alt = self._grad_alt, self._grad
+            self._grad_held = False
+
+    def hold_grad(self):
+        """Keep the flat gradient buffer of the backward pass that just ran (the next backward goes to the alternate
+        buffer) and return it: the joint source+target step adds the two with ONE flat kernel instead of letting
+        autograd accumulate 320 tensors one by one (trainer.JointStepper)."""
+        self._grad_held = True
+        return self._grad
 
     def _pre_forward(self, eng, x, with_grad):
         """hook for per-forward engine state (FCN dropout masks)"""

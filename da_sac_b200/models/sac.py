@@ -152,17 +152,48 @@ class SAC(SAC_Baseline):
     def _tail(self, teacher_logits, y_raw, affine, affine_inv, T, refined=None):
         BT, Cn, h, w = teacher_logits.shape
         H, W = y_raw.shape[-2:]
-        ws = self._workspace(BT, T, H, W, teacher_logits.device)
+        # fractional group (sac.py:243-245, _gather :198-216): this rank holds T0 < T views of ONE group; the other
+        # views live on the neighbouring ranks (train.py:185-209).  The kernels then run with T = T0 and the
+        # reference-frame partial sums are exchanged between the ranks sharing the group.
+        T0 = min(T, BT)
+        ws = self._workspace(BT, T0, H, W, teacher_logits.device)
         cfg = self.cfg
-        d = L.Tail(C.sizeof(L.Tail), BT, T, Cn, h, w, H, W, L.ptr(teacher_logits), L.ptr(y_raw),
-                   L.ptr(affine.contiguous().float()), L.ptr(affine_inv.contiguous().float()), L.ptr(self.running_conf),
-                   1 if self.training else 0, 1 if cfg.CONF_DISCOUNT else 0,
-                   cfg.THRESHOLD_BETA, cfg.STAT_MOMENTUM, cfg.RUN_CONF_UPPER, cfg.RUN_CONF_LOWER,
-                   L.ptr(ws["probs"]), L.ptr(ws["pooled"]), L.ptr(ws["part_sums"]), L.ptr(ws["peaks"]),
-                   L.ptr(ws["conf"]), L.ptr(ws["idx"]), L.ptr(ws["labels"]), L.ptr(ws["conf_mean"]),
-                   L.ptr(ws["thresholds"]), L.ptr(refined))
-        L.check(L.lib().sacb_teacher_tail(C.byref(d), L.stream()), "sacb_teacher_tail")
+        A, Ai = affine.contiguous().float(), affine_inv.contiguous().float()
+
+        def desc(phase):
+            return L.Tail(C.sizeof(L.Tail), BT, T0, Cn, h, w, H, W, L.ptr(teacher_logits), L.ptr(y_raw),
+                          L.ptr(A), L.ptr(Ai), L.ptr(self.running_conf),
+                          1 if self.training else 0, 1 if cfg.CONF_DISCOUNT else 0,
+                          cfg.THRESHOLD_BETA, cfg.STAT_MOMENTUM, cfg.RUN_CONF_UPPER, cfg.RUN_CONF_LOWER,
+                          L.ptr(ws["probs"]), L.ptr(ws["pooled"]), L.ptr(ws["part_sums"]), L.ptr(ws["peaks"]),
+                          L.ptr(ws["conf"]), L.ptr(ws["idx"]), L.ptr(ws["labels"]), L.ptr(ws["conf_mean"]),
+                          L.ptr(ws["thresholds"]), L.ptr(refined), phase)
+        if T0 == T:
+            L.check(L.lib().sacb_teacher_tail(C.byref(desc(0)), L.stream()), "sacb_teacher_tail")
+            return ws
+        d1 = desc(1)
+        L.check(L.lib().sacb_teacher_tail(C.byref(d1), L.stream()), "sacb_teacher_tail(partial sums)")
+        self._exchange_partial_sums(ws["pooled"], BT, T)
+        d2 = desc(2)
+        L.check(L.lib().sacb_teacher_tail(C.byref(d2), L.stream()), "sacb_teacher_tail(labels)")
         return ws
+
+    def _exchange_partial_sums(self, pooled, B, T):
+        """Sum the reference-frame partial sums over the ranks that share this rank's view-group.  The reference
+        all-gathers every rank's [B,19,H,W] probabilities and concatenates ``stride`` of them (sac.py:204-214); only
+        their sum over views is ever used (sac.py:252-253), so one sum all-reduce inside the sub-group is enough."""
+        from ..trainer import fractional_subgroup
+        first, stride = fractional_subgroup(self.rank, B, T)
+        assert dist.is_initialized() and dist.get_world_size() >= first + stride, \
+            "fractional view-groups (local batch %d < GROUP_SIZE %d) need torch.distributed with >= %d ranks" % (B, T, first + stride)
+        key = (dist.get_world_size(), stride)
+        if getattr(self, "_subgroups", None) is None or self._subgroups[0] != key:
+            # new_group is collective: every rank creates every sub-group, in the same order
+            groups = {}
+            for f in range(0, dist.get_world_size() - stride + 1, stride):
+                groups[f] = dist.new_group(list(range(f, f + stride)))
+            self._subgroups = (key, groups)
+        dist.all_reduce(pooled, group=self._subgroups[1][first])
 
     def _loss_desc(self, logits, y, tail, grad_scale, dlogits, use_labels=True):
         BT, Cn, h, w = logits.shape

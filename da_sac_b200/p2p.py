@@ -1,0 +1,128 @@
+"""Peer-memory plumbing for the fused gradient all-reduce + SGD kernel (``sacb_allreduce_sgd``, include/sacb.h).
+
+``P2PContext(backbone, world, rank)`` (collective over the default process group):
+  * re-homes the backbone's flat parameter buffer and flat gradient buffer into ``sacb_symm_alloc`` memory
+    (plain cudaMalloc, so it can be exported; ``nn.Parameter.data`` stay views, nothing else changes),
+  * exchanges CUDA IPC handles of (params, grads, flags) with ``torch.distributed.all_gather_object`` and maps every
+    peer's buffers into this process (NVLink peer access is enabled lazily by the driver),
+  * ``allreduce_sgd(...)`` launches the ONE kernel that replaces DDP's gradient all-reduce (train.py:104,232) and
+    ``optim.step()`` (train.py:233).  No NCCL call is involved, so the whole training step -- including the exchange --
+    can be captured in a CUDA graph at any world size.
+
+torch is used for process-group plumbing and as the owner of ordinary tensors only; the shared buffers are owned by
+libsac_b200.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+MAX_WORLD = 8
+
+
+class AllreduceSgd(C.Structure):
+    _fields_ = [("size", C.c_uint32), ("world", C.c_int32), ("rank", C.c_int32),
+                ("grads", C.c_void_p), ("params", C.c_void_p), ("flags", C.c_void_p),
+                ("mom", C.c_void_p), ("seg_ranges", C.c_void_p), ("seg_lr", C.c_void_p), ("seg_wd", C.c_void_p),
+                ("nseg", C.c_int32), ("n", C.c_int64), ("momentum", C.c_float), ("first_step", C.c_int32)]
+
+
+class SymmBuffer(object):
+    """device memory from sacb_symm_alloc, viewable as a torch tensor (zero-copy) and exportable as a CUDA IPC handle"""
+
+    def __init__(self, nbytes, device):
+        self.nbytes, self.device = int(nbytes), torch.device(device)
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().sacb_symm_alloc(C.c_size_t(self.nbytes), C.byref(p)), "sacb_symm_alloc")
+        self.ptr = p.value
+
+    def tensor(self, dtype, numel):
+        item = torch.empty((), dtype=dtype).element_size()
+        assert numel * item <= self.nbytes
+        typestr = {torch.float32: "<f4", torch.uint32: "<u4", torch.int32: "<i4"}[dtype]
+        holder = type("_SymmView", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+        holder._owner = self                        # keeps the allocation alive as long as the tensor lives
+        t = torch.as_tensor(holder, device=self.device)
+        assert t.data_ptr() == self.ptr, "torch copied the symmetric buffer instead of aliasing it"
+        return t
+
+    def handle(self):
+        h = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().sacb_ipc_export(C.c_void_p(self.ptr), h), "sacb_ipc_export")
+        return bytes(h)
+
+
+def _import(handle, device):
+    p = C.c_void_p()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    with torch.cuda.device(device):
+        L.check(L.lib().sacb_ipc_import(buf, C.byref(p)), "sacb_ipc_import")
+    return p.value
+
+
+class P2PContext(object):
+    def __init__(self, backbone, world, rank, device):
+        assert 1 <= world <= MAX_WORLD, "sacb_allreduce_sgd supports up to %d ranks (one NVSwitch domain)" % MAX_WORLD
+        self.world, self.rank, self.device = world, rank, torch.device(device)
+        self.backbone = backbone
+        lib = L.lib()
+        flat = backbone.ensure_flat(self.device)
+        n = flat.total
+        assert n % 4 == 0
+        self.n = n
+        self._bufs = dict(params=SymmBuffer(4 * n, device), grads=SymmBuffer(4 * n, device),
+                          flags=SymmBuffer(4 * lib.sacb_p2p_flag_words(), device))
+        # ---- re-home the flat buffers (parameter objects keep their identity; values are carried over)
+        p_sym = self._bufs["params"].tensor(torch.float32, n)
+        p_sym.copy_(flat.buf)
+        flat.buf = p_sym
+        tensors = backbone._named_tensors()
+        for k, _, _ in flat.entries:
+            tensors[k].data = flat.view(k)
+        self.grad_sym = self._bufs["grads"].tensor(torch.float32, n)
+        backbone._grad.buf = self.grad_sym
+        for p in backbone._params:
+            p.grad = None
+        backbone.mark_dirty()
+        torch.cuda.synchronize(self.device)
+        # ---- exchange IPC handles, map the peers
+        mine = {k: b.handle() for k, b in self._bufs.items()}
+        if world > 1:
+            allh = [None] * world
+            dist.all_gather_object(allh, mine)
+        else:
+            allh = [mine]
+        self._ptrs = {k: [] for k in mine}
+        err = None
+        try:
+            for r in range(world):
+                for k in mine:
+                    self._ptrs[k].append(self._bufs[k].ptr if r == rank else _import(allh[r][k], self.device))
+        except L.SacbError as e:                # e.g. no peer access between two GPUs
+            err = e
+        if world > 1:
+            # agreement + barrier in one: every rank has mapped every peer before the first kernel touches them, and
+            # either all ranks switch to the fused kernel or none does
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                raise L.SacbError("peer-memory mapping failed on at least one rank: %r" % (err,))
+        elif err is not None:
+            raise err
+        arr = C.c_void_p * world
+        self._arrays = {k: arr(*v) for k, v in self._ptrs.items()}
+
+    def allreduce_sgd(self, grad_buf, mom, ranges, lr, wd, nseg, momentum, first_step):
+        """all ranks: params -= lr * sgd_momentum(mean over ranks of grad) ; ``grad_buf`` is this rank's flat gradient"""
+        if grad_buf.data_ptr() != self.grad_sym.data_ptr():
+            self.grad_sym.copy_(grad_buf)       # a backward pass that landed in the alternate buffer (joint step)
+        d = AllreduceSgd(C.sizeof(AllreduceSgd), self.world, self.rank,
+                         C.cast(self._arrays["grads"], C.c_void_p), C.cast(self._arrays["params"], C.c_void_p),
+                         C.cast(self._arrays["flags"], C.c_void_p), L.ptr(mom), L.ptr(ranges), L.ptr(lr), L.ptr(wd),
+                         nseg, self.n, momentum, 1 if first_step else 0)
+        L.check(L.lib().sacb_allreduce_sgd(C.byref(d), L.stream()), "sacb_allreduce_sgd")

@@ -32,6 +32,34 @@ def shard_batch(batch, group_size, world_size, rank):
     return tuple(t[lo:hi] for t in batch)
 
 
+def fractional_subgroup(rank, local_batch, group_size):
+    """(first rank, number of ranks) of the set of ranks that hold the views of this rank's view-group when a group
+    does not fit one GPU (sac.py:204-214: ``stride = T // B``; ``index = stride * (rank * B // T)``)."""
+    stride = max(1, group_size // local_batch)
+    return stride * (rank * local_batch // group_size), stride
+
+
+def prep_batch(tensor, num_groups, group_size, world_size, rank, device=None):
+    """``Trainer._prep_batch`` (train.py:157-209): ``tensor`` is this rank's loader output [B,T,...].  If at least one
+    whole group fits a GPU the batch is just flattened to [B*T,...]; otherwise every rank's batch is all-gathered and
+    this rank keeps its ``N*L/world`` consecutive views of the group it shares with its neighbours."""
+    N, L_ = num_groups, group_size
+    if (N * L_) % world_size != 0:
+        raise ValueError("Batch size does not fit world size")                    # train.py:179
+    per_gpu = N * L_ // world_size
+    if device is not None:
+        tensor = tensor.to(device, non_blocking=True)
+    if per_gpu >= L_:
+        return tensor.flatten(0, 1)                                               # train.py:186-187
+    T = tensor.size(1)
+    assert T == L_, "Loaded sequence is incorrect {} vs. {}".format(T, L_)       # train.py:193
+    out_list = [torch.empty_like(tensor) for _ in range(world_size)]
+    dist.all_gather(out_list, tensor.contiguous())
+    batch_index = rank * per_gpu
+    index0, index1 = batch_index // T, batch_index % T
+    return out_list[index0].flatten(0, 1)[index1:index1 + per_gpu]
+
+
 def allreduce_mean_(buf):
     """DDP semantics for gradients: sum over ranks, divide by world size (train.py:104). In place."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -49,6 +77,7 @@ class FusedSGD(object):
         self.param_groups = param_groups
         self._built = None
         self.steps = 0
+        self.p2p = None        # p2p.P2PContext: step() then also performs the gradient all-reduce (one fused kernel)
 
     def _build(self):
         bb = self.backbone
@@ -87,6 +116,13 @@ class FusedSGD(object):
             self._build()
             if mom is not None: self._built["mom"] = mom
         b = self._built
+        if self.p2p is not None:
+            # gradient mean over ranks + SGD + weight broadcast in ONE kernel over NVLink peer memory (sacb_allreduce_sgd)
+            self.p2p.allreduce_sgd(bb._grad.buf, b["mom"], b["ranges"], b["lr"], b["wd"], b["n"], self.momentum,
+                                   self.steps == 0)
+            self.steps += 1
+            bb.mark_dirty()
+            return
         L.check(L.lib().sacb_sgd(L.ptr(b["flat"].buf), L.ptr(bb._grad.buf), L.ptr(b["mom"]), L.ptr(b["ranges"]),
                                  L.ptr(b["lr"]), L.ptr(b["wd"]), b["n"], C.c_float(self.momentum),
                                  1 if self.steps == 0 else 0, L.stream()), "sacb_sgd")
@@ -109,6 +145,19 @@ class TargetStepper(object):
         self._graph_launches = 0
         self.launches = 0          # kernels of libsac_b200 launched (eagerly or through graph replays) by step()
 
+    def enable_p2p(self, world=None, rank=None):
+        """Switch the gradient exchange from NCCL all-reduce + SGD to the fused peer-memory kernel (collective call:
+        every rank must make it, before ``capture``).  With it the whole step has no NCCL call inside, so the CUDA-graph
+        replay path works at any world size."""
+        from .p2p import P2PContext
+        if world is None:
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            rank = dist.get_rank() if world > 1 else 0
+        assert self._graph is None, "enable_p2p() must precede capture()"
+        self.optim.p2p = P2PContext(self.net.backbone, world, rank, self.device)
+        self.optim._built = None
+        return self.optim.p2p
+
     def stage_host(self, batch):
         """pinned host copies of a batch (what a DataLoader with pin_memory hands to train.py:183)"""
         self._pinned = tuple(t.contiguous().pin_memory() for t in batch)
@@ -122,7 +171,8 @@ class TargetStepper(object):
         losses, outs = self.net(x, y, x2, A, Ai, use_teacher=True, update_teacher=update_teacher, T=self.T)
         self.optim.zero_grad()                                                      # TARGET_ONLY (train.py:227-228)
         (self.cfg.LR_TARGET * losses["self_ce"].mean()).backward()                  # train.py:231-232
-        allreduce_mean_(self.net.backbone._grad.buf)
+        if self.optim.p2p is None:
+            allreduce_mean_(self.net.backbone._grad.buf)                            # NCCL; else fused into optim.step()
         self.optim.step()                                                           # train.py:233
         return torch.cat([losses["loss_ce"].detach(), losses["self_ce"].detach(), losses["teacher_diff"].detach()])
 
@@ -173,3 +223,39 @@ class TargetStepper(object):
             host = v.cpu()                                                          # .item() host sync (train.py:246)
             return {"loss_ce": float(host[0]), "self_ce": float(host[1]), "teacher_diff": float(host[2])}
         return {"loss_ce": v[0:1], "self_ce": v[1:2], "teacher_diff": v[2:3]}
+
+
+class JointStepper(TargetStepper):
+    """One iteration of ``Trainer.train_epoch`` with TRAIN.TARGET_ONLY = False (train.py:266-298): supervised source pass
+    (``Trainer.step(train=True)``, train.py:119-138: zero_grad, ``loss_ce.backward()``, no optimiser step) followed by the
+    target pass (``_step_target``, train.py:211-233: ``LR_TARGET * self_ce`` backward WITHOUT zero_grad, then
+    ``optim.step()``).  The two backward passes land in two flat buffers that are summed by one kernel; there is ONE
+    gradient all-reduce for the pair (DDP in the reference all-reduces after each backward)."""
+
+    def step_joint(self, batch_source, batch_target, update_teacher=None):
+        if update_teacher is None:
+            update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)
+        bb = self.net.backbone
+        image, masks_gt = batch_source
+        if not image.is_cuda:
+            image, masks_gt = self.h2d((image, masks_gt))
+        if not batch_target[0].is_cuda:
+            batch_target = self.h2d(batch_target)
+        n0 = L.launch_count()
+        losses_src, _ = self.net(image, masks_gt)                                   # train.py:128
+        self.optim.zero_grad()                                                      # train.py:132
+        losses_src["loss_ce"].mean().backward()                                     # train.py:133
+        g_src = bb.hold_grad()
+        self.optim.zero_grad()            # drop the per-tensor views; the held flat buffer keeps the source gradients
+        x, y, x2, A, Ai = batch_target
+        losses, _ = self.net(x, y, x2, A, Ai, use_teacher=True, update_teacher=update_teacher, T=self.T)
+        (self.cfg.LR_TARGET * losses["self_ce"].mean()).backward()                  # train.py:231-232 (accumulates)
+        assert bb._grad is not g_src
+        bb._grad.buf.add_(g_src.buf)
+        if self.optim.p2p is None:
+            allreduce_mean_(bb._grad.buf)
+        self.optim.step()                                                           # train.py:233
+        self.launches += L.launch_count() - n0
+        self.iter += 1
+        return {"loss_ce_source": losses_src["loss_ce"].detach(), "loss_ce": losses["loss_ce"].detach(),
+                "self_ce": losses["self_ce"].detach(), "teacher_diff": losses["teacher_diff"].detach()}

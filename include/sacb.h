@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SACB_ABI_VERSION 1
+#define SACB_ABI_VERSION 2
 
 const char* sacb_last_error(void);
 int sacb_abi_version(void);
@@ -185,6 +185,10 @@ typedef struct SacbTail {
   float* conf_mean;              /* [H,W]  batch-mean confidence (the [B,B,H,W] broadcast of sac.py:148) */
   float* thresholds;             /* [BT,C] */
   float* refined;                /* optional [BT,C,H,W] teacher_refined, NULL to skip */
+  /* fractional groups (train.py:185-209, sac.py:198-216: a group's T views spread over several ranks, here T = the
+   * views THIS rank holds): 0 = whole tail; 1 = stop after writing the un-normalised reference-frame sums to `pooled`
+   * (the caller sum-reduces `pooled` over the ranks sharing the group); 2 = resume: normalise `pooled`, labels. */
+  int32_t phase;
 } SacbTail;
 int sacb_teacher_tail(const SacbTail* d, void* stream);
 size_t sacb_tail_part_sums_elems(int BT, int C, int H, int W);
@@ -228,6 +232,39 @@ int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_ranges, int
 /* torch.optim.SGD step (base_trainer.py:61-66): per-segment lr / weight decay, momentum buffer in place */
 int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_ranges, const float* seg_lr,
              const float* seg_wd, int nseg, float momentum, int first_step, void* stream);
+
+/* ---------------------------------------------------------------- gradient all-reduce fused with SGD over NVLink peer memory
+ * Replaces DistributedDataParallel's gradient all-reduce (train.py:104,232; sum over ranks / world) + torch.optim.SGD.step()
+ * (train.py:233) for the data-parallel target step with ONE kernel per rank and no NCCL call:
+ *   rank r: for its 1/world slice of the flat buffers:  g = (sum_{p=0..world-1} grads[p][i]) / world  (peer loads, fixed order)
+ *           SGD with momentum / weight decay exactly as sacb_sgd (momentum buffer touched on the slice only)
+ *           params[p][i] = new value for EVERY rank p (peer stores)
+ * Ranks synchronise through epoch flags in peer-mapped memory (flags[p]: sacb_p2p_flag_words() zero-initialised uint32 per
+ * rank; the epoch counter is device-resident, so the call is CUDA-graph capturable).  Waits are bounded (trap on timeout).
+ * All ranks must call it once per step with the same n / segment table; world == 1 degenerates to sacb_sgd.
+ * Buffers shared between processes come from sacb_symm_alloc (cudaMalloc, zero-filled) and travel as CUDA IPC handles. */
+#define SACB_P2P_MAX_WORLD 8
+#define SACB_IPC_HANDLE_BYTES 64
+int sacb_symm_alloc(size_t bytes, void** dptr);
+int sacb_symm_free(void* dptr);
+int sacb_ipc_export(const void* dptr, void* handle64 /* out: SACB_IPC_HANDLE_BYTES */);
+int sacb_ipc_import(const void* handle64, void** peer_ptr);
+int sacb_ipc_close(void* peer_ptr);
+int sacb_p2p_flag_words(void);
+typedef struct SacbAllreduceSgd {
+  uint32_t size;
+  int32_t world, rank;
+  float* const* grads;          /* host array [world]: rank p's flat gradient buffer as mapped in THIS process */
+  float* const* params;         /* host array [world]: rank p's flat parameter buffer */
+  uint32_t* const* flags;       /* host array [world]: rank p's flag words */
+  float* mom;                   /* local momentum buffer [n] */
+  const int64_t* seg_ranges; const float* seg_lr; const float* seg_wd;   /* device, as sacb_sgd; segments sorted by begin */
+  int32_t nseg;
+  int64_t n;                    /* elements of the flat buffers (multiple of 4) */
+  float momentum;
+  int32_t first_step;
+} SacbAllreduceSgd;
+int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream);
 
 #ifdef __cplusplus
 }

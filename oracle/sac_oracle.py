@@ -240,6 +240,37 @@ def refine(slow_logits, hw, T, affine, affine_inv, ignore_mask, running_conf, cf
     return refined, running_conf, {"teacher_aligned": aligned, "teacher_init": up}
 
 
+def refine_fractional(slow_logits_parts, hw, T, affine_parts, affine_inv_parts, ignore_parts, running_conf_parts, cfg,
+                      training=True):
+    """SAC._refine when ONE view-group is spread over several ranks (train.py:185-209; sac.py:198-216,243-245):
+    element r of every ``*_parts`` list is what rank r holds (T0 = T / len(parts) views).  ``_gather`` concatenates the
+    ranks' ``aligned * valid`` tensors in rank order, ``_avg_pool`` pools over all T views and hands every rank T0 copies
+    of the pooled map, which each rank warps back with its own ``affine_inv``.  Returns [(refined_r, running_conf_r)]."""
+    H, W = hw
+    prods, rcs = [], []
+    for lg, A, Ai, ign, rc in zip(slow_logits_parts, affine_parts, affine_inv_parts, ignore_parts, running_conf_parts):
+        up = F.interpolate(lg, (H, W), mode="bilinear", align_corners=True)
+        probs = F.softmax(up, 1)
+        if training:
+            rc = update_running_conf(rc, probs, cfg)          # local statistics of each rank (sac.py:278-279)
+        rcs.append(rc)
+        probs = probs * (1 - ign[:, None].type_as(probs))
+        aligned = _warp(probs, A)
+        valid_aligned = _warp(torch.ones_like(aligned), Ai)
+        prods.append(aligned * valid_aligned)
+    gathered = torch.cat(prods, 0)                            # _gather (sac.py:214)
+    assert gathered.shape[0] == T
+    pooled, valid = avg_pool(gathered, T)
+    out = []
+    for r, Ai in enumerate(affine_inv_parts):
+        T0 = Ai.shape[0]
+        grid_inv = F.affine_grid(Ai, size=[T0] + list(pooled.shape[1:]), align_corners=False)
+        refined = F.grid_sample(pooled[:T0], grid_inv, align_corners=False)
+        refined_valid = F.grid_sample(valid[:T0], grid_inv, align_corners=False)
+        out.append((refined * refined_valid, rcs[r]))
+    return out
+
+
 def pseudo_labels_probs(probs, ignore_augm, running_conf, cfg, discount=True):
     """SAC._pseudo_labels_probs + _threshold_discount (sac.py:151-187)."""
     B, C, H, W = probs.shape

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 25
     missing = [s for s in syms if not hasattr(dll, s)]
     assert not missing, missing
-    assert lib.lib().sacb_abi_version() == 1
+    assert lib.lib().sacb_abi_version() == lib.ABI_VERSION
     assert lib.lib().sacb_aspp_jpad() == 768
 
 
@@ -29,6 +29,24 @@ def test_struct_sizes_match_header_layout():
     # natural alignment on LP64: 14 x int32 then pointers
     assert ctypes.sizeof(lib.ConvGemm) == 14 * 4 + 10 * 8 + 8 + 5 * 8
     assert ctypes.sizeof(lib.ConvWgrad) == 14 * 4 + 5 * 8 + 8
+
+
+def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
+    """sizeof + offset of the last field of every descriptor struct: include/sacb.h compiled by gcc vs the ctypes mirrors"""
+    import subprocess
+    from da_sac_b200 import lib, p2p
+    pairs = [("SacbConvGemm", lib.ConvGemm, "colsum"), ("SacbConvWgrad", lib.ConvWgrad, "splits"), ("SacbTail", lib.Tail, "phase"),
+             ("SacbLoss", lib.Loss, "dlogits"), ("SacbAllreduceSgd", p2p.AllreduceSgd, "first_step")]
+    src = tmp_path / "sz.c"
+    body = "".join('  printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (c, c, last) for c, _, last in pairs)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sacb.h"\nint main(void) {\n' + body + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    for (cname, ct, last), line in zip(pairs, out):
+        size, off = [int(v) for v in line.split()]
+        assert ctypes.sizeof(ct) == size, (cname, ctypes.sizeof(ct), size)
+        assert getattr(ct, last).offset == off, (cname, last)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

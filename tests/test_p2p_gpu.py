@@ -1,0 +1,128 @@
+"""Fused gradient all-reduce + SGD over peer memory (sacb_allreduce_sgd) against the two-step baseline it replaces
+(all-reduce mean, then sacb_sgd == torch.optim.SGD semantics).  world=1 runs on any GPU box; world=2 needs two GPUs."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(rank, device):
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import TargetStepper
+    cfg = synth.ModelCfg()
+    net = get_model(cfg, rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    net.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    net.to(device).train()
+    return net, cfg, TargetStepper(net, cfg, 2, device)
+
+
+def _reference_sgd(params0, grads_mean, groups_of, momentum, steps):
+    """torch.optim.SGD on a flat copy with the same per-tensor lr / weight decay"""
+    p = params0.clone()
+    mom = torch.zeros_like(p)
+    for s in range(steps):
+        g = grads_mean[s]
+        for (b0, b1, lr, wd) in groups_of:
+            d = g[b0:b1] + wd * p[b0:b1] if wd != 0 else g[b0:b1].clone()
+            buf = d if s == 0 else momentum * mom[b0:b1] + d
+            mom[b0:b1] = buf
+            p[b0:b1] -= lr * buf
+    return p
+
+
+def _run_rank(rank, world, device, steps=3):
+    import torch.distributed as dist
+    net, cfg, st = _make(rank, device)
+    bb = net.backbone
+    ctx = st.enable_p2p(world, rank)
+    flat = bb._flat
+    assert flat.buf.data_ptr() == ctx._bufs["params"].ptr and bb._grad.buf.data_ptr() == ctx._bufs["grads"].ptr
+    # parameters are still ordinary nn.Parameters aliasing the (re-homed) flat buffer
+    w = bb.model.layer3[5].conv2.weight
+    assert w.data_ptr() == flat.view("model.layer3.5.conv2.weight").data_ptr()
+    params0 = flat.buf.clone()
+    st.optim._build()
+    b = st.optim._built
+    ranges = b["ranges"].cpu().tolist(); lr = b["lr"].cpu().tolist(); wd = b["wd"].cpu().tolist()
+    segs = [(ranges[2 * i], ranges[2 * i + 1], lr[i], wd[i]) for i in range(len(lr))]
+    gen = torch.Generator(device="cpu").manual_seed(100)
+    means = []
+    for s in range(steps):
+        per_rank = [torch.randn(flat.total, generator=gen) * 1e-2 for _ in range(world)]
+        tot = per_rank[0].clone()
+        for t in per_rank[1:]:
+            tot += t                                     # same order as the kernel: rank 0, 1, ...
+        means.append((tot / world).to(device))
+        bb._grad.buf.copy_(per_rank[rank].to(device))
+        st.optim.step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    ref = _reference_sgd(params0, means, segs, cfg.MOMENTUM, steps)
+    got = flat.buf
+    # the fused kernel uses fmaf like sacb_sgd; the torch restatement rounds each op -> compare to a few ulp of the update
+    upd, ref_upd = (got - params0).double(), (ref - params0).double()
+    err = ((upd - ref_upd).norm() / ref_upd.norm()).item()
+    untouched = torch.ones(flat.total, dtype=torch.bool, device=device)
+    for b0, b1, _, _ in segs:
+        untouched[b0:b1] = False
+    assert torch.equal(got[untouched], params0[untouched]), "BN statistics / padding must not be touched"
+    return err, got
+
+
+def test_allreduce_sgd_world1_matches_sgd():
+    err, _ = _run_rank(0, 1, torch.device("cuda", 0))
+    print("world=1 update rel-L2 vs torch SGD restatement: %.2e" % err)
+    assert err < 1e-6
+
+
+def test_allreduce_sgd_world1_bit_exact_vs_sacb_sgd():
+    """same inputs through sacb_sgd (the kernel the single-GPU step uses) -> identical bits"""
+    dev = torch.device("cuda", 0)
+    net, cfg, st = _make(0, dev)
+    net2, _, st2 = _make(0, dev)
+    st.enable_p2p(1, 0)
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    for s in range(3):
+        g = (torch.randn(net.backbone._flat.total, generator=gen) * 1e-2).to(dev)
+        net.backbone._grad.buf.copy_(g); net2.backbone._grad.buf.copy_(g)
+        st.optim.step(); st2.optim.step()
+    torch.cuda.synchronize()
+    assert torch.equal(net.backbone._flat.buf, net2.backbone._flat.buf)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        err, got = _run_rank(rank, world, dev)
+        # every replica must hold bit-identical weights
+        gathered = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gathered, got.contiguous())
+        same = all(torch.equal(gathered[0], t) for t in gathered[1:])
+        q.put((rank, err, bool(same), ""))
+    except Exception as e:      # surface the failure instead of hanging the parent
+        q.put((rank, float("nan"), False, repr(e)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs: p.join(timeout=120)
+    print(res)
+    for rank, err, same, msg in res:
+        assert msg == "", msg
+        assert same and err < 1e-6, (rank, err, same)

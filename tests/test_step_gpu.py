@@ -367,3 +367,69 @@ def test_fcn8s_dropout_train_mode_runs():
     torch.cuda.synchronize()
     assert all(torch.isfinite(v).all() for v in losses.values())
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.backbone.parameters())
+
+
+def test_joint_source_target_step_matches_oracle(net):
+    """One ``train_epoch`` iteration with TARGET_ONLY=False (train.py:266-298): source ``loss_ce.backward()`` and target
+    ``LR_TARGET*self_ce`` backward accumulate into ONE optimiser step.  Checks (a) plain autograd accumulation through the
+    drop-in (two backward passes without zero_grad, what an unmodified train.py does) and (b) trainer.JointStepper
+    (flat two-buffer sum, one all-reduce) against the oracle's accumulated gradients and post-SGD weights."""
+    from da_sac_b200 import synth
+    from da_sac_b200.trainer import JointStepper
+    from oracle import sac_oracle as O
+    m, cfg = net
+    sd = synth.make_backbone_params(seed=123)
+    G, Kk, hw = 1, 2, (96, 96)
+    tgt = synth.make_target_batch(G, Kk, hw, seed=11)
+    xs, ys, _, _, _ = synth.make_target_batch(1, 2, (96, 128), seed=12)      # source crops: another shape on purpose
+    ys = torch.randint(0, 19, ys.shape); ys[:, :4] = 255
+    # ---- oracle
+    student = O.as_leaf_params(sd)
+    teacher = {k: v.detach().clone() for k, v in student.items()}
+    optim = torch.optim.SGD(O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    optim.zero_grad()
+    ls, _ = O.backbone_forward(student, xs, ys)
+    ls["loss_ce"].mean().backward()
+    rc = torch.full((19,), cfg.THRESHOLD_BETA)
+    lt, _, _ = O.sac_target_forward(student, teacher, rc, tgt, Kk, cfg, True)
+    (cfg.LR_TARGET * lt["self_ce"].mean()).backward()
+    ref_grads = {k: v.grad.clone() for k, v in student.items() if v.requires_grad}
+    optim.step()
+    names = ("model.layer5.conv2d_list.0.weight", "model.layer4.1.conv2.weight", "model.layer3.10.bn2.weight",
+             "model.layer3.10.bn2.bias", "model.layer1.0.conv1.weight", "model.conv1.weight")
+    # ---- (a) autograd accumulation, as train.py drives it
+    m.backbone.load_state_dict(sd); m.train(); m.slow_init[0] = False
+    for p in m.backbone.parameters():
+        p.grad = None
+    losses_s, _ = m(xs.cuda(), ys.clone().cuda())
+    losses_s["loss_ce"].mean().backward()
+    x, y, x2, A, Ai = [t.clone().cuda() for t in tgt]
+    losses_t, _ = m(x, y, x2, A, Ai, use_teacher=True, update_teacher=True, T=Kk)
+    (cfg.LR_TARGET * losses_t["self_ce"].mean()).backward()
+    torch.cuda.synchronize()
+    assert abs(float(losses_s["loss_ce"]) - float(ls["loss_ce"])) < 2e-4 * abs(float(ls["loss_ce"]))
+    assert abs(float(losses_t["self_ce"]) - float(lt["self_ce"])) < 5e-3 * max(abs(float(lt["self_ce"])), 1e-3)
+    params = dict(m.backbone.named_parameters())
+    for n in names:
+        e = rel(params[n].grad, ref_grads[n])[0]
+        print("   joint (autograd) grad", n, "rel-L2 %.2e" % e)
+        assert e < grad_tol(n), n
+    # ---- (b) JointStepper
+    m.backbone.load_state_dict(sd); m.slow_init[0] = False
+    for p in m.backbone.parameters():
+        p.grad = None
+    st = JointStepper(m, cfg, Kk, torch.device("cuda"))
+    out = st.step_joint((xs.cuda(), ys.clone().cuda()), tuple(t.clone().cuda() for t in tgt), update_teacher=True)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss_ce_source"]) - float(ls["loss_ce"])) < 2e-4 * abs(float(ls["loss_ce"]))
+    gflat = m.backbone._grad
+    for n in names:
+        e = rel(gflat.view(n), ref_grads[n])[0]
+        print("   joint (stepper) grad", n, "rel-L2 %.2e" % e)
+        assert e < grad_tol(n), n
+    for n in ("model.layer5.conv2d_list.1.bias", "model.layer3.5.conv2.weight", "model.bn1.weight"):
+        new, ref_new, old = params[n].detach().cpu().double(), student[n].detach().double(), sd[n].double()
+        # compare the UPDATE (the weights themselves agree trivially): w_new - w_old
+        e = ((new - old) - (ref_new - old)).norm() / (ref_new - old).norm().clamp_min(1e-30)
+        print("   joint post-SGD update", n, "rel-L2 %.2e" % float(e))
+        assert float(e) < 2e-2, n
