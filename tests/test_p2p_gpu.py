@@ -76,7 +76,8 @@ def _run_rank(rank, world, device, steps=3):
 def test_allreduce_sgd_world1_matches_sgd():
     err, _ = _run_rank(0, 1, torch.device("cuda", 0))
     print("world=1 update rel-L2 vs torch SGD restatement: %.2e" % err)
-    assert err < 1e-6
+    # fp32 cancellation in (new - old) bounds this at ~ulp(w)/|update|; bit-exactness vs sacb_sgd is the next test
+    assert err < 1e-4
 
 
 def test_allreduce_sgd_world1_bit_exact_vs_sacb_sgd():
@@ -106,6 +107,18 @@ def _worker(rank, world, port, q):
         gathered = [torch.empty_like(got) for _ in range(world)]
         dist.all_gather(gathered, got.contiguous())
         same = all(torch.equal(gathered[0], t) for t in gathered[1:])
+        # and the two-step baseline it replaces (NCCL all-reduce mean, then sacb_sgd) gives the same bits at world 2
+        # ((a + b) * 0.5 is order-independent); same random gradients as _run_rank
+        from da_sac_b200.trainer import allreduce_mean_
+        net2, cfg2, st2 = _make(rank, dev)
+        gen = torch.Generator(device="cpu").manual_seed(100)
+        for s in range(3):
+            per_rank = [torch.randn(net2.backbone._flat.total, generator=gen) * 1e-2 for _ in range(world)]
+            net2.backbone._grad.buf.copy_(per_rank[rank].to(dev))
+            allreduce_mean_(net2.backbone._grad.buf)
+            st2.optim.step()
+        torch.cuda.synchronize(dev)
+        same = same and torch.equal(net2.backbone._flat.buf, got)
         q.put((rank, err, bool(same), ""))
     except Exception as e:      # surface the failure instead of hanging the parent
         q.put((rank, float("nan"), False, repr(e)))
@@ -125,4 +138,4 @@ def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
     print(res)
     for rank, err, same, msg in res:
         assert msg == "", msg
-        assert same and err < 1e-6, (rank, err, same)
+        assert same and err < 1e-4, (rank, err, same)
