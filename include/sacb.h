@@ -233,6 +233,39 @@ int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_ranges, int
 int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_ranges, const float* seg_lr,
              const float* seg_wd, int nseg, float momentum, int first_step, void* stream);
 
+/* ---------------------------------------------------------------- target-view augmentation on the device
+ * Replaces DataTarget.__getitem__'s PIL pipeline (datasets/dataloader_target.py:264-306; datasets/tf_target.py:140-156
+ * GuidedRandHFlip, :158-239 MaskRandScaleCrop, :331-390 blur / jitter / greyscale, :32-98 to-tensor / normalise / mask):
+ * from G base crops (uint8 RGB, already at crop size) to G*T views.  Per view v the host supplies view_params[v][16]:
+ *   [0] flip (+1 / -1)   [1] crop top  [2] crop left  [3] crop height  [4] crop width   (window in the flipped base crop;
+ *                                       it may extend outside for zoom-out, then the outside is black and masked)
+ *   [5] Gaussian blur sigma (0 = off)   [6] colour jitter on/off   [7..10] op order (0 brightness, 1 contrast, 2 saturation,
+ *   3 hue)   [11] brightness  [12] contrast  [13] saturation factors  [14] hue shift in [-0.5, 0.5]   [15] greyscale on/off
+ * Outputs follow the reference's batch_target: frames1 (photometric copy), gt (-1 inside padding, else the label or 255),
+ * frames2 (clean copy); both normalised with mean/std and zeroed inside padding.  affine / affine_inv are computed on the
+ * host from the same parameters (da_sac_b200/augment.py, dataloader_target.py:220-262). */
+#define SACB_AUG_NPARAM 16
+typedef struct SacbAug {
+  uint32_t size;
+  int32_t G, T, H, W;
+  const uint8_t* base;          /* [G,H,W,3] RGB */
+  const uint8_t* base_mask;     /* [G,H,W] > 0 = padding (MaskRandCrop), or NULL */
+  const uint8_t* base_label;    /* [G,H,W] or NULL (= 255: unlabelled target data) */
+  const float* view_params;     /* device [G*T][SACB_AUG_NPARAM] */
+  float mean[3], std[3];
+  /* workspace */
+  uint8_t* raw;                 /* [G*T,H,W,3] resized 8-bit views */
+  uint8_t* mask;                /* [G*T,H,W] */
+  float* tmp;                   /* [G*T,H,W,3] */
+  float* levels;                /* [G*T,H,W,3] */
+  uint64_t* grey_sum;           /* [G*T] */
+  /* outputs */
+  float* frames1;               /* [G*T,3,H,W] */
+  int64_t* gt;                  /* [G*T,H,W] */
+  float* frames2;               /* [G*T,3,H,W] */
+} SacbAug;
+int sacb_target_augment(const SacbAug* d, void* stream);
+
 /* ---------------------------------------------------------------- gradient all-reduce fused with SGD over NVLink peer memory
  * Replaces DistributedDataParallel's gradient all-reduce (train.py:104,232; sum over ranks / world) + torch.optim.SGD.step()
  * (train.py:233) for the data-parallel target step with ONE kernel per rank and no NCCL call:
