@@ -175,7 +175,9 @@ def main():
     def run(n, e2e):
         for _ in range(n):
             if e2e:
-                stepper.step(host, read_losses=True)               # pinned host -> device copies + loss scalars -> host
+                # pinned host -> device copy of EVERY step's inputs (issued on a copy stream while the previous step
+                # computes, as a pin_memory DataLoader would) + loss scalars -> host
+                stepper.step(host, read_losses=True, prefetch_next=host)
             elif stepper._graph is not None:
                 stepper.step(dev_batch, read_losses=False)         # inputs are copied into the graph's static buffers
             else:

@@ -166,6 +166,36 @@ class TargetStepper(object):
     def h2d(self, host_batch):
         return tuple(t.to(self.device, non_blocking=True) for t in host_batch)
 
+    def prefetch(self, host_batch):
+        """Start the host->device copy of the NEXT batch on a side stream so that it overlaps the step that is running
+        (the B200-side equivalent of a DataLoader with pin_memory + ``.cuda(non_blocking=True)``; the reference copies
+        synchronously at train.py:183).  ``step(host_batch)`` then picks the staged copy up."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_batch)
+            self._staging_free = None
+        cs = self._copy_stream
+        if self._staging_free is not None:
+            cs.wait_event(self._staging_free)               # the previous step has finished reading the staging buffers
+        with torch.cuda.stream(cs):
+            for d, s_ in zip(self._staging, host_batch):
+                d.copy_(s_, non_blocking=True)
+            self._staging_ready = torch.cuda.Event()
+            self._staging_ready.record(cs)
+        self._prefetched = host_batch
+
+    def _take_prefetched(self, batch):
+        """device copy of ``batch`` if ``prefetch(batch)`` is pending, else None"""
+        if getattr(self, "_prefetched", None) is None or any(a is not b for a, b in zip(self._prefetched, batch)):
+            return None
+        self._prefetched = None
+        torch.cuda.current_stream().wait_event(self._staging_ready)
+        return self._staging
+
+    def _release_staging(self):
+        self._staging_free = torch.cuda.Event()
+        self._staging_free.record(torch.cuda.current_stream())
+
     def _eager(self, batch, update_teacher):
         x, y, x2, A, Ai = batch
         losses, outs = self.net(x, y, x2, A, Ai, use_teacher=True, update_teacher=update_teacher, T=self.T)
@@ -200,22 +230,31 @@ class TargetStepper(object):
         self.iter += 2
         return g
 
-    def step(self, batch, update_teacher=None, read_losses=False):
-        """one Trainer._step_target(train=True); ``batch`` may live on the device or in pinned host memory"""
+    def step(self, batch, update_teacher=None, read_losses=False, prefetch_next=None):
+        """one Trainer._step_target(train=True); ``batch`` may live on the device or in pinned host memory.
+        ``prefetch_next``: pinned host batch of the following step, copied while this step computes."""
         if update_teacher is None:
             update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)          # train.py:294
+        staged = None if batch[0].is_cuda else self._take_prefetched(batch)
         if self._graph is not None and not update_teacher:
-            for d, s_ in zip(self._static, batch):
+            for d, s_ in zip(self._static, batch if staged is None else staged):
                 d.copy_(s_, non_blocking=True)                                      # H2D when ``batch`` is pinned host memory
+            if staged is not None:
+                self._release_staging()
             self._graph.replay()
             self.launches += self._graph_launches
             v = self._graph_losses
         else:
-            if not batch[0].is_cuda:
+            if staged is not None:
+                batch = tuple(t.clone() for t in staged)                            # y is mutated in place (sac.py:338)
+                self._release_staging()
+            elif not batch[0].is_cuda:
                 batch = self.h2d(batch)
             n0 = L.launch_count()
             v = self._eager(batch, update_teacher)
             self.launches += L.launch_count() - n0
+        if prefetch_next is not None:
+            self.prefetch(prefetch_next)
         self.iter += 1
         if read_losses:
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
