@@ -598,6 +598,101 @@ wgrad_finalize_kernel(const float* __restrict__ dwraw, const float* __restrict__
   if (dbias && threadIdx.x == 0) dbias[k] = sc * dbeta[k];        // d(conv bias) = sum g * dy/dz = scale * d(beta)
 }
 
+// ---------------------------------------------------------------- batched (multi-layer) variants: ONE launch per network
+// block -> item through a prefix table of blocks (binary search, <= 8 steps)
+SACB_DEVINL int find_item(const int32_t* __restrict__ block_begin, int n_items, int blk) {
+  int lo = 0, hi = n_items;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (block_begin[mid] <= blk) lo = mid + 1; else hi = mid; }
+  return lo - 1;
+}
+
+constexpr int PREP_PER_BLOCK = 2048;
+__global__ void __launch_bounds__(256)
+prepare_batched_kernel(const SacbPrepItem* __restrict__ items, const int32_t* __restrict__ block_begin, int n_items, float eps) {
+  const int it = find_item(block_begin, n_items, blockIdx.x);
+  const SacbPrepItem d = items[it];
+  const int cb = blockIdx.x - block_begin[it];
+  if (cb == 0 && d.scale) {                        // BN fold (same expressions as bn_fold_kernel)
+    for (int c = threadIdx.x; c < d.K; c += 256) {
+      const float bias = d.conv_bias ? d.conv_bias[c] : 0.f;
+      if (!d.gamma) { d.scale[c] = 1.f; d.shift[c] = bias; continue; }
+      const float invstd = 1.0f / sqrtf(d.var[c] + eps);
+      const float sc = d.gamma[c] * invstd;
+      d.scale[c] = sc;
+      d.shift[c] = d.beta[c] + (bias - d.mean[c]) * sc;
+    }
+  }
+  if (!d.wf_hi) return;
+  const int RS = d.R * d.S, K = d.K, C = d.C, Kf = d.Kf, Kt = d.Kt;
+  const size_t nf = (size_t)RS * Kf * C;
+  const size_t nt = d.wt_hi ? (size_t)RS * C * Kt : 0;
+  uint16_t* wf_hi = (uint16_t*)d.wf_hi; uint16_t* wf_lo = (uint16_t*)d.wf_lo;
+  uint16_t* wt_hi = (uint16_t*)d.wt_hi; uint16_t* wt_lo = (uint16_t*)d.wt_lo;
+  const size_t i0 = (size_t)cb * PREP_PER_BLOCK;
+  for (int e = threadIdx.x; e < PREP_PER_BLOCK; e += 256) {
+    const size_t i = i0 + e;
+    if (i >= nf + nt) break;
+    if (i < nf) {
+      const int c = (int)(i % C);
+      size_t t = i / C;
+      const int k = (int)(t % Kf);
+      const int rs = (int)(t / Kf);
+      float v = 0.f;
+      if (k < K) v = d.w[((size_t)k * C + c) * RS + rs];
+      st_split(wf_hi, wf_lo, i, v);
+    } else {
+      const size_t j = i - nf;
+      const int k = (int)(j % Kt);
+      size_t t = j / Kt;
+      const int c = (int)(t % C);
+      const int rs = (int)(t / C);
+      float v = 0.f;
+      if (k < K) {
+        v = d.w[((size_t)k * C + c) * RS + (RS - 1 - rs)];     // 180-degree flipped tap
+        if (d.gamma) v *= d.gamma[k] * (1.0f / sqrtf(d.var[k] + eps));     // folded BN scale, recomputed (bit-identical)
+      }
+      st_split(wt_hi, wt_lo, j, v);
+    }
+  }
+}
+
+// block per (item, output channel)
+__global__ void __launch_bounds__(256)
+wgrad_finalize_batched_kernel(const SacbFinalizeItem* __restrict__ items, const int32_t* __restrict__ block_begin, int n_items,
+                              float eps) {
+  const int it = find_item(block_begin, n_items, blockIdx.x);
+  const SacbFinalizeItem d = items[it];
+  const int k = blockIdx.x - block_begin[it];
+  const int K = d.K, C = d.C, RS = d.RS;
+  const float sc = d.scale ? d.scale[k] : 1.f;
+  float dot = 0.f;
+  const size_t base = (size_t)k * RS * C;
+  for (int i = threadIdx.x; i < RS * C; i += 256) {
+    const int rs = i / C, c = i - rs * C;
+    float g = 0.f;                                   // [split][k][rs][c], summed in split order (deterministic)
+    for (int sp = 0; sp < d.splits; ++sp) g += d.dwraw[(size_t)sp * K * RS * C + base + i];
+    const size_t o = base + (size_t)c * RS + rs;     // [k][c][rs]
+    dot = fmaf(d.w[o], g, dot);
+    d.dw[o] = sc * g;
+  }
+  if (d.dgamma) {
+    __shared__ float red[8];
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffff, dot, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i];
+      const float b = d.conv_bias ? d.conv_bias[k] : 0.f;
+      d.dgamma[k] = (s + (b - d.mean[k]) * d.dbeta[k]) * (1.0f / sqrtf(d.var[k] + eps));
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (d.dbias) d.dbias[k] = sc * d.dbeta[k];
+    if (d.dbeta_out) d.dbeta_out[k] = d.dbeta[k];    // d(beta) lands in the flat gradient buffer
+  }
+}
+
 static inline int grid_for(size_t n, int block) {
   size_t g = (n + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -740,6 +835,28 @@ extern "C" int sacb_wgrad_finalize(const float* dwraw, const float* w, const flo
                                    void* stream) {
   wgrad_finalize_kernel<<<K, 256, 0, ST>>>(dwraw, w, scale, mean, var, eps, dbeta, dw, dgamma, conv_bias, dbias, K, C,
                                           R * S, splits);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_prep_item_blocks(int K, int C, int R, int S, int Kf, int Kt, int with_wf, int with_wt) {
+  const size_t n = (with_wf ? (size_t)R * S * Kf * C : 0) + (with_wf && with_wt ? (size_t)R * S * C * Kt : 0);
+  const size_t b = (n + PREP_PER_BLOCK - 1) / PREP_PER_BLOCK;
+  return (int)(b ? b : 1);
+}
+
+extern "C" int sacb_prepare_batched(const SacbPrepItem* items_dev, const int32_t* block_begin_dev, int n_items, int total_blocks,
+                                    float eps, void* stream) {
+  SACB_REQUIRE(items_dev && block_begin_dev && n_items > 0 && total_blocks > 0, "sacb_prepare_batched: bad arguments");
+  prepare_batched_kernel<<<total_blocks, 256, 0, ST>>>(items_dev, block_begin_dev, n_items, eps);
+  LAUNCHED();
+  return 0;
+}
+
+extern "C" int sacb_wgrad_finalize_batched(const SacbFinalizeItem* items_dev, const int32_t* block_begin_dev, int n_items,
+                                           int total_blocks, float eps, void* stream) {
+  SACB_REQUIRE(items_dev && block_begin_dev && n_items > 0 && total_blocks > 0, "sacb_wgrad_finalize_batched: bad arguments");
+  wgrad_finalize_batched_kernel<<<total_blocks, 256, 0, ST>>>(items_dev, block_begin_dev, n_items, eps);
   LAUNCHED();
   return 0;
 }

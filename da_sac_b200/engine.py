@@ -260,27 +260,40 @@ class WeightPlanes(object):
         s = self.net["specs"][name]; o = self.off[name][2]
         return self.scale[o:o + s.Kf], self.shift[o:o + s.Kf]
 
-    def prepare(self, flat):
-        lib, st = L.lib(), L.stream()
+    def _prep_table(self, flat):
+        """device descriptor table for sacb_prepare_batched (rebuilt if the flat buffer moved, e.g. into peer memory)"""
+        key = flat.buf.data_ptr()
+        if getattr(self, "_ptab", None) is not None and self._ptab[0] == key:
+            return self._ptab[1]
+        lib = L.lib()
+        items, blocks = [], []
         for name in self.net["order"]:
             s = self.net["specs"][name]
-            sc, sh = self.affine(name)
             if s.head:
                 continue
-            cb = L.ptr(flat.view(name + ".bias")) if s.bias else None
-            if s.bn is not None:
-                L.check(lib.sacb_bn_fold(L.ptr(flat.view(s.bn + ".weight")), L.ptr(flat.view(s.bn + ".bias")),
-                                         L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
-                                         C.c_float(BN_EPS), cb, L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
-            else:
-                L.check(lib.sacb_bn_fold(None, None, None, None, C.c_float(BN_EPS), cb, L.ptr(sc), L.ptr(sh), s.K, st), "sacb_bn_fold")
-            if s.C == 3:
-                continue
-            fh, fl = self.wf(name)
-            th, tl = self.wt(name) if self.with_dgrad else (None, None)
-            L.check(lib.sacb_prep_weight(L.ptr(flat.view(name + ".weight")), L.ptr(sc),
-                                         s.K, s.C, s.R, s.R, s.Kf, s.Kt, L.ptr(fh), L.ptr(fl), L.ptr(th), L.ptr(tl), st),
-                    "sacb_prep_weight")
+            sc, sh = self.affine(name)
+            bn = s.bn is not None
+            planes = s.C != 3
+            fh, fl = self.wf(name) if planes else (None, None)
+            th, tl = self.wt(name) if (planes and self.with_dgrad) else (None, None)
+            items.append(L.PrepItem(L.dptr(flat.view(name + ".weight")),
+                                    L.dptr(flat.view(s.bn + ".weight")) if bn else None,
+                                    L.dptr(flat.view(s.bn + ".bias")) if bn else None,
+                                    L.dptr(flat.view(s.bn + ".running_mean")) if bn else None,
+                                    L.dptr(flat.view(s.bn + ".running_var")) if bn else None,
+                                    L.dptr(flat.view(name + ".bias")) if s.bias else None,
+                                    L.dptr(sc), L.dptr(sh), L.dptr(fh), L.dptr(fl), L.dptr(th), L.dptr(tl),
+                                    s.K, s.C, s.R, s.R, s.Kf, s.Kt))
+            blocks.append(lib.sacb_prep_item_blocks(s.K, s.C, s.R, s.R, s.Kf, s.Kt, 1 if planes else 0,
+                                                    1 if (planes and self.with_dgrad) else 0))
+        self._ptab = (key, L.item_table(items, blocks, flat.buf.device))
+        return self._ptab[1]
+
+    def prepare(self, flat):
+        lib, st = L.lib(), L.stream()
+        # BN fold + fprop / dgrad weight planes of every conv unit: ONE launch (was 2 per layer)
+        items, begin, n, total = self._prep_table(flat)
+        L.check(lib.sacb_prepare_batched(L.ptr(items), L.ptr(begin), n, total, C.c_float(BN_EPS), st), "sacb_prepare_batched")
         sh_, sl_ = self.stem()
         stem = self.net["stem"]
         L.check(lib.sacb_stem_pack_weight(L.ptr(flat.view(stem.name + ".weight")), L.ptr(sh_), L.ptr(sl_), stem.K,
@@ -387,8 +400,12 @@ class EngineBase(object):
         self.tpool_hi.reset(); self.tpool_lo.reset(); self.fpool.reset()
         # d(beta) of every BN unit (d(bias) of bias-only convs) = column sums of the gradient arriving at it; accumulated by
         # the epilogue of the GEMM that produces that gradient (colsum=...), into one zero-filled buffer
-        self._dbeta_pool = torch.zeros(sum(s.K for s in self.net["specs"].values() if not s.head) + 64, device=self.device)
+        if getattr(self, "_dbeta_pool", None) is None:      # persistent: the batched finalize table holds pointers into it
+            self._dbeta_pool = torch.zeros(sum(s.K for s in self.net["specs"].values() if not s.head) + 4096, device=self.device)
+        else:
+            self._dbeta_pool.zero_()
         self._dbeta_off = 0
+        self._fin_pending = []
 
     def _aspp_bwd(self, flat, wp, xlast, dlogits, grad):
         """Gcol (shifted copies of dlogits) -> bias / filter / data gradients as plain GEMMs. Returns (gout, dbeta of xlast's unit)."""
@@ -467,10 +484,11 @@ class EngineBase(object):
     def _new_dbeta(self, K):
         o = self._dbeta_off
         self._dbeta_off = o + K
+        assert self._dbeta_off <= self._dbeta_pool.numel(), "d(beta) pool exhausted"
         return self._dbeta_pool[o:o + K]
 
     def _dbeta(self, g, M, K):
-        d = torch.zeros(K, device=self.device)
+        d = self._new_dbeta(K)                 # slice of the zero-filled persistent pool
         L.check(L.lib().sacb_colsum(L.ptr(g.hi), L.ptr(g.lo), L.ptr(d), C.c_int64(M), K, L.stream()), "sacb_colsum")
         return d
 
@@ -479,28 +497,48 @@ class EngineBase(object):
             self.dwraw = torch.empty(n, device=self.device)
         return self.dwraw
 
+    def _dw_for(self, name, n):
+        """split-K partial planes of one layer: every layer keeps its own region until the batched finalize at the end
+        of the backward pass (~38 MB per layer: one 256x256 fp32 tile per CTA pair)"""
+        arena = self.__dict__.setdefault("_dw_arena", {})
+        t = arena.get(name)
+        if t is None or t.numel() < n:
+            t = arena[name] = torch.empty(n, device=self.device)
+            self._fin_table = None
+        return t
+
     def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
-        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, self._dw_workspace,
+        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, lambda n: self._dw_for(s.name, n),
                                      (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
         self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R, splits=splits)
 
     def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS, splits=1):
-        """dW (OIHW), d gamma, d beta and the conv-bias gradient of one unit from its raw filter gradient and d beta"""
-        lib, st = L.lib(), L.stream()
-        cb = L.ptr(flat.view(s.name + ".bias")) if s.bias else None
-        db = L.ptr(grad.view(s.name + ".bias")) if s.bias else None
-        if s.bn is not None:
-            sc, _ = wp.affine(s.name)
-            grad.view(s.bn + ".bias").copy_(dbeta)
-            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), L.ptr(sc),
-                                            L.ptr(flat.view(s.bn + ".running_mean")), L.ptr(flat.view(s.bn + ".running_var")),
-                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")),
-                                            L.ptr(grad.view(s.bn + ".weight")), cb, db, s.K, C_eff, RS, 1, splits, st),
-                    "sacb_wgrad_finalize")
-        else:
-            L.check(lib.sacb_wgrad_finalize(L.ptr(dwraw), L.ptr(flat.view(s.name + ".weight")), None, None, None,
-                                            C.c_float(BN_EPS), L.ptr(dbeta), L.ptr(grad.view(s.name + ".weight")), None,
-                                            cb, db, s.K, C_eff, RS, 1, splits, st), "sacb_wgrad_finalize")
+        """dW (OIHW), d gamma, d beta and the conv-bias gradient of one unit from its raw filter gradient and d beta.
+        Deferred: all units of a backward pass are finalised by ONE launch (``_finalize_all``)."""
+        self._fin_pending.append((s, dwraw, dbeta, C_eff, RS, splits))
+
+    def _finalize_all(self, flat, wp, grad):
+        key = (flat.buf.data_ptr(), grad.buf.data_ptr(), wp.scale.data_ptr(), len(self._fin_pending))
+        tab = getattr(self, "_fin_table", None)
+        if tab is None or tab[0] != key:
+            items, blocks = [], []
+            for s, dwraw, dbeta, C_eff, RS, splits in self._fin_pending:
+                bn = s.bn is not None
+                sc = wp.affine(s.name)[0] if bn else None
+                items.append(L.FinalizeItem(
+                    L.dptr(dwraw), L.dptr(flat.view(s.name + ".weight")), L.dptr(sc),
+                    L.dptr(flat.view(s.bn + ".running_mean")) if bn else None,
+                    L.dptr(flat.view(s.bn + ".running_var")) if bn else None, L.dptr(dbeta),
+                    L.dptr(grad.view(s.name + ".weight")), L.dptr(grad.view(s.bn + ".weight")) if bn else None,
+                    L.dptr(flat.view(s.name + ".bias")) if s.bias else None,
+                    L.dptr(grad.view(s.name + ".bias")) if s.bias else None,
+                    L.dptr(grad.view(s.bn + ".bias")) if bn else None, s.K, C_eff, RS, splits))
+                blocks.append(s.K)
+            tab = self._fin_table = (key, L.item_table(items, blocks, self.device))
+        items, begin, n, total = tab[1]
+        L.check(L.lib().sacb_wgrad_finalize_batched(L.ptr(items), L.ptr(begin), n, total, C.c_float(BN_EPS), L.stream()),
+                "sacb_wgrad_finalize_batched")
+        self._fin_pending = []
 
 
 class ResNet101Engine(EngineBase):
@@ -633,6 +671,7 @@ class ResNet101Engine(EngineBase):
                                      N, stem.hout, stem.wout, 64, ph, pw, st), "sacb_maxpool_bwd")
         dbeta = self._dbeta(gs, N * stem.hout * stem.wout, 64)
         self._first_conv_bwd(flat, wp, gs, grad, dbeta)
+        self._finalize_all(flat, wp, grad)
 
 
 class VGG16Engine(EngineBase):
@@ -685,6 +724,7 @@ class VGG16Engine(EngineBase):
         last = seq[-1][1]
         g, dbeta = self._aspp_bwd(flat, wp, self.act[last.name], dlogits, grad)      # g = grad at fc7's output (masked)
         self._trunk_backward(flat, wp, seq, len(seq) - 1, g, dbeta, None, grad)
+        self._finalize_all(flat, wp, grad)
 
 
 class FCN8sEngine(EngineBase):
@@ -807,6 +847,7 @@ class FCN8sEngine(EngineBase):
         self._tput("gout")
         seq = net["seq"]
         self._trunk_backward(flat, wp, seq, len(seq) - 1, None, None, gp, grad, inject={"pool30": self.inj4, "pool20": self.inj3})
+        self._finalize_all(flat, wp, grad)
 
 
 def make_engine(arch, N, H, W, device):

@@ -103,6 +103,37 @@ class Loss(C.Structure):
                 ("dlogits", _vp)]
 
 
+class PrepItem(C.Structure):
+    _fields_ = [("w", _vp), ("gamma", _vp), ("beta", _vp), ("mean", _vp), ("var", _vp), ("conv_bias", _vp),
+                ("scale", _vp), ("shift", _vp), ("wf_hi", _vp), ("wf_lo", _vp), ("wt_hi", _vp), ("wt_lo", _vp),
+                ("K", C.c_int32), ("C", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kf", C.c_int32), ("Kt", C.c_int32)]
+
+
+class FinalizeItem(C.Structure):
+    _fields_ = [("dwraw", _vp), ("w", _vp), ("scale", _vp), ("mean", _vp), ("var", _vp), ("dbeta", _vp),
+                ("dw", _vp), ("dgamma", _vp), ("conv_bias", _vp), ("dbias", _vp), ("dbeta_out", _vp),
+                ("K", C.c_int32), ("C", C.c_int32), ("RS", C.c_int32), ("splits", C.c_int32)]
+
+
+def dptr(t):
+    """raw device address (int) of a tensor or None -- for descriptor tables that live on the device"""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+def item_table(items, blocks, device):
+    """(items_dev, block_begin_dev, n_items, total_blocks) for the batched multi-layer kernels"""
+    arr = (type(items[0]) * len(items))(*items)
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    begin, tot = [], 0
+    for b in blocks:
+        begin.append(tot); tot += int(b)
+    begin.append(tot)
+    return raw, torch.tensor(begin, dtype=torch.int32, device=device), len(items), tot
+
+
 # optional per-launch CUDA-event profiling of the GEMM kernels (used by bench.py's roofline leg only)
 _prof = None
 

@@ -144,6 +144,30 @@ int sacb_wgrad_finalize(const float* dwraw, const float* w_oihw, const float* sc
                         const float* var, float eps, const float* dbeta, float* dw_oihw, float* dgamma,
                         const float* conv_bias, float* dbias, int K, int C, int R, int S, int splits, void* stream);
 
+/* Multi-layer variants: ONE launch for a whole network.  `items_dev` is a DEVICE array of per-layer descriptors (the
+ * arguments of sacb_bn_fold + sacb_prep_weight, resp. sacb_wgrad_finalize, with the same meaning); `block_begin_dev[i]` is
+ * the first thread block of item i (prefix sums of sacb_prep_item_blocks(...), resp. of K), `total_blocks` their sum.
+ * sacb_prepare_batched: scale == NULL skips the fold, wf_hi == NULL skips the planes (first conv: packed separately);
+ * the dgrad planes are pre-multiplied by gamma * rsqrt(var + eps) when gamma != NULL.
+ * sacb_wgrad_finalize_batched additionally copies d(beta) to dbeta_out (the BN bias gradient in the flat buffer). */
+typedef struct SacbPrepItem {
+  const float* w;                                   /* OIHW fp32 */
+  const float* gamma; const float* beta; const float* mean; const float* var; const float* conv_bias;
+  float* scale; float* shift;                       /* [K] folded affine out */
+  void* wf_hi; void* wf_lo; void* wt_hi; void* wt_lo;
+  int32_t K, C, R, S, Kf, Kt;
+} SacbPrepItem;
+int sacb_prep_item_blocks(int K, int C, int R, int S, int Kf, int Kt, int with_wf, int with_wt);
+int sacb_prepare_batched(const SacbPrepItem* items_dev, const int32_t* block_begin_dev, int n_items, int total_blocks,
+                         float eps, void* stream);
+typedef struct SacbFinalizeItem {
+  const float* dwraw; const float* w; const float* scale; const float* mean; const float* var; const float* dbeta;
+  float* dw; float* dgamma; const float* conv_bias; float* dbias; float* dbeta_out;
+  int32_t K, C, RS, splits;
+} SacbFinalizeItem;
+int sacb_wgrad_finalize_batched(const SacbFinalizeItem* items_dev, const int32_t* block_begin_dev, int n_items,
+                                int total_blocks, float eps, void* stream);
+
 /* ---------------------------------------------------------------- ASPP head as a tap-unrolled 1x1 GEMM
  * Classifier_Module (deeplabv2.py:101-116): sum of four 3x3 dilated convs 2048 -> 19 (+ biases).
  *   Z[pix, (i*9 + r*3+s)*19 + k] = sum_c X[pix,c] * W_i[k,c,r,s]   via sacb_conv_gemm (1x1, K = sacb_aspp_jpad() = 768)
