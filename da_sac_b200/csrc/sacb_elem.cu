@@ -175,9 +175,12 @@ stem_wgrad_kernel(const float* __restrict__ x, const uint16_t* __restrict__ g_hi
 // 7x7 s2 conv becomes a 1x1 conv_gemm with C = 192 (and its filter gradient a plain conv_wgrad).
 // ------------------------------------------------------------------------------------------------
 // Generic for any 3-input-channel first conv: R x R taps, `stride`, `pad`; TAPS = 3*R*R columns padded to KP (multiple of 64).
+// RT > 0: filter size known at compile time (7: ResNet stem, 3: VGG features.0) so the tap index arithmetic is constant-folded
+template <int RT>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ a_hi, uint16_t* __restrict__ a_lo, int N, int H,
-                   int W, int P, int Q, int R, int stride, int pad, int KP) {
+                   int W, int P, int Q, int R_rt, int stride, int pad, int KP) {
+  const int R = RT > 0 ? RT : R_rt;
   const int RR = R * R, TAPS = 3 * RR;
   const size_t total = (size_t)N * P * Q * (KP / 8);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
@@ -726,7 +729,9 @@ extern "C" int sacb_stem_im2col(const float* x, void* a_hi, void* a_lo, int N, i
   SACB_REQUIRE(P == (H + 2 * pad - R) / stride + 1 && Q == (W + 2 * pad - R) / stride + 1, "sacb_stem_im2col: bad output size");
   SACB_REQUIRE(KP % 64 == 0 && KP >= 3 * R * R, "sacb_stem_im2col: KP must be a multiple of 64 covering 3*R*R taps");
   const size_t total = (size_t)N * P * Q * (KP / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q, R, stride, pad, KP);
+  if (R == 7) stem_im2col_kernel<7><<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q, R, stride, pad, KP);
+  else if (R == 3) stem_im2col_kernel<3><<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q, R, stride, pad, KP);
+  else stem_im2col_kernel<0><<<grid_for(total, 256), 256, 0, ST>>>(x, (uint16_t*)a_hi, (uint16_t*)a_lo, N, H, W, P, Q, R, stride, pad, KP);
   LAUNCHED();
   return 0;
 }

@@ -155,7 +155,7 @@ tail_running_conf_kernel(const float* __restrict__ part_sums, int nparts, int C,
 template <int C_>
 __global__ void __launch_bounds__(256)
 tail_pool_kernel(const float* __restrict__ probs, const float* __restrict__ affine, const float* __restrict__ affine_inv,
-                 float* __restrict__ pooled, int T, int C, int CP, int CP2, int H, int W, int partial) {
+                 float* __restrict__ pooled, int T, int C, int CP, int CP2, int H, int W, int partial, int minent) {
   const int g = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int HW = H * W;
@@ -164,6 +164,10 @@ tail_pool_kernel(const float* __restrict__ probs, const float* __restrict__ affi
   float S[C_];
 #pragma unroll
   for (int c = 0; c < C_; ++c) S[c] = 0.f;
+  float best_ent = INFINITY, Zall = 0.f;     // CONF_POOL = minentropy_pool (sac.py:218-236)
+  float Bst[C_];
+#pragma unroll
+  for (int c = 0; c < C_; ++c) Bst[c] = 0.f;
   for (int t = 0; t < T; ++t) {
     const int b = g * T + t;
     const Taps ta = make_taps(affine + b * 6, i, j, H, W);          // view -> reference (sac.py:289-290)
@@ -190,10 +194,37 @@ tail_pool_kernel(const float* __restrict__ probs, const float* __restrict__ affi
         }
       }
     }
+    if (minent) {
+      // entropy of this view's (aligned * valid) distribution (sac.py:189-196), views with no mass get 1/eps
+      const float eps = 1e-5f;
+      float ent = 0.f, z = 0.f;
+#pragma unroll
+      for (int c = 0; c < C_; ++c) if (c < C) {
+        const float pv = A[c] * V;
+        A[c] = pv;
+        z += pv;
+        ent -= pv * logf((pv + eps) / (1.f + eps));
+      }
+      if (z < 0.1f) ent = 1.f / eps;
+      Zall += z;
+      if (ent < best_ent) {                      // strict: the first view wins ties (torch.argmin)
+        best_ent = ent;
+#pragma unroll
+        for (int c = 0; c < C_; ++c) Bst[c] = A[c];
+      }
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) S[c] += A[c] * V;        // sac.py:305 aligned * valid, summed over T
   }
   float* dst = pooled + ((size_t)g * HW + pix) * CP2;
+  if (minent) {
+    // every view of the group receives the distribution of its min-entropy view; mask = total mass over views > 0.1
+#pragma unroll
+    for (int c = 0; c < C_; ++c) if (c < C) dst[c] = Bst[c];
+    dst[C] = Zall > 0.1f ? 1.f : 0.f;
+    return;
+  }
   if (partial) {
     // fractional group (sac.py:198-216,243-245): this rank holds only T of the group's views; the un-normalised sums
     // are exchanged (sum over the ranks that share the group) and tail_pool_finalize_kernel normalises them
@@ -235,7 +266,7 @@ template <int C_>
 __global__ void __launch_bounds__(256)
 tail_refine_kernel(const float* __restrict__ pooled, const float* __restrict__ affine_inv, float* __restrict__ conf,
                    uint8_t* __restrict__ idx, int* __restrict__ peaks, float* __restrict__ refined, int T, int C,
-                   int CP2, int H, int W) {
+                   int CP2, int H, int W, const float* __restrict__ probs_direct, int CP) {
   __shared__ int speak[C_];
   const int b = blockIdx.y;
   const int g = b / T;
@@ -245,11 +276,17 @@ tail_refine_kernel(const float* __restrict__ pooled, const float* __restrict__ a
   __syncthreads();
   if (pix < HW) {
     const int i = pix / W, j = pix - i * W;
-    const Taps t = make_taps(affine_inv + b * 6, i, j, H, W);       // reference -> view (sac.py:309-310)
     float R[C_];
 #pragma unroll
     for (int c = 0; c < C_; ++c) R[c] = 0.f;
     float Mv = 0.f;
+    if (probs_direct) {                                             // CONF_POOL_ON = False: _refine(pool=False), sac.py:284-285
+      const float* src = probs_direct + ((size_t)b * HW + pix) * CP;
+#pragma unroll
+      for (int c = 0; c < C_; ++c) if (c < C) R[c] = src[c];
+      Mv = 1.f;
+    } else {
+    const Taps t = make_taps(affine_inv + b * 6, i, j, H, W);       // reference -> view (sac.py:309-310)
     const float wts[4] = {t.nw, t.ne, t.sw, t.se};
     const bool inb[4] = {t.in_y0 && t.in_x0, t.in_y0 && t.in_x1, t.in_y1 && t.in_x0, t.in_y1 && t.in_x1};
     const float* base = pooled + (size_t)g * HW * CP2;
@@ -271,11 +308,12 @@ tail_refine_kernel(const float* __restrict__ pooled, const float* __restrict__ a
         }
       }
     }
+    }
     float best = -INFINITY; int bi = 0;
 #pragma unroll
     for (int c = 0; c < C_; ++c) {
       if (c < C) {
-        R[c] *= Mv;                                                    // sac.py:311
+        if (!probs_direct) R[c] *= Mv;                                 // sac.py:311
         if (R[c] > best) { best = R[c]; bi = c; }                      // first index on ties (torch.max)
       }
     }
@@ -606,6 +644,8 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   const int nb = (HW + 255) / 256;
   dim3 gridB(nb, d->BT), gridG(nb, d->BT / d->T);
   SACB_REQUIRE(d->phase >= 0 && d->phase <= 2, "sacb_teacher_tail: phase must be 0, 1 or 2");
+  SACB_REQUIRE(d->pool_mode >= 0 && d->pool_mode <= 2, "sacb_teacher_tail: pool_mode must be 0 (avg), 1 (min-entropy) or 2 (off)");
+  SACB_REQUIRE(d->pool_mode == 0 || d->phase == 0, "sacb_teacher_tail: fractional groups need the average pool");
   if (d->phase != 2) {
     tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
     LAUNCHED();
@@ -614,9 +654,11 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
                                                 d->stat_momentum, d->running_conf);
       LAUNCHED();
     }
-    tail_pool_kernel<C_><<<gridG, 256, 0, ST>>>(d->probs, d->affine, d->affine_inv, d->pooled, d->T, C, CP, CP2, d->H, d->W,
-                                               d->phase == 1);
-    LAUNCHED();
+    if (d->pool_mode != 2) {
+      tail_pool_kernel<C_><<<gridG, 256, 0, ST>>>(d->probs, d->affine, d->affine_inv, d->pooled, d->T, C, CP, CP2, d->H, d->W,
+                                                 d->phase == 1, d->pool_mode == 1);
+      LAUNCHED();
+    }
     if (d->phase == 1) return 0;          // caller sums `pooled` over the ranks that share the group, then phase 2
   } else {
     const size_t npix = (size_t)(d->BT / d->T) * HW;
@@ -625,7 +667,7 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   }
   SACB_CHECK_CUDA(cudaMemsetAsync(d->peaks, 0, sizeof(float) * d->BT * C, ST));
   tail_refine_kernel<C_><<<gridB, 256, 0, ST>>>(d->pooled, d->affine_inv, d->conf, d->idx, reinterpret_cast<int*>(d->peaks),
-                                               d->refined, d->T, C, CP2, d->H, d->W);
+                                               d->refined, d->T, C, CP2, d->H, d->W, d->pool_mode == 2 ? d->probs : nullptr, CP);
   LAUNCHED();
   tail_threshold_kernel<<<(d->BT * C + 127) / 128, 128, 0, ST>>>(reinterpret_cast<const int*>(d->peaks), d->running_conf,
                                                                d->thresholds, d->BT, C, d->conf_upper, d->conf_lower,

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsac_b200.so")
-ABI_VERSION = 2          # SACB_ABI_VERSION in include/sacb.h
+ABI_VERSION = 3          # SACB_ABI_VERSION in include/sacb.h
 
 
 class SacbError(RuntimeError):
@@ -90,7 +90,7 @@ class Tail(C.Structure):
                 ("training", C.c_int32), ("discount", C.c_int32),
                 ("beta", C.c_float), ("stat_momentum", C.c_float), ("conf_upper", C.c_float), ("conf_lower", C.c_float),
                 ("probs", _vp), ("pooled", _vp), ("part_sums", _vp), ("peaks", _vp),
-                ("conf", _vp), ("idx", _vp), ("labels", _vp), ("conf_mean", _vp), ("thresholds", _vp), ("refined", _vp), ("phase", C.c_int32)]
+                ("conf", _vp), ("idx", _vp), ("labels", _vp), ("conf_mean", _vp), ("thresholds", _vp), ("refined", _vp), ("phase", C.c_int32), ("pool_mode", C.c_int32)]
 
 
 class Loss(C.Structure):

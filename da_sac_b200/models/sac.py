@@ -92,8 +92,10 @@ class SAC(SAC_Baseline):
     def __init__(self, cfg, backbone, slow_copy, rank, **kwargs):
         super().__init__(cfg, backbone, rank, **kwargs)
         self.cfg = cfg
-        assert cfg.CONF_POOL == "avg_pool" and cfg.LOSS == "focal_ce_conf", \
-            "libsac_b200 implements the default CONF_POOL=avg_pool / LOSS=focal_ce_conf path"
+        # MODEL.CONF_POOL / CONF_POOL_ON / LOSS select methods by name in the reference (sac.py:46-47,65-68,353)
+        assert cfg.CONF_POOL in ("avg_pool", "minentropy_pool"), "Pooling OP _%s not found" % cfg.CONF_POOL
+        assert cfg.LOSS in ("focal_ce_conf", "focal_ce"), "Pooling OP _%s not found" % cfg.LOSS
+        self._pool_mode = 2 if not getattr(cfg, "CONF_POOL_ON", True) else (1 if cfg.CONF_POOL == "minentropy_pool" else 0)
         self.register_buffer("running_conf", torch.zeros(kwargs["num_classes"]))
         self.slow_net = slow_copy
         self.slow_net.eval()
@@ -167,10 +169,11 @@ class SAC(SAC_Baseline):
                           cfg.THRESHOLD_BETA, cfg.STAT_MOMENTUM, cfg.RUN_CONF_UPPER, cfg.RUN_CONF_LOWER,
                           L.ptr(ws["probs"]), L.ptr(ws["pooled"]), L.ptr(ws["part_sums"]), L.ptr(ws["peaks"]),
                           L.ptr(ws["conf"]), L.ptr(ws["idx"]), L.ptr(ws["labels"]), L.ptr(ws["conf_mean"]),
-                          L.ptr(ws["thresholds"]), L.ptr(refined), phase)
-        if T0 == T:
+                          L.ptr(ws["thresholds"]), L.ptr(refined), phase, self._pool_mode)
+        if T0 == T or self._pool_mode == 2:
             L.check(L.lib().sacb_teacher_tail(C.byref(desc(0)), L.stream()), "sacb_teacher_tail")
             return ws
+        assert self._pool_mode == 0, "fractional view-groups are implemented for CONF_POOL=avg_pool (the reference's _gather lives there)"
         d1 = desc(1)
         L.check(L.lib().sacb_teacher_tail(C.byref(d1), L.stream()), "sacb_teacher_tail(partial sums)")
         self._exchange_partial_sums(ws["pooled"], BT, T)
@@ -199,8 +202,13 @@ class SAC(SAC_Baseline):
         BT, Cn, h, w = logits.shape
         H, W = y.shape[-2:]
         keep = tail
+        conf_mean = tail["conf_mean"]
+        if self.cfg.LOSS == "focal_ce":                 # sac.py:119-132: no confidence weighting
+            if "ones" not in tail:
+                tail["ones"] = torch.ones_like(conf_mean)
+            conf_mean = tail["ones"]
         d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), L.ptr(tail["labels"]) if use_labels else None,
-                   L.ptr(tail["conf_mean"]), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
+                   L.ptr(conf_mean), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
                    L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits))
         return d, keep
 

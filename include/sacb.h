@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SACB_ABI_VERSION 2
+#define SACB_ABI_VERSION 3
 
 const char* sacb_last_error(void);
 int sacb_abi_version(void);
@@ -213,6 +213,10 @@ typedef struct SacbTail {
    * views THIS rank holds): 0 = whole tail; 1 = stop after writing the un-normalised reference-frame sums to `pooled`
    * (the caller sum-reduces `pooled` over the ranks sharing the group); 2 = resume: normalise `pooled`, labels. */
   int32_t phase;
+  /* MODEL.CONF_POOL / CONF_POOL_ON (core/config.py:150-151): 0 = avg_pool (sac.py:238-269, default), 1 = minentropy_pool
+   * (sac.py:218-236: every view receives the distribution of the group's lowest-entropy view), 2 = pooling off
+   * (_refine(pool=False), sac.py:284-285: labels straight from each view's masked teacher probabilities) */
+  int32_t pool_mode;
 } SacbTail;
 int sacb_teacher_tail(const SacbTail* d, void* stream);
 size_t sacb_tail_part_sums_elems(int BT, int C, int H, int W);

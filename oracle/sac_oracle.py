@@ -222,17 +222,42 @@ def avg_pool(probs, T, tolerance=0.1):
     return avg.flatten(0, 1), mask.flatten(0, 1)
 
 
-def refine(slow_logits, hw, T, affine, affine_inv, ignore_mask, running_conf, cfg, training=True):
-    """SAC._refine (sac.py:271-313). Returns (teacher_refined, new running_conf, diags)."""
+def entropy(probs, eps=1e-5):
+    """SAC._entropy (sac.py:189-196)"""
+    probs_eps = (probs + eps) / (1 + eps)
+    ent = -(probs * torch.log(probs_eps)).sum(1, keepdim=True)
+    ent[probs.sum(1, keepdim=True) < 0.1] = 1.0 / eps
+    return ent
+
+
+def minentropy_pool(probs, T, tolerance=0.1):
+    """SAC._minentropy_pool (sac.py:218-236): every view of a group receives the distribution of the group's
+    lowest-entropy view (first view on ties); mask = total mass over views and classes > tolerance."""
+    BT, C, H, W = probs.shape
+    ent_T = entropy(probs).view(-1, T, 1, H, W)
+    sel = ent_T.argmin(1, keepdim=True).expand(-1, -1, C, -1, -1)
+    probs_T = probs.view(-1, T, C, H, W)
+    masks = probs_T.sum(1, keepdim=True).sum(2, keepdim=True) > tolerance
+    picked = probs_T.gather(1, sel).expand(-1, T, -1, -1, -1)
+    masks = masks.expand(-1, T, -1, -1, -1).type_as(probs)
+    return picked.reshape(BT, C, H, W), masks.reshape(BT, 1, H, W)
+
+
+def refine(slow_logits, hw, T, affine, affine_inv, ignore_mask, running_conf, cfg, training=True, pool="avg_pool"):
+    """SAC._refine (sac.py:271-313). Returns (teacher_refined, new running_conf, diags).
+    ``pool``: "avg_pool" (default), "minentropy_pool", or None for MODEL.CONF_POOL_ON = False (sac.py:284-285)."""
     H, W = hw
     up = F.interpolate(slow_logits, (H, W), mode="bilinear", align_corners=True)   # :275
     probs = F.softmax(up, 1)                                                       # :276
     if training:
         running_conf = update_running_conf(running_conf, probs, cfg)               # :278-279
     probs = probs * (1 - ignore_mask[:, None].type_as(probs))                      # :282
+    if pool is None:
+        return probs, running_conf, {"teacher_init": up}
     aligned = _warp(probs, affine)                                                 # :289-290
     valid_aligned = _warp(torch.ones_like(aligned), affine_inv)                    # :299-301
-    refined_aligned, valid = avg_pool(aligned * valid_aligned, T)                  # :305
+    pool_fn = {"avg_pool": avg_pool, "minentropy_pool": minentropy_pool}[pool]
+    refined_aligned, valid = pool_fn(aligned * valid_aligned, T)                   # :305
     grid_inv = F.affine_grid(affine_inv, size=list(probs.shape), align_corners=False)
     refined = F.grid_sample(refined_aligned, grid_inv, align_corners=False)        # :309
     refined_valid = F.grid_sample(valid, grid_inv, align_corners=False)            # :310
@@ -299,6 +324,12 @@ def focal_ce_conf(logits_up, pseudo_gt, teacher_conf, running_conf, p=3):
     ce = F.cross_entropy(logits_up, pseudo_gt, weight=w, ignore_index=255, reduction="none")
     m = teacher_conf.mean(0)              # [1,H,W] batch-mean confidence
     return (ce * m).mean()
+
+
+def focal_ce(logits_up, pseudo_gt, running_conf, p=3):
+    """SAC._focal_ce (sac.py:119-132): MODEL.LOSS = focal_ce, no confidence weighting."""
+    w = (1 - running_conf.clamp(0.0)) ** p
+    return F.cross_entropy(logits_up, pseudo_gt, weight=w, ignore_index=255, reduction="none").mean()
 
 
 def focal_ce_conf_literal(logits_up, pseudo_gt, teacher_conf, running_conf, p=3):

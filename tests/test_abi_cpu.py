@@ -35,7 +35,7 @@ def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
     """sizeof + offset of the last field of every descriptor struct: include/sacb.h compiled by gcc vs the ctypes mirrors"""
     import subprocess
     from da_sac_b200 import lib, p2p
-    pairs = [("SacbConvGemm", lib.ConvGemm, "colsum"), ("SacbConvWgrad", lib.ConvWgrad, "splits"), ("SacbTail", lib.Tail, "phase"),
+    pairs = [("SacbConvGemm", lib.ConvGemm, "colsum"), ("SacbConvWgrad", lib.ConvWgrad, "splits"), ("SacbTail", lib.Tail, "pool_mode"),
              ("SacbLoss", lib.Loss, "dlogits"), ("SacbAllreduceSgd", p2p.AllreduceSgd, "first_step")]
     src = tmp_path / "sz.c"
     body = "".join('  printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (c, c, last) for c, _, last in pairs)
