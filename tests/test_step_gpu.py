@@ -433,3 +433,41 @@ def test_joint_source_target_step_matches_oracle(net):
         e = ((new - old) - (ref_new - old)).norm() / (ref_new - old).norm().clamp_min(1e-30)
         print("   joint post-SGD update", n, "rel-L2 %.2e" % float(e))
         assert float(e) < 2e-2, n
+
+
+def test_training_reduces_the_loss_and_teacher_follows():
+    """Does it actually train?  30 target steps on one fixed batch (device-augmented views, fused SGD): the supervised
+    monitor loss against fixed pseudo ground truth is not what is optimised, so the check is on self_ce itself, on the
+    teacher distance (0 right after the teacher is initialised from the student, growing while the student moves) and on
+    finiteness."""
+    import random
+    from da_sac_b200 import augment as AUG, synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import TargetStepper
+    cfg = type("Cfg", (synth.ModelCfg,), {"NET_MOMENTUM_ITER": 10, "LR": 2.5e-3})()
+    m = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    m.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    m.cuda().train()
+    G, Kk, hw = 2, 2, (128, 128)
+    st = TargetStepper(m, cfg, Kk, torch.device("cuda"))
+    random.seed(4); torch.manual_seed(4)
+    g = torch.Generator().manual_seed(9)
+    low = torch.rand(G, 3, 6, 6, generator=g)
+    base = (torch.nn.functional.interpolate(low, hw, mode="bicubic", align_corners=False).clamp(0, 1) * 255).round()
+    base = base.to(torch.uint8).permute(0, 2, 3, 1).contiguous().cuda()
+    aug = AUG.TargetAugmenter(Kk, hw)
+    batch = aug(base)
+    hist = []
+    for it in range(30):
+        out = st.step(tuple(t.clone() for t in batch), read_losses=True)
+        hist.append(out)
+        assert all(np.isfinite(v) for v in out.values()), (it, out)
+    first, last = np.mean([h["self_ce"] for h in hist[1:6]]), np.mean([h["self_ce"] for h in hist[-5:]])
+    print("self_ce first/last: %.5f -> %.5f; teacher_diff at it 9/10/11: %.4f %.4f %.4f"
+          % (first, last, hist[9]["teacher_diff"], hist[10]["teacher_diff"], hist[11]["teacher_diff"]))
+    assert last < first, (first, last)
+    assert hist[0]["teacher_diff"] == 0.0 and hist[9]["teacher_diff"] > hist[1]["teacher_diff"] > 0.0
+    # replicas of the parameters stay finite and actually moved
+    w0 = synth.make_backbone_params(seed=123)["model.layer5.conv2d_list.0.weight"]
+    w1 = m.backbone.model.layer5.conv2d_list[0].weight.detach().cpu()
+    assert torch.isfinite(w1).all() and (w1 - w0).abs().max() > 0
