@@ -111,6 +111,7 @@ def run_reference(args, rank):
 
 
 def main():
+    global GROUP_SIZE, CROP, TFLOP_PER_CROP, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -118,6 +119,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--groups", type=int, default=NUM_GROUPS, help="view-groups per GPU (default: configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # the other BASELINE.json configs (parity-test cases, not the bench line): e.g. configs[3] per-GPU shard
+    # `--arch fcn --groups 4 --group-size 4 --crop 640 640`, configs[4] `--groups 1 --group-size 6 --crop 1024 1024`
+    ap.add_argument("--arch", default="resnet101", choices=["resnet101", "vgg16", "fcn"])
+    ap.add_argument("--group-size", type=int, default=GROUP_SIZE)
+    ap.add_argument("--crop", type=int, nargs=2, default=list(CROP))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-p2p", action="store_true", help="N>1: NCCL all-reduce + SGD instead of the fused peer-memory kernel")
     args = ap.parse_args()
@@ -136,15 +142,26 @@ def main():
     from da_sac_b200.trainer import TargetStepper
 
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    default_cfg = (args.arch, args.group_size, tuple(args.crop)) == ("resnet101", 3, (512, 512))
+    if not default_cfg:
+        GROUP_SIZE, CROP = args.group_size, tuple(args.crop)
+        METRIC = "target-crops/sec (%dx%d, K=%d)" % (CROP[0], CROP[1], GROUP_SIZE)
+        # forward GFLOP per crop from SURVEY.md 8(a)/appendix D (probe of the reference modules), scaled by area otherwise
+        known = {("resnet101", 512): 376.52, ("resnet101", 1024): 1483.27, ("vgg16", 512): 325.55, ("vgg16", 256): 81.39, ("fcn", 640): 346.34}
+        base = {"resnet101": (376.52, 512), "vgg16": (325.55, 512), "fcn": (346.34, 640)}[args.arch]
+        gf = known.get((args.arch, CROP[0])) if CROP[0] == CROP[1] else None
+        TFLOP_PER_CROP = 4e-3 * (gf if gf is not None else base[0] * CROP[0] * CROP[1] / float(base[1] ** 2))
+        args.no_cpu_baseline = True
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.lib()        # fail loudly if the CUDA extension is missing
 
-    cfg = synth.ModelCfg()
+    cfg = {"resnet101": synth.ModelCfg, "vgg16": synth.ModelCfgVGG16, "fcn": synth.ModelCfgFCN}[args.arch]()
     net = get_model(cfg, rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
-    net.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    net.backbone.load_state_dict({"resnet101": lambda: synth.make_backbone_params(seed=123), "vgg16": lambda: synth.make_vgg16_params(seed=321),
+                                  "fcn": lambda: synth.make_fcn_params(seed=213)}[args.arch]())
     net.to(dev).train()
     stepper = TargetStepper(net, cfg, GROUP_SIZE, dev)
     exchange = "none (1 GPU)"
@@ -238,7 +255,7 @@ def main():
     achieved = by[dom][0] / (by[dom][1] * 1e-3) / 1e12
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on its most frequent shape
     # (3x3 d2 256->256, 23 layers x 3 passes), from the committed ncu --set full capture profiles/ncu_gemm_pair_r1k.txt
-    traffic = 106.904832e6 + 62.850816e6 if dom.startswith("conv_gemm_pair") else None
+    traffic = 106.904832e6 + 62.850816e6 if (dom.startswith("conv_gemm_pair") and default_cfg) else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["sustained"], "traffic": traffic,
                 "traffic_note": "bytes per launch on the 3x3 d2 256->256 layer (algorithmic activations in+out 208 MB, weights 2.4 MB); per-launch FLOPs there: 119.6 GFLOP",
@@ -251,7 +268,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 (bf16 hi/lo split operands, fp32 TMEM accumulation; fp32-equivalent)", "data": "synthetic",
-            "config": {"workload": "ResNet-101 DeepLabv2 SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % (args.groups, GROUP_SIZE, CROP[0], CROP[1]),
+            "config": {"workload": "%s SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % ({"resnet101": "ResNet-101 DeepLabv2", "vgg16": "VGG-16 DeepLabv2", "fcn": "VGG-16 FCN-8s"}[args.arch], args.groups, GROUP_SIZE, CROP[0], CROP[1]),
                        "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world, "gradient_exchange": exchange,
                        "l2": "inputs larger than L2 (>20 GB of activations per step)",
                        "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches"},
