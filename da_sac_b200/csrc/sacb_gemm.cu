@@ -292,7 +292,10 @@ SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_sc
   if constexpr (MY_CHUNKS % 2 == 0) {
     // chunk pairs (64 channels = one 128-byte line per row and plane): math per chunk, stores transposed per pair
     const int m_warp0 = m_row0 + quad * 32;
-#pragma unroll
+    // NOT unrolled: one 64-channel piece is ~25 KB of SASS; with both pieces unrolled the epilogue-bound 1x1 layers stalled
+    // on instruction fetch (ncu: no_instruction second only to long_scoreboard).  Rolled: 256->1024 fprop + residual
+    // 281 -> 253 us, 1024->256 dgrad + residual gradient 364 -> 324 us, tensor-bound 3x3 layers unchanged.
+#pragma unroll 1
     for (int jp = 0; jp < MY_CHUNKS / 2; ++jp) {
       uint32_t ph[4][8], pl[4][8];
       {

@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsac_b200.so")
+LIB_PATH = os.environ.get("SACB_LIB") or os.path.join(_HERE, "libsac_b200.so")      # SACB_LIB: A/B runs of two builds
 ABI_VERSION = 3          # SACB_ABI_VERSION in include/sacb.h
 
 

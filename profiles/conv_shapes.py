@@ -51,6 +51,18 @@ def run(d, mode):
     if mode == "fprop":
         L.conv_gemm(d["x"][0], d["x"][1], d["wf"][0], d["wf"][1], s.geom(N), scale=d["sc"], shift=d["sh"], relu=True,
                     out_hi=d["out"][0], out_lo=d["out"][1])
+    elif mode == "fprop_res":      # bottleneck conv3 as it runs in the step: BN affine + residual (split planes) + ReLU
+        if "res" not in d:
+            d["res"] = (rnd(d["M"] * s.Kf), rnd(d["M"] * s.Kf))
+        L.conv_gemm(d["x"][0], d["x"][1], d["wf"][0], d["wf"][1], s.geom(N), scale=d["sc"], shift=d["sh"], relu=True,
+                    add_hi=d["res"][0], add_lo=d["res"][1], out_hi=d["out"][0], out_lo=d["out"][1])
+    elif mode in ("dgrad_cs", "dgrad_res"):   # data gradient as it runs in the step: ReLU mask + d(beta) column sums (+ residual gradient)
+        if "cs" not in d:
+            d["cs"] = torch.zeros(s.C, device=dev)
+            d["gres"] = (rnd(N * s.hout * s.wout * s.C), rnd(N * s.hout * s.wout * s.C))
+        extra = dict(add_hi=d["gres"][0], add_lo=d["gres"][1]) if mode == "dgrad_res" else {}
+        L.conv_gemm(d["g"][0], d["g"][1], d["wt"][0], d["wt"][1], s.geom_dgrad(N), mask_hi=d["mask"], colsum=d["cs"],
+                    out_hi=d["gin"][0], out_lo=d["gin"][1], **extra)
     elif mode == "dgrad":
         L.conv_gemm(d["g"][0], d["g"][1], d["wt"][0], d["wt"][1], s.geom_dgrad(N), mask_hi=d["mask"],
                     out_hi=d["gin"][0], out_lo=d["gin"][1])
@@ -67,6 +79,29 @@ def main():
             flush.zero_()
             run(d, sys.argv[3])
         torch.cuda.synchronize()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "epilogues":
+        # the epilogue variants the real step uses, on the shapes that carry them
+        print("%-28s %-10s %9s %8s" % ("shape", "mode", "us", "TF/s"))
+        for nm, modes in (("model.layer3.1.conv3", ("fprop", "fprop_res", "dgrad", "dgrad_cs")),
+                          ("model.layer3.1.conv1", ("fprop", "dgrad", "dgrad_cs", "dgrad_res")),
+                          ("model.layer3.1.conv2", ("fprop", "dgrad", "dgrad_cs"))):
+            s = net["specs"][nm]
+            d = make(s)
+            fl = 2.0 * d["M"] * s.K * s.C * s.R * s.R
+            for mode in modes:
+                for _ in range(2): run(d, mode)
+                ts = []
+                for _ in range(5):
+                    flush.zero_()
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(); run(d, mode); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                t = sorted(ts)[len(ts) // 2]
+                print("%-28s %-10s %9.1f %8.1f" % ("C%d K%d %dx%d" % (s.C, s.K, s.R, s.R), mode, t * 1e3, fl / (t * 1e-3) / 1e12))
+            del d
+            torch.cuda.empty_cache()
         return
     seen = {}
     for name in net["order"]:
