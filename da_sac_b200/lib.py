@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SACB_LIB") or os.path.join(_HERE, "libsac_b200.so")      # SACB_LIB: A/B runs of two builds
-ABI_VERSION = 3          # SACB_ABI_VERSION in include/sacb.h
+ABI_VERSION = 4          # SACB_ABI_VERSION in include/sacb.h
 
 
 class SacbError(RuntimeError):
@@ -100,7 +100,7 @@ class Loss(C.Structure):
                 ("focal_p", C.c_float),
                 ("losses", _vp), ("scratch", _vp),
                 ("grad_scale", C.c_float),
-                ("dlogits", _vp)]
+                ("dlogits", _vp), ("grad_px", _vp), ("grad_rows", _vp)]
 
 
 class PrepItem(C.Structure):

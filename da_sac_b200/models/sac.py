@@ -209,7 +209,12 @@ class SAC(SAC_Baseline):
             conf_mean = tail["ones"]
         d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), L.ptr(tail["labels"]) if use_labels else None,
                    L.ptr(conf_mean), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
-                   L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits))
+                   L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits), None, None)
+        if dlogits is not None:                         # backward: workspace of the two-stage form
+            if "grad_px" not in tail:
+                tail["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device)
+                tail["grad_rows"] = torch.empty(BT * Cn * H * w, device=logits.device)
+            d.grad_px, d.grad_rows = L.ptr(tail["grad_px"]), L.ptr(tail["grad_rows"])
         return d, keep
 
     # ---------------------------------------------------------------- forward (sac.py:315-378)

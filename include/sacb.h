@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SACB_ABI_VERSION 3
+#define SACB_ABI_VERSION 4
 
 const char* sacb_last_error(void);
 int sacb_abi_version(void);
@@ -238,6 +238,10 @@ typedef struct SacbLoss {
   /* backward */
   float grad_scale;              /* d(total)/d(self_ce), e.g. LR_TARGET */
   float* dlogits;                /* [BT,C,h,w] or NULL */
+  /* optional backward workspace: both non-NULL selects the two-stage backward (per-pixel gradient once, then the
+   * separable adjoint of the upsample) instead of the gather kernel */
+  float* grad_px;                /* [BT,C,H,W] */
+  float* grad_rows;              /* [BT,C,H,w] */
 } SacbLoss;
 int sacb_student_loss_fwd(const SacbLoss* d, void* stream);
 /* dlogits = grad_scale * d(self_ce)/d(logits); with d->labels == NULL: grad_scale * d(loss_ce)/d(logits) (CE against y) */
