@@ -110,6 +110,55 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_cuda(args, rank):
+    """Second baseline of SURVEY.md 8(d): the same reference modules (oracle port = functional restatement of the reference's
+    PyTorch code) executed by stock PyTorch on THIS GPU -- ATen / cuDNN kernels, cudnn.benchmark = True as train.py:40 sets it,
+    TF32 convolutions as PyTorch's default allows -- on the full configs[1] batch.  None of this repo's kernels run here."""
+    if rank != 0:
+        return
+    import torch
+    from da_sac_b200 import synth
+    from oracle import sac_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    cfg = synth.ModelCfg()
+    sd = synth.make_backbone_params(seed=123)
+    student = O.as_leaf_params({k: v.to(dev) for k, v in sd.items()})
+    teacher = {k: v.detach().clone() for k, v in student.items()}
+    optim = torch.optim.SGD(O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
+    rc = torch.full((19,), cfg.THRESHOLD_BETA, device=dev)
+    batch = tuple(t.to(dev) for t in synth.make_target_batch(args.groups, GROUP_SIZE, CROP, seed=0))
+    crops = args.groups * GROUP_SIZE
+
+    def timed(tf32, warm, steps):
+        nonlocal rc
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        for _ in range(warm):
+            _, _, rc = O.sac_target_step(student, teacher, rc, batch, GROUP_SIZE, cfg, optim=optim)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            _, _, rc = O.sac_target_step(student, teacher, rc, batch, GROUP_SIZE, cfg, optim=optim)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"crops_per_s": crops / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": warm}
+
+    r = timed(True, args.warmup, args.steps)
+    line = {"impl": "reference", "device": "cuda", "metric": METRIC, "value": r["crops_per_s"], "unit": "crops/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 convolutions (PyTorch default: cudnn.allow_tf32 = True), fp32 elsewhere",
+            "data": "synthetic",
+            "config": {"workload": "ResNet-101 DeepLabv2 SAC target step, %d groups x K=%d crops %dx%d, stock PyTorch %s + cuDNN %s on the GPU (oracle port of the reference modules, cudnn.benchmark = True)"
+                                   % (args.groups, GROUP_SIZE, CROP[0], CROP[1], torch.__version__, torch.backends.cudnn.version())},
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+    if args.ref_strict_fp32:
+        line["strict_fp32"] = timed(False, 1, max(1, args.steps // 2))
+    print(json.dumps(line), flush=True)
+
+
 def main():
     global GROUP_SIZE, CROP, TFLOP_PER_CROP, METRIC
     ap = argparse.ArgumentParser()
@@ -126,10 +175,15 @@ def main():
     ap.add_argument("--crop", type=int, nargs=2, default=list(CROP))
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-p2p", action="store_true", help="N>1: NCCL all-reduce + SGD instead of the fused peer-memory kernel")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: cpu = the reference arm of the contract; cuda = stock PyTorch/cuDNN on the GPU (second baseline)")
+    ap.add_argument("--ref-strict-fp32", action="store_true", help="--ref-device cuda: also time with cudnn.allow_tf32 = False")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and args.ref_device == "cuda":
+        return run_reference_cuda(args, rank)
     if args.impl == "reference":
         if args.steps > 3: args.steps = 3
         if args.warmup > 1: args.warmup = 1

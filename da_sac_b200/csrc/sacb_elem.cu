@@ -714,13 +714,34 @@ wgrad_finalize_batched_kernel(const SacbFinalizeItem* __restrict__ items, const 
   const float sc = d.scale ? d.scale[k] : 1.f;
   float dot = 0.f;
   const size_t base = (size_t)k * RS * C;
-  for (int i = threadIdx.x; i < RS * C; i += 256) {
-    const int rs = i / C, c = i - rs * C;
-    float g = 0.f;                                   // [split][k][rs][c], summed in split order (deterministic)
-    for (int sp = 0; sp < d.splits; ++sp) g += d.dwraw[(size_t)sp * K * RS * C + base + i];
-    const size_t o = base + (size_t)c * RS + rs;     // [k][c][rs]
-    dot = fmaf(d.w[o], g, dot);
-    d.dw[o] = sc * g;
+  const size_t plane = (size_t)K * RS * C;           // one split's partial sums
+  if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(d.dwraw) & 15) == 0) {
+    // 16-byte reads of the split-K partials (4 consecutive input channels of one tap): this kernel streams ~3.6 GB of
+    // partials per step and was latency-bound with 4-byte loads (31 % of the HBM roofline, profiles/stream_kernels_r1p.txt)
+    for (int i = threadIdx.x * 4; i < RS * C; i += 1024) {
+      const int rs = i / C, c = i - rs * C;
+      const float* src = d.dwraw + base + i;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);    // [split][k][rs][c], summed in split order (deterministic)
+#pragma unroll 4
+      for (int sp = 0; sp < d.splits; ++sp) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)sp * plane);
+        g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      }
+      const size_t o = base + (size_t)c * RS + rs;   // [k][c][rs]
+      dot = fmaf(d.w[o], g.x, dot);              d.dw[o] = sc * g.x;
+      dot = fmaf(d.w[o + RS], g.y, dot);         d.dw[o + RS] = sc * g.y;
+      dot = fmaf(d.w[o + 2 * (size_t)RS], g.z, dot); d.dw[o + 2 * (size_t)RS] = sc * g.z;
+      dot = fmaf(d.w[o + 3 * (size_t)RS], g.w, dot); d.dw[o + 3 * (size_t)RS] = sc * g.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < RS * C; i += 256) {
+      const int rs = i / C, c = i - rs * C;
+      float g = 0.f;
+      for (int sp = 0; sp < d.splits; ++sp) g += d.dwraw[sp * plane + base + i];
+      const size_t o = base + (size_t)c * RS + rs;
+      dot = fmaf(d.w[o], g, dot);
+      d.dw[o] = sc * g;
+    }
   }
   if (d.dgamma) {
     __shared__ float red[8];

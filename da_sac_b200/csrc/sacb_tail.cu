@@ -107,8 +107,24 @@ tail_probs_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
     // sac.py:282 -- zero the probabilities inside augmentation padding (after the class sums, sac.py:278)
     const float keep = (y[(size_t)b * HW + pix] == -1) ? 0.f : 1.f;
     float* dst = probs + ((size_t)b * HW + pix) * CP;
+    if (C == C_ && CP == (C_ + 3) / 4 * 4 && (reinterpret_cast<uintptr_t>(probs) & 15) == 0) {
+      // one 80-byte record per pixel: five 16-byte stores instead of 19 scalar ones at an 80-byte lane stride (the pad
+      // channel is written as 0; nobody reads it)
+      constexpr int V = (C_ + 3) / 4;
+      float4* dst4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-    for (int c = 0; c < C_; ++c) if (c < C) dst[c] = p[c] * keep;
+      for (int v = 0; v < V; ++v) {
+        float4 o;
+        o.x = p[4 * v] * keep;
+        o.y = 4 * v + 1 < C_ ? p[(4 * v + 1) % C_] * keep : 0.f;
+        o.z = 4 * v + 2 < C_ ? p[(4 * v + 2) % C_] * keep : 0.f;
+        o.w = 4 * v + 3 < C_ ? p[(4 * v + 3) % C_] * keep : 0.f;
+        dst4[v] = o;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C_; ++c) if (c < C) dst[c] = p[c] * keep;
+    }
   }
   // deterministic block reduction of the (unmasked) class sums
   __shared__ float red[8][C_];
@@ -683,21 +699,55 @@ __global__ void ema_norm_finalize_kernel(const float* __restrict__ seg_sq, int n
     out[0] = s;
   }
 }
+// One (segment, chunk) per block.  A segment is one parameter tensor (lr / weight decay differ per tensor); the largest
+// (3x3 512->512: 2.4 M elements) used to be walked by 16 blocks with scalar accesses -- 576 dependent round trips per thread,
+// 415 us for the 0.8 GB the step touches (24 % of the HBM roofline, ncu profiles/stream_kernels_r1p.txt).  Now 64 chunks per
+// segment, 16-byte accesses whenever the chunk is aligned: the arithmetic per element is unchanged (bit-identical update).
+constexpr int SGD_CHUNKS = 64;
+SACB_DEVINL void sgd_update(float gv, float pv, float mv, float w, float mu, float l, int first, float& mo, float& po) {
+  float d = gv;
+  if (w != 0.f) d = fmaf(w, pv, d);                          // grad.add(param, alpha=weight_decay)
+  const float buf = first ? d : fmaf(mu, mv, d);             // buf.mul_(momentum).add_(grad)
+  mo = buf;
+  po = pv - l * buf;                                         // param.add_(buf, alpha=-lr)
+}
 __global__ void __launch_bounds__(256)
 sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, const int64_t* __restrict__ offs,
            const float* __restrict__ lr, const float* __restrict__ wd, float mu, int first) {
   const int seg = blockIdx.x;
   const int64_t b0 = offs[2 * seg], b1 = offs[2 * seg + 1];
-  const int64_t per = (b1 - b0 + SEG_CHUNKS - 1) / SEG_CHUNKS;
+  int64_t per = (b1 - b0 + SGD_CHUNKS - 1) / SGD_CHUNKS;
+  per = (per + 3) & ~(int64_t)3;                             // chunk starts stay 16-byte aligned when the segment start is
   const int64_t s0 = b0 + per * blockIdx.y, s1 = min(b1, s0 + per);
+  if (s0 >= s1) return;
   const float l = lr[seg], w = wd[seg];
-  for (int64_t i = s0 + threadIdx.x; i < s1; i += 256) {
-    float d = g[i];
-    const float pv = p[i];
-    if (w != 0.f) d = fmaf(w, pv, d);                        // grad.add(param, alpha=weight_decay)
-    float buf = first ? d : fmaf(mu, mom[i], d);             // buf.mul_(momentum).add_(grad)
-    mom[i] = buf;
-    p[i] = pv - l * buf;                                     // param.add_(buf, alpha=-lr)
+  int64_t i = s0;
+  const bool aligned = (s0 & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mom)) & 15) == 0;
+  if (aligned) {
+    const int64_t n4 = (s1 - s0) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(p + s0);
+    const float4* g4 = reinterpret_cast<const float4*>(g + s0);
+    float4* m4 = reinterpret_cast<float4*>(mom + s0);
+#pragma unroll 2
+    for (int64_t k = threadIdx.x; k < n4; k += 256) {
+      const float4 gv = g4[k], pv = p4[k];
+      const float4 mv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : m4[k];
+      float4 mo, po;
+      sgd_update(gv.x, pv.x, mv.x, w, mu, l, first, mo.x, po.x);
+      sgd_update(gv.y, pv.y, mv.y, w, mu, l, first, mo.y, po.y);
+      sgd_update(gv.z, pv.z, mv.z, w, mu, l, first, mo.z, po.z);
+      sgd_update(gv.w, pv.w, mv.w, w, mu, l, first, mo.w, po.w);
+      m4[k] = mo;
+      p4[k] = po;
+    }
+    i = s0 + (n4 << 2);
+  }
+  for (i += threadIdx.x; i < s1; i += 256) {
+    float mo, po;
+    sgd_update(g[i], p[i], first ? 0.f : mom[i], w, mu, l, first, mo, po);
+    mom[i] = mo;
+    p[i] = po;
   }
 }
 
@@ -847,7 +897,7 @@ extern "C" int sacb_ema_norm(float* slow, const float* fast, const int64_t* seg_
 
 extern "C" int sacb_sgd(float* p, const float* g, float* mom, const int64_t* seg_offsets, const float* seg_lr,
                         const float* seg_wd, int nseg, float momentum, int first_step, void* stream) {
-  sgd_kernel<<<dim3(nseg, SEG_CHUNKS), 256, 0, ST>>>(p, g, mom, seg_offsets, seg_lr, seg_wd, momentum, first_step);
+  sgd_kernel<<<dim3(nseg, SGD_CHUNKS), 256, 0, ST>>>(p, g, mom, seg_offsets, seg_lr, seg_wd, momentum, first_step);
   LAUNCHED();
   return 0;
 }
