@@ -177,6 +177,21 @@ def make_target_batch(num_groups, group_size, crop_hw, seed=0, ignore_rows=8):
     return cat(f1), cat(ys), cat(f2), cat(As), cat(Ais)
 
 
+def make_source_batch(n, crop_hw, seed=0, ignore_rows=8):
+    """``(image, mask)`` of the source loader (what ``Trainer.step`` consumes, /root/reference/train.py:119-125):
+    ``image`` fp32 [n,3,H,W] (smooth noise, like the target frames), ``mask`` int64 [n,H,W] with classes 0..18 in 16x16
+    cells and 255 (ignore) in the last ``ignore_rows`` rows."""
+    H, W = crop_hw
+    g = torch.Generator().manual_seed(1000 + seed)
+    base = torch.randn(n, 3, max(H // 8, 2), max(W // 8, 2), generator=g)
+    img = F.interpolate(base, size=(H, W), mode="bicubic", align_corners=False) + 0.1 * torch.randn(n, 3, H, W, generator=g)
+    cells = torch.randint(0, NUM_CLASSES, (n, (H + 15) // 16, (W + 15) // 16), generator=g)
+    y = cells.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :H, :W].contiguous()
+    if ignore_rows > 0:
+        y[:, H - ignore_rows:, :] = 255
+    return img.contiguous(), y
+
+
 class ModelCfg(object):
     """Hot-path keys of cfg.MODEL (/root/reference/core/config.py:134-159)
     with the values of configs/deeplabv2_resnet101_train.yaml:22-33."""

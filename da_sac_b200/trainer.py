@@ -24,6 +24,20 @@ def shard_groups(num_groups, world_size, rank):
     return list(range(rank * per, (rank + 1) * per))
 
 
+def sync_bn_sums(sums, count, group=None):
+    """Cross-rank part of nn.SyncBatchNorm in the ABN baseline (deeplabv2.py:15,183; train.py:104): the per-channel sums a
+    rank computed over its local batch ([k, C] float64 -- forward: sum z, sum z^2; backward: sum g, sum g*xhat) and its
+    element count are summed over the ranks, so that every rank normalises with the statistics of the GLOBAL batch.
+    torch's SyncBatchNorm all-gathers (mean, invstd, count) per rank and recombines them; summing raw moments is the
+    same statistic in one all-reduce.  In place; returns (sums, total_count).  World size 1: no communication."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        buf = torch.cat([sums.reshape(-1), count.reshape(-1).to(sums.dtype)])
+        dist.all_reduce(buf, group=group)
+        sums.copy_(buf[:-1].view_as(sums))
+        count = buf[-1:].clone()
+    return sums, float(count.reshape(-1)[0])
+
+
 def shard_batch(batch, group_size, world_size, rank):
     """slice a flattened [G*T, ...] target batch to this rank's groups (train.py:186-187 early-out path)"""
     G = batch[0].shape[0] // group_size

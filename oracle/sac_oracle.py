@@ -41,35 +41,58 @@ def _bn_eval(x, p, prefix):
                         p[prefix + ".weight"], p[prefix + ".bias"], False, 0.0, BN_EPS)
 
 
-def _bottleneck(x, p, prefix, stride, dilation, has_ds):
+BN_MOMENTUM = 0.1  # nn.SyncBatchNorm default momentum (deeplabv2.py:15,28: no momentum argument)
+
+
+def bn_train_recorder(new_stats, momentum=BN_MOMENTUM, taps=None):
+    """Training-mode BN of the ABN baseline (models/__init__.py:29: freeze_bn = not cfg.BASELINE, so BaseNet.train()
+    leaves every SyncBatchNorm in training mode, basenet.py:86-100).  Without an initialised process group
+    nn.SyncBatchNorm.forward falls back to F.batch_norm(..., training=True, momentum, eps): batch statistics
+    (biased variance) normalise, the running statistics move by ``momentum`` (unbiased variance).  Returns a
+    ``bn(x, p, prefix)`` callable that leaves ``p`` untouched and records the updated running statistics in
+    ``new_stats`` (functional form of the in-place buffer update)."""
+    def bn(x, p, prefix):
+        rm = p[prefix + ".running_mean"].detach().clone()
+        rv = p[prefix + ".running_var"].detach().clone()
+        if taps is not None:
+            taps[prefix + ".z"] = x
+        out = F.batch_norm(x, rm, rv, p[prefix + ".weight"], p[prefix + ".bias"], True, momentum, BN_EPS)
+        new_stats[prefix + ".running_mean"] = rm
+        new_stats[prefix + ".running_var"] = rv
+        return out
+    return bn
+
+
+def _bottleneck(x, p, prefix, stride, dilation, has_ds, bn=_bn_eval):
     # Bottleneck.forward (deeplabv2.py:77-99); stride sits on conv1 (:59)
     out = F.conv2d(x, p[prefix + ".conv1.weight"], None, stride)
-    out = F.relu(_bn_eval(out, p, prefix + ".bn1"))
+    out = F.relu(bn(out, p, prefix + ".bn1"))
     out = F.conv2d(out, p[prefix + ".conv2.weight"], None, 1, dilation, dilation)
-    out = F.relu(_bn_eval(out, p, prefix + ".bn2"))
+    out = F.relu(bn(out, p, prefix + ".bn2"))
     out = F.conv2d(out, p[prefix + ".conv3.weight"], None, 1)
-    out = _bn_eval(out, p, prefix + ".bn3")
+    out = bn(out, p, prefix + ".bn3")
     if has_ds:
         res = F.conv2d(x, p[prefix + ".downsample.0.weight"], None, stride)
-        res = _bn_eval(res, p, prefix + ".downsample.1")
+        res = bn(res, p, prefix + ".downsample.1")
     else:
         res = x
     return F.relu(out + res)
 
 
-def resnet101_logits(p, x, taps=None):
+def resnet101_logits(p, x, taps=None, bn=_bn_eval):
     """ResNet.forward (deeplabv2.py:160-171). ``p``: state_dict-like mapping with
     keys ``model.*``. Returns logits [n,19,h,w]. ``taps`` (optional dict) gets
-    intermediate activations for layer-wise kernel tests."""
+    intermediate activations for layer-wise kernel tests.  ``bn``: ``_bn_eval`` (frozen BN, the SAC path) or a
+    ``bn_train_recorder`` (ABN baseline)."""
     x = F.conv2d(x, p["model.conv1.weight"], None, 2, 3)
-    x = F.relu(_bn_eval(x, p, "model.bn1"))
+    x = F.relu(bn(x, p, "model.bn1"))
     if taps is not None: taps["stem"] = x
     x = F.max_pool2d(x, 3, 2, 1, ceil_mode=True)          # deeplabv2.py:126
     if taps is not None: taps["pool"] = x
     cfg = ((64, 3, 1, 1), (128, 4, 2, 1), (256, 23, 1, 2), (512, 3, 1, 4))
     for li, (planes, blocks, stride, dil) in enumerate(cfg, start=1):
         for b in range(blocks):
-            x = _bottleneck(x, p, "model.layer%d.%d" % (li, b), stride if b == 0 else 1, dil, b == 0)
+            x = _bottleneck(x, p, "model.layer%d.%d" % (li, b), stride if b == 0 else 1, dil, b == 0, bn)
         if taps is not None: taps["layer%d" % li] = x
     # Classifier_Module.forward (deeplabv2.py:112-116): sum of 4 dilated convs
     out = None
@@ -404,6 +427,55 @@ def sac_target_step(student, teacher, running_conf, batch, T, cfg, optim=None):
     if optim is not None:
         optim.step()
     return losses, outs, rc
+
+
+# --------------------------------------------------------------------------
+# ABN baseline (cfg.MODEL.BASELINE = True): SAC_Baseline (models/sac.py:15-38) around a backbone whose BN layers train
+# --------------------------------------------------------------------------
+
+def baseline_forward(params, x, y=None, taps=None):
+    """SAC_Baseline.forward -> DeepLabV2_ResNet101.forward in train() mode with freeze_bn=False (sac.py:34-35,
+    deeplabv2.py:213-227).  Returns (losses, outs, new_stats); ``new_stats`` holds the running statistics after the
+    forward pass (every BN layer updates them, also under torch.no_grad())."""
+    assert "model.conv1.weight" in params, "the ABN baseline oracle covers the ResNet-101 backbone"
+    new_stats = OrderedDict()
+    logits = resnet101_logits(params, x, taps=taps, bn=bn_train_recorder(new_stats, taps=taps))
+    logits_up = F.interpolate(logits, x.shape[-2:], mode="bilinear", align_corners=True)
+    if y is None:
+        return (logits, logits_up), None, new_stats
+    ce = F.cross_entropy(logits_up, y, ignore_index=255, reduction="none")
+    return {"loss_ce": ce.mean().view(1)}, {"logits_up": logits_up, "logits": logits}, new_stats
+
+
+def commit_bn_stats(params, new_stats):
+    """the in-place buffer update of training-mode BN (+ num_batches_tracked, which the SAC path never reads)"""
+    for k, v in new_stats.items():
+        params[k] = v
+    for k in list(params.keys()):
+        if k.endswith(".num_batches_tracked") and (k[:-len("num_batches_tracked")] + "running_mean") in new_stats:
+            params[k] = params[k] + 1
+
+
+def baseline_source_step(params, x, y, optim=None):
+    """Trainer.step(train=True) in BASELINE mode (train.py:119-138): forward with batch statistics, zero_grad,
+    loss_ce.mean().backward(), optimiser step (immediately: train.py:134-138)."""
+    losses, outs, new_stats = baseline_forward(params, x, y)
+    if optim is not None:
+        optim.zero_grad()
+    losses["loss_ce"].mean().backward()
+    if optim is not None:
+        optim.step()
+    commit_bn_stats(params, new_stats)
+    return losses, outs
+
+
+def baseline_target_pass(params, x, y):
+    """The ABN target pass (train.py:113-115,281-289): ``step(train=False)`` under torch.no_grad() with the net in
+    train() mode -- nothing is learnt, only the BN running statistics absorb the target batch."""
+    with torch.no_grad():
+        losses, outs, new_stats = baseline_forward(params, x, y)
+    commit_bn_stats(params, new_stats)
+    return losses, outs
 
 
 def as_leaf_params(sd):
