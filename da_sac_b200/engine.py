@@ -212,8 +212,11 @@ class WeightPlanes(object):
     BN affine (scale/shift).  Rebuilt from a FlatParams by ``prepare`` (once per optimiser step for the
     student, once per EMA update for the teacher)."""
 
-    def __init__(self, net, device, with_dgrad):
+    def __init__(self, net, device, with_dgrad, fold_bn=True):
         self.net, self.with_dgrad = net, with_dgrad
+        # fold_bn=False (ABN baseline, training-mode BN): the dgrad planes stay un-scaled and scale/shift are filled by the
+        # batch-statistics kernels of engine_abn instead of the running statistics
+        self.fold_bn = fold_bn
         nf = nt = nsc = 0
         self.off = {}
         for name in net["order"]:
@@ -272,7 +275,7 @@ class WeightPlanes(object):
             if s.head:
                 continue
             sc, sh = self.affine(name)
-            bn = s.bn is not None
+            bn = s.bn is not None and self.fold_bn
             planes = s.C != 3
             fh, fl = self.wf(name) if planes else (None, None)
             th, tl = self.wt(name) if (planes and self.with_dgrad) else (None, None)
@@ -850,5 +853,8 @@ class FCN8sEngine(EngineBase):
         self._finalize_all(flat, wp, grad)
 
 
-def make_engine(arch, N, H, W, device):
+def make_engine(arch, N, H, W, device, train_bn=False):
+    if train_bn:
+        from . import engine_abn
+        return engine_abn.make_engine(arch, N, H, W, device)
     return {"resnet101": ResNet101Engine, "vgg16": VGG16Engine, "fcn": FCN8sEngine}[arch](N, H, W, device)

@@ -31,6 +31,9 @@ def lib():
         _lib.sacb_launch_count.restype = C.c_int64
         for f in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):
             getattr(_lib, f).restype = C.c_size_t
+        if hasattr(_lib, "sacb_bn_moments_partial_elems"):
+            _lib.sacb_bn_moments_partial_elems.restype = C.c_size_t
+            _lib.sacb_bn_moments_partial_elems.argtypes = [C.c_int64, C.c_int]
         if _lib.sacb_abi_version() != ABI_VERSION:
             raise SacbError("libsac_b200.so ABI version mismatch")
     return _lib

@@ -86,7 +86,10 @@ class _EngineBackbone(BaseNet):
     """Shared machinery of the B200 backbones: flat fp32 parameter storage, bf16 weight planes, per-shape engines."""
     ARCH = None
 
-    def _init_engine_state(self):
+    def _init_engine_state(self, freeze_bn=True):
+        # freeze_bn=False is the ABN baseline (models/__init__.py:29): BN layers normalise with batch statistics and update
+        # their running statistics while the module is in train() mode (engine_abn.py); eval() uses the frozen-BN engine
+        self._train_bn = not freeze_bn
         self._flat = None
         self._grad = None
         self._wp = None
@@ -157,9 +160,13 @@ class _EngineBackbone(BaseNet):
         """hook for per-forward engine state (FCN dropout masks)"""
         return None
 
+    def _bn_training(self):
+        return self._train_bn and self.training
+
     def _planes(self, with_dgrad):
-        if self._wp is None or self._wp.with_dgrad != with_dgrad:
-            self._wp = E.WeightPlanes(E.build_net(self.ARCH, 64, 64), self._flat.buf.device, with_dgrad)
+        fold = not self._bn_training()
+        if self._wp is None or self._wp.with_dgrad != with_dgrad or self._wp.fold_bn != fold:
+            self._wp = E.WeightPlanes(E.build_net(self.ARCH, 64, 64), self._flat.buf.device, with_dgrad, fold_bn=fold)
             self._wp_version = -1
         if self._wp_version != self._version:
             self._wp.prepare(self._flat)
@@ -167,11 +174,19 @@ class _EngineBackbone(BaseNet):
         return self._wp
 
     def engine(self, N, H, W, shared=None):
-        key = (self.ARCH, N, H, W)
+        train_bn = self._bn_training()
+        key = (self.ARCH, N, H, W) + (("train_bn",) if train_bn else ())
         cache = self._engines if shared is None else shared
         if key not in cache:
-            cache[key] = E.make_engine(self.ARCH, N, H, W, self._flat.buf.device)
+            cache[key] = E.make_engine(self.ARCH, N, H, W, self._flat.buf.device, train_bn=train_bn)
         return cache[key]
+
+    def _after_forward(self):
+        """training-mode BN also counts its batches (nn.BatchNorm2d.num_batches_tracked; unused by momentum=0.1 BN, kept for
+        checkpoint parity)"""
+        if self._bn_training():
+            nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+            torch._foreach_add_(nbt, 1)
 
     # ---------------------------------------------------------------- forward
     def logits(self, im, engines=None, refresh=True):
@@ -184,10 +199,13 @@ class _EngineBackbone(BaseNet):
         if refresh:
             self.mark_dirty()
         if trainable and torch.is_grad_enabled():
-            return _BackboneFn.apply(self, eng, im, *self._params)
+            out = _BackboneFn.apply(self, eng, im, *self._params)
+            self._after_forward()
+            return out
         out = torch.empty(im.shape[0], E.NUM_CLASSES, *eng.net["out_hw"], device=im.device)
         self._pre_forward(eng, im, False)
         eng.forward(self._flat, self._planes(trainable), im, out, keep=False)
+        self._after_forward()
         return out
 
     def forward(self, im, y=None):
@@ -216,7 +234,7 @@ class DeepLabV2_ResNet101(_EngineBackbone):
             self._freeze_bn(self)
         self._from_scratch(self.model.layer5)
         self.criterion = criterion
-        self._init_engine_state()
+        self._init_engine_state(freeze_bn)
 
 
 class DeepLabV2_VGG16(_EngineBackbone):
@@ -249,7 +267,7 @@ class DeepLabV2_VGG16(_EngineBackbone):
         self._from_scratch(self.classifier)
         self._from_scratch(fc6)
         self._from_scratch(fc7)
-        self._init_engine_state()
+        self._init_engine_state(freeze_bn)
 
 
 class _UpsampleFn(torch.autograd.Function):

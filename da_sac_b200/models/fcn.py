@@ -45,7 +45,7 @@ class VGG16_FCN8s(_EngineBackbone):
         self.score_pool3 = nn.Conv2d(256, num_classes, 1)
         self.score_pool3.weight.data.normal_(0, 0.01)
         self._from_scratch(self.score_pool3)
-        self._init_engine_state()
+        self._init_engine_state(freeze_bn)
 
     def _pre_forward(self, eng, x, with_grad):
         """Dropout2d(p) of the head (fcn.py:52,56): active in train mode only; one Bernoulli draw per (sample, channel)"""

@@ -44,7 +44,31 @@ class LazyOuts(dict):
         return [(k, self[k]) for k in self.keys()]
 
 
+class _CELossFn(torch.autograd.Function):
+    """loss_ce = CrossEntropyLoss(ignore_index=255, reduction="none")(upsample(logits), y).mean() (deeplabv2.py:217-224) through
+    the fused loss kernels (``labels == NULL`` mode: plain cross-entropy against ``y``), so that the source step of the ABN
+    baseline (train.py:119-138) never materialises logits_up."""
+
+    @staticmethod
+    def forward(ctx, owner, logits, y):
+        ws = owner._ce_workspace(logits, y)
+        L.check(L.lib().sacb_student_loss_fwd(C.byref(owner._ce_desc(logits, y, ws, 0.0, None)), L.stream()), "sacb_student_loss_fwd")
+        ctx.owner, ctx.logits, ctx.y = owner, logits, y
+        return ws["losses"][0:1].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        dl = torch.empty_like(ctx.logits)
+        ws = ctx.owner._ce_workspace(ctx.logits, ctx.y)
+        L.check(L.lib().sacb_student_loss_bwd(C.byref(ctx.owner._ce_desc(ctx.logits, ctx.y, ws, 1.0, dl)), L.stream()),
+                "sacb_student_loss_bwd")
+        return None, dl * g, None
+
+
 class SAC_Baseline(BaseNet):
+    """models/sac.py:15-38: the backbone alone.  With cfg.BASELINE the backbone's BN layers train (models/__init__.py:29), which
+    the B200 backbones run through engine_abn (batch statistics, running-statistics update, BN backward)."""
+
     def __init__(self, cfg, backbone, rank, **kwargs):
         super().__init__()
         self.backbone = backbone
@@ -52,9 +76,48 @@ class SAC_Baseline(BaseNet):
         self.rank = rank
         if "criterion" in kwargs:
             self.criterion = kwargs["criterion"]
+        self._ce_ws = {}
+
+    def _ce_workspace(self, logits, y):
+        BT, Cn, h, w = logits.shape
+        H, W = y.shape[-2:]
+        key = (BT, h, w, H, W, logits.device)
+        if key not in self._ce_ws:
+            f32 = dict(device=logits.device, dtype=torch.float32)
+            self._ce_ws[key] = dict(losses=torch.empty(2, **f32), scratch=torch.empty(2, device=logits.device, dtype=torch.float64),
+                                    conf_mean=torch.zeros(H, W, **f32), running_conf=torch.zeros(Cn, **f32),
+                                    grad_px=None, grad_rows=None)
+        return self._ce_ws[key]
+
+    def _ce_desc(self, logits, y, ws, grad_scale, dlogits):
+        BT, Cn, h, w = logits.shape
+        H, W = y.shape[-2:]
+        d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), None, L.ptr(ws["conf_mean"]),
+                   L.ptr(ws["running_conf"]), 3.0, L.ptr(ws["losses"]), L.ptr(ws["scratch"]), float(grad_scale), L.ptr(dlogits), None, None)
+        if dlogits is not None:                         # backward: workspace of the two-stage form
+            if ws["grad_px"] is None:
+                ws["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device)
+                ws["grad_rows"] = torch.empty(BT * Cn * H * w, device=logits.device)
+            d.grad_px, d.grad_rows = L.ptr(ws["grad_px"]), L.ptr(ws["grad_rows"])
+        return d
 
     def forward(self, x=None, y=None, x2=None, use_teacher=False, update_teacher=False):
-        return self.backbone(x, y)
+        bb = self.backbone
+        if not hasattr(bb, "ensure_flat"):
+            return bb(x, y)
+        bb.ensure_flat(x.device)
+        H, W = x.shape[-2:]
+        from .deeplabv2 import upsample
+        if y is None:                                                    # (logits, logits_up), deeplabv2.py:219-220
+            with torch.no_grad():
+                logits = bb.logits(x)
+            return logits, upsample(logits, H, W)
+        logits = bb.logits(x)
+        y = y.contiguous()
+        losses = {"loss_ce": _CELossFn.apply(self, logits, y)}           # deeplabv2.py:223-224
+        outs = LazyOuts(logits=logits)
+        outs.lazy("logits_up", lambda: upsample(logits.detach(), H, W))
+        return losses, outs
 
     def parameter_groups(self, base_lr, wd):
         return self.backbone.parameter_groups(base_lr, wd)

@@ -331,6 +331,33 @@ typedef struct SacbAllreduceSgd {
 } SacbAllreduceSgd;
 int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream);
 
+/* ---------------------------------------------------------------- training-mode batch norm (ABN baseline, cfg.MODEL.BASELINE)
+ * Replaces torch.nn.SyncBatchNorm in TRAINING mode (models/deeplabv2.py:15,28-31,60-71,124,149,183; active when
+ * models/__init__.py:29 sets freeze_bn = False) around the same tcgen05 convolutions, run with a raw epilogue:
+ *   forward : z = conv(x);  (sum z, sum z^2) -> [all-reduce over ranks] -> mean, invstd, running-stat update;
+ *             y = relu?((z - mean) * gamma * invstd + beta (+ residual))
+ *   backward: g = dL/dy_pre;  (sum g, sum g * xhat) -> [all-reduce] -> d gamma, d beta (local sums),
+ *             dz = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)),   xhat = (z - mean) * invstd
+ * Planes are bf16 split planes [M][C], C % 8 == 0.  Moments are deterministic: per-block partial sums in double, added in
+ * block order.  `partials` needs sacb_bn_moments_partial_elems(M, C) doubles; `sums` is [2][C] doubles.              */
+size_t sacb_bn_moments_partial_elems(int64_t M, int C);
+/* mode 0: sums = (sum a, sum a^2) with a = z;  mode 1: sums = (sum a, sum a * xhat(z)) with a = g */
+int sacb_bn_moments(const void* a_hi, const void* a_lo, const void* z_hi, const void* z_lo, const float* mean,
+                    const float* invstd, int mode, int64_t M, int C, double* partials, double* sums, void* stream);
+/* count = elements per channel over ALL ranks.  Writes mean, invstd, scale = gamma * invstd and, if running_mean != NULL,
+ * running = (1 - momentum) * running + momentum * batch (unbiased variance), as nn.BatchNorm2d does in training mode. */
+int sacb_bn_train_finalize(const double* sums, double count, const float* gamma, float eps, float momentum,
+                           float* running_mean, float* running_var, float* mean, float* invstd, float* scale, int C,
+                           void* stream);
+int sacb_bn_apply(const void* z_hi, const void* z_lo, const float* mean, const float* scale, const float* beta,
+                  const void* res_hi, const void* res_lo, int relu, void* y_hi, void* y_lo, int64_t M, int C, void* stream);
+/* d gamma / d beta from this rank's sums; coef [3][C] = (gamma * invstd, mean(g), mean(g * xhat)) from the global sums */
+int sacb_bn_bwd_finalize(const double* sums_local, const double* sums_global, double count_global, const float* gamma,
+                         const float* invstd, float* dgamma, float* dbeta, float* coef, int C, void* stream);
+/* may run in place (dz == g) */
+int sacb_bn_bwd_apply(const void* g_hi, const void* g_lo, const void* z_hi, const void* z_lo, const float* mean,
+                      const float* invstd, const float* coef, void* dz_hi, void* dz_lo, int64_t M, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,123 @@
+"""CPU dry run of the host-side layer schedules: every C-ABI call is replaced by a recorder that returns success, tensors live
+on the CPU.  No arithmetic is checked here (that is what the GPU parity tests do) -- this catches what only shows up when the
+Python schedule actually executes: wrong tags in the scratch-plane pools, pool exhaustion, missing keys, argument-count /
+ctypes conversion errors, autograd wiring.  Covers the frozen-BN ResNet-101 engine (the verified SAC path, as a sanity check of
+the harness) and the training-BN engine of the ABN baseline (engine_abn.py)."""
+import collections
+import ctypes as C
+
+import pytest
+import torch
+
+
+class FakeLib(object):
+    def __init__(self):
+        self.calls = collections.Counter()
+
+    def __getattr__(self, name):
+        if not name.startswith("sacb_"):
+            raise AttributeError(name)
+
+        def fn(*args):
+            self.calls[name] += 1
+            for a in args:                                   # every argument must be something ctypes can pass
+                assert a is None or isinstance(a, (int, C._SimpleCData, C.Array, type(C.byref(C.c_int(0))))), (name, type(a))
+            if name == "sacb_bn_moments_partial_elems":
+                M, Cn = args
+                return ((M.value + 511) // 512) * 2 * Cn
+            if name == "sacb_conv_wgrad_splits":
+                return 3
+            if name == "sacb_prep_item_blocks":
+                return 2
+            if name == "sacb_abi_version":
+                return 4
+            if name == "sacb_launch_count":
+                return sum(self.calls.values())
+            if name in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):
+                return 1024
+            return 0
+        return fn
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    from da_sac_b200 import lib as L
+    f = FakeLib()
+    monkeypatch.setattr(L, "lib", lambda: f)
+    monkeypatch.setattr(L, "stream", lambda: C.c_void_p(0))
+    monkeypatch.setattr(L, "ptr", lambda t: None if t is None else C.c_void_p(t.data_ptr()))
+    monkeypatch.setattr(L, "dptr", lambda t: None if t is None else t.data_ptr())
+    return f
+
+
+def _net(baseline):
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+
+    class Cfg(synth.ModelCfg):
+        BASELINE = baseline
+    return get_model(Cfg(), 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none")), Cfg()
+
+
+def test_frozen_bn_engine_schedule_runs(fake):
+    from da_sac_b200 import engine as E
+    net, _ = _net(False)
+    bb = net.backbone
+    bb.train()
+    x = torch.randn(2, 3, 65, 65)
+    logits = bb.logits(x)                                    # student forward through _BackboneFn
+    assert logits.shape == (2, 19, 9, 9) and logits.requires_grad
+    logits.sum().backward()
+    assert all(p.grad is not None for p in bb.parameters())
+    eng = bb.engine(2, 65, 65)
+    assert type(eng) is E.ResNet101Engine
+    assert fake.calls["sacb_conv_gemm"] > 200 and fake.calls["sacb_conv_wgrad"] > 100
+    assert fake.calls["sacb_bn_moments"] == 0                # frozen BN: folded into the GEMM epilogue
+
+
+def test_training_bn_engine_schedule_runs(fake):
+    from da_sac_b200 import engine_abn, synth
+    net, cfg = _net(True)
+    net.train()
+    bb = net.backbone
+    assert bb._bn_training()
+    xs, ys = synth.make_source_batch(2, (65, 65), seed=0)
+    # source step: forward with autograd, fused CE loss, backward
+    losses, outs = net(xs, ys)
+    eng = bb.engine(2, 65, 65)
+    assert type(eng) is engine_abn.ResNet101TrainBNEngine and not bb._wp.fold_bn
+    n_units = len(eng.units)
+    assert n_units == 104                                    # stem + 33 x (conv1, conv2, conv3) + 4 downsample convs
+    assert fake.calls["sacb_bn_moments"] == n_units and fake.calls["sacb_bn_apply"] == n_units
+    assert fake.calls["sacb_bn_train_finalize"] == n_units
+    assert int(bb.model.layer3[5].bn2.num_batches_tracked) == 1
+    losses["loss_ce"].mean().backward()
+    assert fake.calls["sacb_bn_moments"] == 2 * n_units and fake.calls["sacb_bn_bwd_apply"] == n_units
+    assert fake.calls["sacb_bn_bwd_finalize"] == n_units
+    assert fake.calls["sacb_student_loss_fwd"] == 1 and fake.calls["sacb_student_loss_bwd"] == 1
+    assert all(p.grad is not None for p in bb.parameters())
+    assert set(outs.keys()) >= {"logits", "logits_up"}
+    # ABN target pass: no-grad forward in train mode (scratch planes only), statistics kernels still run
+    before = fake.calls["sacb_bn_train_finalize"]
+    with torch.no_grad():
+        losses_t, _ = net(xs, ys)
+    assert fake.calls["sacb_bn_train_finalize"] == before + n_units
+    assert int(bb.model.layer3[5].bn2.num_batches_tracked) == 2
+    # eval: frozen-BN engine, folded planes again
+    net.eval()
+    calls = fake.calls["sacb_bn_moments"]
+    logits, up = net(xs)
+    assert fake.calls["sacb_bn_moments"] == calls and bb._wp.fold_bn
+    assert logits.shape == (2, 19, 9, 9)
+
+
+def test_training_bn_is_refused_for_backbones_without_a_schedule(fake):
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+
+    class Cfg(synth.ModelCfgVGG16):
+        BASELINE = True
+    net = get_model(Cfg(), 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.randn(1, 3, 64, 64), torch.zeros(1, 64, 64, dtype=torch.long))
