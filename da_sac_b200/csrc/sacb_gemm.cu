@@ -178,10 +178,18 @@ SACB_DEVINL void store_plane_transposed(uint16_t* __restrict__ plane, uint32_t (
 
 // DEFER_E < 0: store the planes directly (one row per lane).  DEFER_E = 0/1: write the packed words into pieces
 // [2*DEFER_E, 2*DEFER_E+1] of dh/dl for the line-coalesced (transposed) store done by the caller.
-template <int DEFER_E>
+// STAGED: the residual planes (add_hi / add_lo) of this row were staged in shared memory by TMA (SWIZZLE_128B boxes of
+// [128 rows][64 channels]); rs_hi / rs_lo point at the row's 128-byte line, sw = row & 7 is its swizzle key.
+SACB_DEVINL uint4 lds128(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+template <int DEFER_E, bool STAGED = false>
 SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
                               float* __restrict__ s_colsum, uint32_t (&r)[32], int m, int c0, int lane,
-                              uint32_t (&dh)[4][8], uint32_t (&dl)[4][8]) {
+                              uint32_t (&dh)[4][8], uint32_t (&dl)[4][8], const uint8_t* rs_hi = nullptr,
+                              const uint8_t* rs_lo = nullptr, int sw = 0) {
   const bool valid = m < a.M_total;       // rows past M (last tile) are not loaded / stored but still join the shuffles
   float v[32];
 #pragma unroll
@@ -205,7 +213,19 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
       for (int j = 0; j < 8; ++j) v[8 * i + j] += __uint_as_float(t[j]);
     }
   }
-  if (a.add_hi && valid) {
+  if constexpr (STAGED && DEFER_E >= 0) {
+    // 32 channels = four 16-byte chunks of the row's 128-byte line: chunks 4*DEFER_E .. 4*DEFER_E+3, XOR-swizzled by sw
+    // (rows past M were zero-filled by the TMA unit)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = ((4 * DEFER_E + i) ^ sw) << 4;
+      const uint4 h = lds128(rs_hi + chunk), l = lds128(rs_lo + chunk);
+      float fh[8], fl[8];
+      unpack8(h, fh); unpack8(l, fl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[8 * i + j] += fh[j] + fl[j];
+    }
+  } else if (a.add_hi && valid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       uint32_t h[8], l[8];
@@ -280,10 +300,14 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
 
 // Epilogue of one 128-row x BN-column accumulator tile held in this CTA's TMEM at column `tcol0`.
 // quad = TMEM lane quadrant of the calling warp, half = which half of the column chunks it owns.
-template <int BN>
+// STAGED (pair kernel, residual layers): per 64-channel piece the residual comes from the shared-memory staging buffer
+// `res_buf` ([plane][half][128 rows][64 ch], filled by the residual-producer warp, signalled on res_full); once a warp has
+// read its rows it arrives on res_empty so that the next piece can be fetched while this one is transposed and stored.
+template <int BN, bool STAGED = false>
 SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
                                float* __restrict__ s_colsum, uint32_t tcol0, int m_row0, int n_col0, int quad, int half,
-                               int lane) {
+                               int lane, const uint8_t* res_buf = nullptr, uint64_t* res_full = nullptr,
+                               uint64_t* res_empty = nullptr, uint32_t* res_phase = nullptr) {
   constexpr int CHUNKS = BN / 32;
   constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
   const int m = m_row0 + quad * 32 + lane;
@@ -302,11 +326,25 @@ SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_sc
         const int ch = ch0 + 2 * jp;
         uint32_t r[32];                      // (register budget: 168/thread, so no TMEM-load double buffering here)
         tmem_ld32(tbase + ch * 32, r);
-        tmem_ld_wait();
-        epilogue_row<0>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + ch * 32, lane, ph, pl);
-        tmem_ld32(tbase + (ch + 1) * 32, r);
-        tmem_ld_wait();
-        epilogue_row<1>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + (ch + 1) * 32, lane, ph, pl);
+        if constexpr (STAGED) {
+          const uint8_t* rs_hi = res_buf + half * 16384 + (quad * 32 + lane) * 128;
+          const uint8_t* rs_lo = rs_hi + 32768;
+          mbar_wait(res_full, *res_phase);
+          tmem_ld_wait();
+          epilogue_row<0, true>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + ch * 32, lane, ph, pl, rs_hi, rs_lo, lane & 7);
+          tmem_ld32(tbase + (ch + 1) * 32, r);
+          tmem_ld_wait();
+          epilogue_row<1, true>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + (ch + 1) * 32, lane, ph, pl, rs_hi, rs_lo, lane & 7);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(res_empty);       // this warp's rows of the piece are in registers
+          *res_phase ^= 1;
+        } else {
+          tmem_ld_wait();
+          epilogue_row<0>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + ch * 32, lane, ph, pl);
+          tmem_ld32(tbase + (ch + 1) * 32, r);
+          tmem_ld_wait();
+          epilogue_row<1>(a, s_scale, s_shift, s_colsum, r, m, n_col0 + (ch + 1) * 32, lane, ph, pl);
+        }
       }
       if (a.out_hi) {
         const int c0 = n_col0 + (ch0 + 2 * jp) * 32;
@@ -551,29 +589,44 @@ SACB_DEVINL void tmem2_dealloc(uint32_t addr) {
 }
 
 constexpr int PAIR_BN = 256;              // N of the pair tile; each CTA stages PAIR_BN/2 rows of B
-struct PairCfg {
+// STAGED = the residual-staging variant for the 1x1 expand / reduce layers (short K loops, epilogue-bound): two operand
+// stages instead of three and a 64 KB buffer that TMA fills with the residual planes of the 64-channel piece the epilogue
+// warps work on next ([hi|lo][half][128 rows][64 channels], SWIZZLE_128B), one extra warp issuing those loads.
+constexpr uint32_t RES_BOX_BYTES = BM * 64 * 2;                               // [128 rows][64 channels] bf16
+constexpr uint32_t RES_BYTES = 4 * RES_BOX_BYTES;                             // hi, lo  x  the two column halves of the tile
+template <bool STAGED>
+struct PairCfgT {
   static constexpr uint32_t B_BYTES = (PAIR_BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;         // per CTA
-  static constexpr int STAGES = 3;
+  static constexpr int STAGES = STAGED ? 2 : 3;
   static constexpr int TMEM_COLS = 2 * PAIR_BN;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
+  static constexpr int THREADS = STAGED ? GEMM_THREADS + 32 : GEMM_THREADS;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (STAGED ? RES_BYTES : 0) + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
 };
+using PairCfg = PairCfgT<false>;
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <bool STAGED>
+__global__ void __launch_bounds__(PairCfgT<STAGED>::THREADS, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                      const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                       const GemmArgs a) {
-  using Cfg = PairCfg;
+  using Cfg = PairCfgT<STAGED>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = PAIR_BN;
+  constexpr size_t OPER_BYTES = (size_t)STAGES * Cfg::STAGE_BYTES;
+  constexpr size_t BAR_OFF = OPER_BYTES + (STAGED ? RES_BYTES : 0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES);
+  uint8_t* res_buf = smem + OPER_BYTES;                          // STAGED only (1024-byte aligned: both terms are)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * Cfg::STAGE_BYTES + 256);
+  uint64_t* res_full = tempty_bar + 3;                           // STAGED only (the word after tmem_slot's 8-byte slot)
+  uint64_t* res_empty = res_full + 1;
+  float* s_scale = reinterpret_cast<float*>(smem + BAR_OFF + 256);
   float* s_shift = s_scale + MAX_AFFINE;
   float* s_colsum = s_shift + MAX_AFFINE;
 
@@ -583,16 +636,17 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const bool leader = crank == 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl);
+    if constexpr (STAGED) { prefetch_tmap(&tmRh); prefetch_tmap(&tmRl); }
   }
   // per-channel vectors are staged in shared memory when they fit (N_total <= MAX_AFFINE); wider layers (FCN head, 4096
   // channels) read scale/shift from global memory and accumulate the column sums with global atomics instead
   const bool staged = a.N_total <= MAX_AFFINE;
   if (staged) {
     if (a.scale) {
-      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+      for (int i = threadIdx.x; i < a.N_total; i += Cfg::THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
     }
     if (a.colsum) {
-      for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+      for (int i = threadIdx.x; i < a.N_total; i += Cfg::THREADS) s_colsum[i] = 0.f;
     }
   } else {
     s_scale = const_cast<float*>(a.scale); s_shift = const_cast<float*>(a.shift); s_colsum = a.colsum;
@@ -601,6 +655,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+      if constexpr (STAGED) { mbar_init(res_full, 1); mbar_init(res_empty, EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -681,27 +736,54 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if (!STAGED || warp < 2 + EPI_WARPS) {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM, n_idx * BN,
-                        quad, half, lane);
+      if constexpr (STAGED)
+        epilogue_tile<BN, true>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
+                                n_idx * BN, quad, half, lane, res_buf, res_full, res_empty, &res_phase);
+      else
+        epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM, n_idx * BN,
+                          quad, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);      // the leader issues the MMAs for both CTAs
       acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // STAGED: residual producer (warp 10).  Piece jp of a tile = channels [jp*64, +64) of both 128-channel halves, i.e. what
+    // the eight epilogue warps touch in their jp-th iteration; one buffer, refilled as soon as all of them have read it.
+    if (lane == 0) {
+      uint32_t ph = 0;
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+        const int m0 = m_idx * 2 * BM + crank * BM;
+#pragma unroll 1
+        for (int jp = 0; jp < 2; ++jp) {
+          mbar_wait(res_empty, ph ^ 1);
+          mbar_expect_tx(res_full, RES_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = n_idx * BN + h * (BN / 2) + jp * 64;
+            tma_load_2d(&tmRh, res_full, res_buf + h * RES_BOX_BYTES, c0, m0);
+            tma_load_2d(&tmRl, res_full, res_buf + 2 * RES_BOX_BYTES + h * RES_BOX_BYTES, c0, m0);
+          }
+          ph ^= 1;
+        }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   if (a.colsum && staged) {
-    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
+    for (int i = threadIdx.x; i < a.N_total; i += Cfg::THREADS) {
       const float cs = s_colsum[i];
       if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
     }
@@ -1103,6 +1185,10 @@ static int g_init_status = 0;
 static bool g_cluster = false;
 static bool g_pair = true;            // SACB_PAIR=0 disables the CTA-pair (tcgen05 cta_group::2) 256x256 tile kernels
 static bool g_no_bn256 = false;       // SACB_NO_BN256=1: cap the N tile at 128 (A/B comparison)
+// SACB_EPI_STAGED=1: the 1x1 layers with a residual run the residual-staging variant of the pair kernel (TMA brings the
+// residual planes into shared memory ahead of the epilogue).  Written in round 1 after the GPU budget was spent: compiles,
+// NOT yet run on a B200, therefore off by default.
+static bool g_epi_staged = false;
 
 static void init_once() {
   cudaDriverEntryPointQueryResult q;
@@ -1120,6 +1206,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_CLUSTER")) g_cluster = (e[0] == '1');
   if (const char* e = getenv("SACB_NO_BN256")) g_no_bn256 = (e[0] == '1');
   if (const char* e = getenv("SACB_PAIR")) g_pair = (e[0] != '0');
+  if (const char* e = getenv("SACB_EPI_STAGED")) g_epi_staged = (e[0] == '1');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1183,22 +1270,24 @@ static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   return 0;
 }
 
+template <bool STAGED>
 static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                            const GemmArgs& a, cudaStream_t st) {
+                            const CUtensorMap& rh, const CUtensorMap& rl, const GemmArgs& a, cudaStream_t st) {
+  using Cfg = PairCfgT<STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
   const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
   const int grid = units * 2 < g_num_sms ? units * 2 : (g_num_sms / 2) * 2;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = PairCfg::SMEM; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel, ah, al, bh, bl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED>, ah, al, bh, bl, rh, rl, a));
   g_launches++;
   return 0;
 }
@@ -1288,7 +1377,21 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
-  if (pair) return launch_gemm_pair(ah, al, bh, bl, a, st);
+  if (pair) {
+    // residual-staging variant: short K loops (<= 8 k-blocks: the 1x1 layers up to 512 input channels) whose epilogue adds
+    // split-plane residuals; two operand stages are enough there because the layer is bound by the epilogue's HBM traffic
+    const bool staged = g_epi_staged && d->add_hi && d->add_lo && a.taps * a.kc_blocks <= 8;
+    if (staged) {
+      CUtensorMap rh, rl;
+      cuuint64_t rd[2] = {(cuuint64_t)d->K, (cuuint64_t)a.M_total};
+      cuuint64_t rs[1] = {(cuuint64_t)d->K * 2};
+      cuuint32_t rb[2] = {64, (cuuint32_t)BM};
+      if (int e = make_tiled_map(&rh, d->add_hi, 2, rd, rs, rb)) return e;
+      if (int e = make_tiled_map(&rl, d->add_lo, 2, rd, rs, rb)) return e;
+      return launch_gemm_pair<true>(ah, al, bh, bl, rh, rl, a, st);
+    }
+    return launch_gemm_pair<false>(ah, al, bh, bl, ah, al, a, st);      // tmRh / tmRl are not referenced by this instantiation
+  }
   switch (BN) {
     case 256: return launch_gemm<256, 1>(ah, al, bh, bl, a, st);
     case 128: return CL == 2 ? launch_gemm<128, 2>(ah, al, bh, bl, a, st) : launch_gemm<128, 1>(ah, al, bh, bl, a, st);
