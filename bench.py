@@ -315,15 +315,19 @@ def main():
                 "traffic_note": "bytes per launch on the 3x3 d2 256->256 layer (algorithmic activations in+out 208 MB, weights 2.4 MB); per-launch FLOPs there: 119.6 GFLOP",
                 "launches": by[dom][2],
                 "share_of_step": by[dom][1] / (ms / args.steps),
-                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3 split), so frac <= 1/3 by construction" % pk["src"],
+                "peak_source": "%s bf16 sustained (MEASURED_PEAKS.json); precision mode '%s': in the parity mode the kernel issues 3 bf16 MMAs per algorithmic MAC (bf16x3 split), so frac <= 1/3 by construction" % (pk["src"], L.PRECISION),
                 "step_tensor_frac": value / world * TFLOP_PER_CROP / pk["sustained"],
                 "kernels": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms": v[1], "launches": v[2]} for k, v in by.items()}}
 
     line = {"metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 (bf16 hi/lo split operands, fp32 TMEM accumulation; fp32-equivalent)", "data": "synthetic",
+            "dtype": {"parity": "bf16x3 (bf16 hi/lo split operands, fp32 TMEM accumulation; fp32-equivalent)",
+                      "fast_bwd": "bf16x3 forward (fp32-equivalent logits / pseudo labels), single-pass bf16 gradient GEMMs (SACB_PRECISION=fast_bwd)",
+                      "fast": "bf16 single-pass everywhere, fp32 TMEM accumulation (SACB_PRECISION=fast; NOT the parity mode: logits ~1e-2)"}[L.PRECISION],
+            "data": "synthetic",
             "config": {"workload": "%s SAC target step (teacher fwd + tail + student fwd/bwd + grad all-reduce + SGD), %d groups x K=%d crops %dx%d per GPU" % ({"resnet101": "ResNet-101 DeepLabv2", "vgg16": "VGG-16 DeepLabv2", "fcn": "VGG-16 FCN-8s"}[args.arch], args.groups, GROUP_SIZE, CROP[0], CROP[1]),
                        "global_batch_crops": crops_per_step, "parallelism": "dp%d" % world, "gradient_exchange": exchange,
+                       "precision_mode": L.PRECISION,
                        "l2": "inputs larger than L2 (>20 GB of activations per step)",
                        "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches"},
             "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,

@@ -376,7 +376,8 @@ SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_sc
 // CL = 1: one CTA per output tile.  CL = 2: a cluster of two CTAs works on two adjacent N tiles of the same M tile; the
 // activation (A) tile they share is fetched once -- each CTA loads half of its pixels and TMA-multicasts them into both
 // CTAs' shared memory -- which cuts the L2->SM traffic per MMA from 64 KB to 48 KB per k-block (the binding resource).
-template <int BN, int CL>
+// FAST = SACB_PRECISION_BF16: only the hi planes are fetched and one MMA per k16 step is issued (hi*hi).
+template <int BN, int CL, bool FAST = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)   // 10 warps -> 3 on one SM sub-partition -> at most 168 registers/thread
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -454,18 +455,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
           for (int cb = 0; cb < a.kc_blocks; ++cb) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[ps.stage], Cfg::STAGE_BYTES);
+            mbar_expect_tx(&full_bar[ps.stage], FAST ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
             if constexpr (CL == 1) {
               tma_load_im2col(&tmAh, &full_bar[ps.stage], st, cb * BK, w0, h0, n_img, ow, oh);
-              tma_load_im2col(&tmAl, &full_bar[ps.stage], st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+              if constexpr (!FAST) tma_load_im2col(&tmAl, &full_bar[ps.stage], st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
             } else {
               tma_load_im2col_mc(&tmAh, &full_bar[ps.stage], st + crank * HALF_BYTES, cb * BK, w0, h0, n_img, ow, oh,
                                  (uint16_t)((1u << CL) - 1));
-              tma_load_im2col_mc(&tmAl, &full_bar[ps.stage], st + A_BYTES + crank * HALF_BYTES, cb * BK, w0, h0, n_img, ow, oh,
-                                 (uint16_t)((1u << CL) - 1));
+              if constexpr (!FAST)
+                tma_load_im2col_mc(&tmAl, &full_bar[ps.stage], st + A_BYTES + crank * HALF_BYTES, cb * BK, w0, h0, n_img, ow, oh,
+                                   (uint16_t)((1u << CL) - 1));
             }
             tma_load_3d(&tmBh, &full_bar[ps.stage], st + 2 * A_BYTES, cb * BK, n_idx * BN, tap);
-            tma_load_3d(&tmBl, &full_bar[ps.stage], st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, n_idx * BN, tap);
+            if constexpr (!FAST) tma_load_3d(&tmBl, &full_bar[ps.stage], st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, n_idx * BN, tap);
             ps.advance<STAGES>();
           }
         }
@@ -494,9 +496,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant
             const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 32, 16, 1024);
             const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 32, 16, 1024);
             const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 32, 16, 1024);
-            tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
-            tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
-            tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            if constexpr (FAST) {
+              tc_mma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+            } else {
+              tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+              tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
             accumulate = 1;
           }
           if constexpr (CL == 1) tc_commit(&empty_bar[ps.stage]);
@@ -605,7 +611,7 @@ struct PairCfgT {
 };
 using PairCfg = PairCfgT<false>;
 
-template <bool STAGED>
+template <bool STAGED, bool FAST = false>
 __global__ void __launch_bounds__(PairCfgT<STAGED>::THREADS, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -691,11 +697,11 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
             const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
-            if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * Cfg::STAGE_BYTES);     // bytes of BOTH CTAs
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? Cfg::STAGE_BYTES : 2 * Cfg::STAGE_BYTES);     // bytes of BOTH CTAs
             tma2_load_im2col(&tmAh, lbar, st, cb * BK, w0, h0, n_img, ow, oh);
-            tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            if constexpr (!FAST) tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
             tma2_load_3d(&tmBh, lbar, st + 2 * A_BYTES, cb * BK, brow, tap);
-            tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
+            if constexpr (!FAST) tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
             ps.advance<STAGES>();
           }
         }
@@ -724,9 +730,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
             const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 32, 16, 1024);
             const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 32, 16, 1024);
             const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 32, 16, 1024);
-            tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
-            tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
-            tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            if constexpr (FAST) {
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+            } else {
+              tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
             accumulate = 1;
           }
           tc2_commit_mc(&empty_bar[ps.stage], 0x3);          // frees the stage in both CTAs
@@ -797,7 +807,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
 //   swap=1: rows = input channels (X, im2col map), cols = output channels (G, tiled map)
 // work item = (row tile, col tile, filter tap, K split); results accumulated with fp32 atomics.
 // ------------------------------------------------------------------------------------------------
-template <int BN, int CL>
+template <int BN, int CL, bool FAST = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                   const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
@@ -867,7 +877,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
           mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
           uint64_t* fb = &full_bar[ps.stage];
-          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          mbar_expect_tx(fb, FAST ? Cfg::STAGE_BYTES / 2 : Cfg::STAGE_BYTES);
           uint8_t* sa_hi = st; uint8_t* sa_lo = st + A_BYTES;
           uint8_t* sb_hi = st + 2 * A_BYTES; uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
           constexpr uint16_t MC = (uint16_t)((1u << CL) - 1);
@@ -876,32 +886,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 tma_load_2d(&tmGh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, m0);
-                tma_load_2d(&tmGl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, m0);
+                if constexpr (!FAST) tma_load_2d(&tmGl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, m0);
               }
             } else {
               tma_load_2d_mc(&tmGh, fb, sa_hi + crank * BOX_BYTES, m_idx * BM + crank * 64, m0, MC);
-              tma_load_2d_mc(&tmGl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, m0, MC);
+              if constexpr (!FAST) tma_load_2d_mc(&tmGl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, m0, MC);
             }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
               tma_load_im2col(&tmXh, fb, sb_hi + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
-              tma_load_im2col(&tmXl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
+              if constexpr (!FAST) tma_load_im2col(&tmXl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, w0, h0, n_img, ow, oh);
             }
           } else {
             if constexpr (CL == 1) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 tma_load_im2col(&tmXh, fb, sa_hi + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
-                tma_load_im2col(&tmXl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
+                if constexpr (!FAST) tma_load_im2col(&tmXl, fb, sa_lo + j * BOX_BYTES, m_idx * BM + j * 64, w0, h0, n_img, ow, oh);
               }
             } else {
               tma_load_im2col_mc(&tmXh, fb, sa_hi + crank * BOX_BYTES, m_idx * BM + crank * 64, w0, h0, n_img, ow, oh, MC);
-              tma_load_im2col_mc(&tmXl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, w0, h0, n_img, ow, oh, MC);
+              if constexpr (!FAST) tma_load_im2col_mc(&tmXl, fb, sa_lo + crank * BOX_BYTES, m_idx * BM + crank * 64, w0, h0, n_img, ow, oh, MC);
             }
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
               tma_load_2d(&tmGh, fb, sb_hi + j * BOX_BYTES, n_idx * BN + j * 64, m0);
-              tma_load_2d(&tmGl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, m0);
+              if constexpr (!FAST) tma_load_2d(&tmGl, fb, sb_lo + j * BOX_BYTES, n_idx * BN + j * 64, m0);
             }
           }
           ps.advance<STAGES>();
@@ -935,9 +945,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
             const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 2048, BOX_BYTES, 1024);
             const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 2048, BOX_BYTES, 1024);
             const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 2048, BOX_BYTES, 1024);
-            tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
-            tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
-            tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            if constexpr (FAST) {
+              tc_mma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+            } else {
+              tc_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              tc_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+              tc_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
             accumulate = 1;
           }
           if constexpr (CL == 1) tc_commit(&empty_bar[ps.stage]);
@@ -1007,6 +1021,7 @@ SACB_DEVINL void tma2_load_2d(const CUtensorMap* m, uint32_t bar_addr, void* dst
       : "memory");
 }
 
+template <bool FAST = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
                        const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
@@ -1075,15 +1090,15 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_co
           mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
           const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
-          if (leader) mbar_expect_tx(&full_bar[ps.stage], 2 * Cfg::STAGE_BYTES);
+          if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? Cfg::STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
           uint8_t* sa_hi = st; uint8_t* sa_lo = st + A_BYTES;
           uint8_t* sb_hi = st + 2 * A_BYTES; uint8_t* sb_lo = sb_hi + Cfg::B_BYTES;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             tma2_load_2d(&tmGh, lbar, sa_hi + j * BOX_BYTES, gch + j * 64, m0);
-            tma2_load_2d(&tmGl, lbar, sa_lo + j * BOX_BYTES, gch + j * 64, m0);
+            if constexpr (!FAST) tma2_load_2d(&tmGl, lbar, sa_lo + j * BOX_BYTES, gch + j * 64, m0);
             tma2_load_im2col(&tmXh, lbar, sb_hi + j * BOX_BYTES, xch + j * 64, w0, h0, n_img, ow, oh);
-            tma2_load_im2col(&tmXl, lbar, sb_lo + j * BOX_BYTES, xch + j * 64, w0, h0, n_img, ow, oh);
+            if constexpr (!FAST) tma2_load_im2col(&tmXl, lbar, sb_lo + j * BOX_BYTES, xch + j * 64, w0, h0, n_img, ow, oh);
           }
           ps.advance<STAGES>();
         }
@@ -1114,9 +1129,13 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_co
             const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 2048, BOX_BYTES, 1024);
             const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 2048, BOX_BYTES, 1024);
             const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 2048, BOX_BYTES, 1024);
-            tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
-            tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
-            tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            if constexpr (FAST) {
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+            } else {
+              tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
             accumulate = 1;
           }
           tc2_commit_mc(&empty_bar[ps.stage], 0x3);
@@ -1248,12 +1267,12 @@ static int make_tiled_map(CUtensorMap* m, const void* base, int rank, const cuui
   return 0;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool FAST = false>
 static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                        const GemmArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, CL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TileCfg<BN>::SMEM));
     attr_set = true;
   }
@@ -1265,18 +1284,18 @@ static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL>, ah, al, bh, bl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, CL, FAST>, ah, al, bh, bl, a));
   g_launches++;
   return 0;
 }
 
-template <bool STAGED>
+template <bool STAGED, bool FAST = false>
 static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                             const CUtensorMap& rh, const CUtensorMap& rl, const GemmArgs& a, cudaStream_t st) {
   using Cfg = PairCfgT<STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<STAGED, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
   const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
@@ -1287,16 +1306,17 @@ static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED>, ah, al, bh, bl, rh, rl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED, FAST>, ah, al, bh, bl, rh, rl, a));
   g_launches++;
   return 0;
 }
 
+template <bool FAST>
 static int launch_wgrad_pair(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                              const WgradArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel<FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM));
     attr_set = true;
   }
   const int work = a.m_tiles * a.n_tiles * a.taps * a.splits;
@@ -1307,17 +1327,17 @@ static int launch_wgrad_pair(const CUtensorMap& gh, const CUtensorMap& gl, const
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_pair_kernel, gh, gl, xh, xl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_pair_kernel<FAST>, gh, gl, xh, xl, a));
   g_launches++;
   return 0;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool FAST = false>
 static int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUtensorMap& xh, const CUtensorMap& xl,
                         const WgradArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, CL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TileCfg<BN>::SMEM));
     attr_set = true;
   }
@@ -1329,7 +1349,7 @@ static int launch_wgrad(const CUtensorMap& gh, const CUtensorMap& gl, const CUte
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, CL>, gh, gl, xh, xl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<BN, CL, FAST>, gh, gl, xh, xl, a));
   g_launches++;
   return 0;
 }
@@ -1355,6 +1375,8 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   // cluster of 2 (A tile shared by TMA multicast) whenever there are at least two N tiles to pair up
   const int CL = (BN == 128 && (d->K / BN) % 2 == 0 && g_cluster) ? 2 : 1;
   const bool pair = g_pair && d->K % PAIR_BN == 0;         // CTA-pair (cta_group::2) 256x256 tiles
+  SACB_REQUIRE(d->precision == SACB_PRECISION_BF16X3 || d->precision == SACB_PRECISION_BF16, "sacb_conv_gemm: unknown precision %d", d->precision);
+  const bool fast = d->precision == SACB_PRECISION_BF16;
   CUtensorMap ah, al, bh, bl;
   if (int e = make_im2col_map(&ah, d->x_hi, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
   if (int e = make_im2col_map(&al, d->x_lo, d->N, d->H, d->W, d->C, d->pad, d->R, d->dil, d->stride, BM / CL)) return e;
@@ -1388,9 +1410,18 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
       cuuint32_t rb[2] = {64, (cuuint32_t)BM};
       if (int e = make_tiled_map(&rh, d->add_hi, 2, rd, rs, rb)) return e;
       if (int e = make_tiled_map(&rl, d->add_lo, 2, rd, rs, rb)) return e;
-      return launch_gemm_pair<true>(ah, al, bh, bl, rh, rl, a, st);
+      return fast ? launch_gemm_pair<true, true>(ah, al, bh, bl, rh, rl, a, st) : launch_gemm_pair<true>(ah, al, bh, bl, rh, rl, a, st);
     }
-    return launch_gemm_pair<false>(ah, al, bh, bl, ah, al, a, st);      // tmRh / tmRl are not referenced by this instantiation
+    // tmRh / tmRl are not referenced by these instantiations
+    return fast ? launch_gemm_pair<false, true>(ah, al, bh, bl, ah, al, a, st) : launch_gemm_pair<false>(ah, al, bh, bl, ah, al, a, st);
+  }
+  if (fast) {
+    switch (BN) {
+      case 256: return launch_gemm<256, 1, true>(ah, al, bh, bl, a, st);
+      case 128: return launch_gemm<128, 1, true>(ah, al, bh, bl, a, st);
+      case 64: return launch_gemm<64, 1, true>(ah, al, bh, bl, a, st);
+      default: return launch_gemm<32, 1, true>(ah, al, bh, bl, a, st);
+    }
   }
   switch (BN) {
     case 256: return launch_gemm<256, 1>(ah, al, bh, bl, a, st);
@@ -1453,7 +1484,14 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream) {
   if (int e = make_tiled_map(&gh, d->g_hi, 2, gd, gs, gb)) return e;
   if (int e = make_tiled_map(&gl, d->g_lo, 2, gd, gs, gb)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == -256) return launch_wgrad_pair(gh, gl, xh, xl, a, st);
+  SACB_REQUIRE(d->precision == SACB_PRECISION_BF16X3 || d->precision == SACB_PRECISION_BF16, "sacb_conv_wgrad: unknown precision %d", d->precision);
+  if (d->precision == SACB_PRECISION_BF16) {
+    if (BN == -256) return launch_wgrad_pair<true>(gh, gl, xh, xl, a, st);
+    if (BN == 256) return launch_wgrad<256, 1, true>(gh, gl, xh, xl, a, st);
+    if (BN == 128) return launch_wgrad<128, 1, true>(gh, gl, xh, xl, a, st);
+    return launch_wgrad<64, 1, true>(gh, gl, xh, xl, a, st);
+  }
+  if (BN == -256) return launch_wgrad_pair<false>(gh, gl, xh, xl, a, st);
   const bool pair = (a.n_tiles % 2 == 0) && g_cluster && BN != 256;     // two adjacent column tiles share the row operand
   if (BN == 256) return launch_wgrad<256, 1>(gh, gl, xh, xl, a, st);
   if (BN == 128) return pair ? launch_wgrad<128, 2>(gh, gl, xh, xl, a, st) : launch_wgrad<128, 1>(gh, gl, xh, xl, a, st);

@@ -11,7 +11,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SACB_LIB") or os.path.join(_HERE, "libsac_b200.so")      # SACB_LIB: A/B runs of two builds
-ABI_VERSION = 4          # SACB_ABI_VERSION in include/sacb.h
+ABI_VERSION = 5          # SACB_ABI_VERSION in include/sacb.h
 
 
 class SacbError(RuntimeError):
@@ -72,7 +72,8 @@ class ConvGemm(C.Structure):
                 ("x_hi", _vp), ("x_lo", _vp), ("wt_hi", _vp), ("wt_lo", _vp),
                 ("scale", _vp), ("shift", _vp), ("add_f32", _vp), ("add_hi", _vp), ("add_lo", _vp), ("mask_hi", _vp),
                 ("relu", C.c_int32),
-                ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp), ("colsum", _vp)]
+                ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp), ("colsum", _vp),
+                ("precision", C.c_int32)]
 
 
 class ConvWgrad(C.Structure):
@@ -82,7 +83,7 @@ class ConvWgrad(C.Structure):
                 ("R", C.c_int32), ("S", C.c_int32), ("stride", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
                 ("P", C.c_int32), ("Q", C.c_int32),
                 ("x_hi", _vp), ("x_lo", _vp), ("g_hi", _vp), ("g_lo", _vp), ("dw", _vp),
-                ("splits", C.c_int32)]
+                ("splits", C.c_int32), ("precision", C.c_int32)]
 
 
 class Tail(C.Structure):
@@ -164,6 +165,23 @@ def _prof_wrap(kind, flops, fn):
     return r
 
 
+# Precision policy: "parity" = bf16x3 everywhere (default; what every golden test and the headline bench
+# run), "fast_bwd" = single-pass bf16 for the data / filter gradient GEMMs only, "fast" = single-pass bf16 everywhere.  The
+# engines announce the phase they are in; the wrappers below translate (policy, phase) into the descriptor's precision field.
+PRECISION = os.environ.get("SACB_PRECISION", "parity")
+assert PRECISION in ("parity", "fast_bwd", "fast"), "SACB_PRECISION must be parity, fast_bwd or fast"
+_phase = "fwd"
+
+
+def set_phase(phase):
+    global _phase
+    _phase = phase
+
+
+def _precision():
+    return 1 if (PRECISION == "fast" or (PRECISION == "fast_bwd" and _phase == "bwd")) else 0
+
+
 def conv_out_hw(H, W, R, stride, dil, pad):
     return ((H + 2 * pad - (R - 1) * dil - 1) // stride + 1, (W + 2 * pad - (R - 1) * dil - 1) // stride + 1)
 
@@ -175,7 +193,8 @@ def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift
     P, Q = conv_out_hw(H, W, R, s, d, p)
     desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                     ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
-                    ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw), ptr(colsum))
+                    ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw), ptr(colsum),
+                    _precision())
     # mirrors the dispatch in csrc/sacb_gemm.cu (sacb_conv_gemm)
     pair = os.environ.get("SACB_PAIR", "1") != "0" and K % 256 == 0
     kind = "conv_gemm_pair<256x256>" if pair else "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))
@@ -190,7 +209,7 @@ def conv_wgrad(x_hi, x_lo, g_hi, g_lo, dw, geom, *, k_valid=None, splits=0):
     P, Q = conv_out_hw(H, W, R, s, d, p)
     kv = K if k_valid is None else k_valid
     desc = ConvWgrad(C.sizeof(ConvWgrad), N, H, W, Cc, K, kv, R, R, s, d, p, P, Q,
-                     ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), None, splits)
+                     ptr(x_hi), ptr(x_lo), ptr(g_hi), ptr(g_lo), None, splits, _precision())
     n = lib().sacb_conv_wgrad_splits(C.byref(desc))
     if n <= 0:
         check(n if n < 0 else -1, "sacb_conv_wgrad_splits")

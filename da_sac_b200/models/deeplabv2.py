@@ -78,7 +78,11 @@ class _BackboneFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         net, eng = ctx.net, ctx.eng
         net._select_grad_buffer()
-        eng.backward(net._flat, net._planes(True), ctx.x, dlogits.contiguous(), net._grad)
+        L.set_phase("bwd")                       # precision policy: the gradient GEMMs may run single-pass bf16 (lib.PRECISION)
+        try:
+            eng.backward(net._flat, net._planes(True), ctx.x, dlogits.contiguous(), net._grad)
+        finally:
+            L.set_phase("fwd")
         return (None, None, None) + tuple(net._grad.view(k) for k in net._param_keys)
 
 

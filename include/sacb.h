@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SACB_ABI_VERSION 4
+#define SACB_ABI_VERSION 5
 
 const char* sacb_last_error(void);
 int sacb_abi_version(void);
@@ -49,6 +49,8 @@ int64_t sacb_launch_count(void);
  *   out_hi/out_lo[m*K+k] = split(v); out_f32[m*K+k] = v; out_nchw[((n*k_valid+k)*P+p)*Q+q] = v
  *   colsum[k] += sum_m v                               (if colsum; caller zero-fills; fp32 atomics, one per CTA and k)
  * with m = (n*P + p)*Q + q.                                                          */
+#define SACB_PRECISION_BF16X3 0   /* lo*hi + hi*lo + hi*hi: the parity mode every golden test runs in */
+#define SACB_PRECISION_BF16 1     /* hi*hi only: SURVEY.md's "fast mode", AMP-class accuracy (~1e-2 on logits), reported separately */
 typedef struct SacbConvGemm {
   uint32_t size;              /* sizeof(SacbConvGemm), ABI versioning */
   int32_t N, H, W, C;         /* input NHWC; C % 64 == 0 */
@@ -67,6 +69,8 @@ typedef struct SacbConvGemm {
   float* out_f32;                         /* [M,K] or NULL */
   float* out_nchw;                        /* [N,k_valid,P,Q] or NULL */
   float* colsum;                          /* [K] or NULL: BN d(beta) of the unit that consumes this gradient */
+  int32_t precision;                      /* SACB_PRECISION_*: 0 = bf16x3 split (parity mode, fp32-equivalent), 1 = single-pass
+                                             bf16 on the hi planes only (fast mode; the lo planes are still written) */
 } SacbConvGemm;
 int sacb_conv_gemm(const SacbConvGemm* d, void* stream);
 
@@ -85,6 +89,7 @@ typedef struct SacbConvWgrad {
   const void* g_hi; const void* g_lo;   /* bf16 [N,P,Q,K] */
   float* dw;                            /* fp32 [splits][k_valid][R*S][C] */
   int32_t splits;                       /* requested split-K factor over pixels; 0 = auto */
+  int32_t precision;                    /* as in SacbConvGemm */
 } SacbConvWgrad;
 int sacb_conv_wgrad_splits(const SacbConvWgrad* d);
 int sacb_conv_wgrad(const SacbConvWgrad* d, void* stream);

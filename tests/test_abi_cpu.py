@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header_layout():
     from da_sac_b200 import lib
     # natural alignment on LP64: 14 x int32 then pointers
-    assert ctypes.sizeof(lib.ConvGemm) == 14 * 4 + 10 * 8 + 8 + 5 * 8
+    assert ctypes.sizeof(lib.ConvGemm) == 14 * 4 + 10 * 8 + 8 + 5 * 8 + 8      # ... colsum, precision (+ tail padding)
     assert ctypes.sizeof(lib.ConvWgrad) == 14 * 4 + 5 * 8 + 8
 
 
@@ -35,7 +35,7 @@ def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
     """sizeof + offset of the last field of every descriptor struct: include/sacb.h compiled by gcc vs the ctypes mirrors"""
     import subprocess
     from da_sac_b200 import lib, p2p
-    pairs = [("SacbConvGemm", lib.ConvGemm, "colsum"), ("SacbConvWgrad", lib.ConvWgrad, "splits"), ("SacbTail", lib.Tail, "pool_mode"),
+    pairs = [("SacbConvGemm", lib.ConvGemm, "precision"), ("SacbConvWgrad", lib.ConvWgrad, "precision"), ("SacbTail", lib.Tail, "pool_mode"),
              ("SacbLoss", lib.Loss, "grad_rows"), ("SacbAllreduceSgd", p2p.AllreduceSgd, "first_step")]
     src = tmp_path / "sz.c"
     body = "".join('  printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (c, c, last) for c, _, last in pairs)

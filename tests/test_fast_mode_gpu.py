@@ -1,0 +1,79 @@
+"""Fast precision mode (SACB_PRECISION_BF16: one bf16 MMA per k step on the hi planes; csrc/sacb_gemm.cu, FAST instantiations).
+SURVEY.md section 7 plans two modes: bf16x3 as the parity mode (everything else in tests/ runs in it) and plain bf16 as a fast
+mode that is reported separately.  Checked here at kernel level: the result equals the fp64 convolution of the bf16-ROUNDED
+operands (hi planes) to fp32-accumulation accuracy, for fprop / dgrad-style epilogues and the filter gradient, on the single-CTA
+and the CTA-pair kernels.
+
+Written after round 1's GPU budget was spent: compiles, not yet run on a B200 -> gated behind SACB_RUN_UNVERIFIED=1."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
+                                 reason="fast (single-pass bf16) mode not yet verified on a B200 (set SACB_RUN_UNVERIFIED=1 to run)")]
+
+
+def split(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture
+def fast(monkeypatch):
+    from da_sac_b200 import lib as L
+    monkeypatch.setattr(L, "PRECISION", "fast")
+    return L
+
+
+@pytest.mark.parametrize("geom", [(2, 17, 17, 64, 64, 1, 1, 1, 0), (2, 17, 17, 128, 128, 3, 1, 2, 2), (3, 33, 33, 256, 256, 3, 1, 2, 2),
+                                  (2, 20, 31, 128, 512, 1, 1, 1, 0), (1, 65, 65, 256, 1024, 1, 1, 1, 0)])
+def test_fast_fprop_equals_conv_of_bf16_rounded_operands(fast, geom):
+    L = fast
+    N, H, W, C, K, R, s, d, p = geom
+    torch.manual_seed(0)
+    x = torch.randn(N, C, H, W, device="cuda"); w = torch.randn(K, C, R, R, device="cuda") / (C * R * R) ** 0.5
+    scale = torch.rand(K, device="cuda") + 0.5; shift = torch.randn(K, device="cuda") * 0.1
+    res = torch.randn(N, K, *L.conv_out_hw(H, W, R, s, d, p), device="cuda")
+    xh, xl = split(nhwc(x)); rh, rl = split(nhwc(res))
+    wt = w.permute(2, 3, 0, 1).reshape(R * R, K, C).contiguous(); wh, wl = split(wt)
+    xr = xh.float().permute(0, 3, 1, 2).double(); wr = wh.float().reshape(R, R, K, C).permute(2, 3, 0, 1).double()
+    ref = F.relu(F.conv2d(xr, wr, None, s, p, d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+                 + (rh.float() + rl.float()).double().permute(0, 3, 1, 2))
+    oh = torch.empty(N, ref.shape[2], ref.shape[3], K, device="cuda", dtype=torch.bfloat16); ol = torch.empty_like(oh)
+    L.conv_gemm(xh, xl, wh, wl, geom, scale=scale, shift=shift, add_hi=rh, add_lo=rl, relu=True, out_hi=oh, out_lo=ol)
+    torch.cuda.synchronize()
+    assert relerr((oh.float() + ol.float()).permute(0, 3, 1, 2), ref) < 5e-5
+    # and it is NOT the parity result: the lo planes were ignored
+    full = F.relu(F.conv2d(x.double(), w.double(), None, s, p, d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+                  + res.double())
+    assert relerr((oh.float() + ol.float()).permute(0, 3, 1, 2), full) > 2e-4
+
+
+@pytest.mark.parametrize("geom", [(2, 17, 17, 64, 64, 1, 1, 1, 0), (3, 33, 33, 256, 128, 3, 1, 2, 2), (2, 17, 17, 512, 256, 1, 1, 1, 0),
+                                  (3, 33, 33, 256, 256, 3, 1, 2, 2)])
+def test_fast_wgrad_equals_filter_gradient_of_bf16_rounded_operands(fast, geom):
+    L = fast
+    N, H, W, C, K, R, s, d, p = geom
+    torch.manual_seed(4)
+    x = torch.randn(N, C, H, W, device="cuda"); P, Q = L.conv_out_hw(H, W, R, s, d, p)
+    g = torch.randn(N, K, P, Q, device="cuda")
+    xh, xl = split(nhwc(x)); gh, gl = split(nhwc(g))
+    w = torch.zeros(K, C, R, R, device="cuda", dtype=torch.double, requires_grad=True)
+    F.conv2d(xh.float().permute(0, 3, 1, 2).double(), w, None, s, p, d).backward(gh.float().permute(0, 3, 1, 2).double())
+    ref = w.grad.permute(0, 2, 3, 1).reshape(K, R * R, C)
+    parts, n = L.conv_wgrad(xh, xl, gh, gl, lambda m: torch.full((m,), float("nan"), device="cuda"), geom)
+    torch.cuda.synchronize()
+    dw = parts[:n * K * R * R * C].view(n, K, R * R, C).sum(0)
+    assert relerr(dw, ref) < 2e-5

@@ -47,6 +47,7 @@ def fake(monkeypatch):
     monkeypatch.setattr(L, "stream", lambda: C.c_void_p(0))
     monkeypatch.setattr(L, "ptr", lambda t: None if t is None else C.c_void_p(t.data_ptr()))
     monkeypatch.setattr(L, "dptr", lambda t: None if t is None else t.data_ptr())
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)     # no CUDA runtime in the CPU container
     return f
 
 
@@ -121,3 +122,28 @@ def test_training_bn_is_refused_for_backbones_without_a_schedule(fake):
     net.train()
     with pytest.raises(NotImplementedError):
         net(torch.randn(1, 3, 64, 64), torch.zeros(1, 64, 64, dtype=torch.long))
+
+
+@pytest.mark.parametrize("arch", ["resnet101", "vgg16", "fcn"])
+def test_full_sac_target_step_schedule_runs(fake, arch):
+    """SAC.forward (EMA / teacher forward / tail / student forward / fused loss) + backward for every backbone: the verified
+    default path, exercised here so that host-side edits to it are caught without a GPU"""
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    cfg = {"resnet101": synth.ModelCfg, "vgg16": synth.ModelCfgVGG16, "fcn": synth.ModelCfgFCN}[arch]()
+    net = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    net.train()
+    assert not net.backbone._bn_training() and not net.slow_net._bn_training()
+    K, HW = 2, (64, 64)
+    x, y, x2, A, Ai = synth.make_target_batch(1, K, HW, seed=0)
+    for step in range(2):
+        losses, outs = net(x.clone(), y.clone(), x2.clone(), A, Ai, use_teacher=True, update_teacher=(step == 0), T=K)
+        assert set(losses) >= {"loss_ce", "self_ce", "teacher_diff"}
+        net.zero_grad()
+        (cfg.LR_TARGET * losses["self_ce"].mean()).backward()
+        assert all(p.grad is not None for p in net.backbone.parameters())
+    assert fake.calls["sacb_teacher_tail"] == 2 and fake.calls["sacb_student_loss_bwd"] == 2
+    assert fake.calls["sacb_bn_moments"] == 0 and net.backbone._wp.fold_bn
+    # source pass of the joint recipe (train.py:119-138 with BASELINE = False): loss_ce backward
+    losses, _ = net(x.clone(), torch.zeros_like(y))
+    losses["loss_ce"].mean().backward()
