@@ -8,6 +8,7 @@ forward/backward and the whole pseudo-label tail run as a fixed schedule of sm_1
 [BT,19,H,W] tensors of the reference (logits_up, teacher_refined, ...) are only materialised when a caller
 actually reads them from ``net_outs``."""
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -15,6 +16,9 @@ import torch.distributed as dist
 from .basenet import BaseNet
 from .. import engine as E
 from .. import lib as L
+
+
+_TWO_STREAM = os.environ.get("SACB_TWO_STREAM", "0") == "1"
 
 
 class LazyOuts(dict):
@@ -166,6 +170,7 @@ class SAC(SAC_Baseline):
             p.requires_grad = False
         self.register_buffer("slow_init", torch.Tensor([False]))
         self._engines = {}
+        self._engines_teacher = {}       # only used with SACB_TWO_STREAM=1
         self._ws = {}
         self._seg = None
 
@@ -300,12 +305,28 @@ class SAC(SAC_Baseline):
         if update_teacher:
             losses["teacher_diff"] = self._momentum_update(True)         # sac.py:342-344
         tail = None
+        # SACB_TWO_STREAM=1 (written in round 1, not yet run on a GPU -> off by default): the teacher forward + tail and the
+        # student forward are independent until the loss, so they are issued on two streams.  Every GEMM is a persistent
+        # kernel that owns all SMs, but its last partial wave (5.36 waves on the 256-channel layers) and the launch gaps leave
+        # SMs idle that the other stream's next kernel can take.  The teacher then needs its own engine (im2col matrix, ASPP
+        # scratch and plane pools are per engine).
+        two_stream = use_teacher and _TWO_STREAM and x.is_cuda
+        side = None
         if use_teacher:
             self.slow_net.eval()
-            with torch.no_grad():                                        # sac.py:348-350
-                t_logits = self.slow_net.logits(x2, self._engines, refresh=False)
-            tail = self._tail(t_logits, y_raw, affine, affine_inv, T)   # sac.py:353-357
+            if two_stream:
+                side = self._side_stream = getattr(self, "_side_stream", None) or torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())           # EMA / inputs are ordered before the fork
+                with torch.cuda.stream(side), torch.no_grad():
+                    t_logits = self.slow_net.logits(x2, self._engines_teacher, refresh=False)
+                    tail = self._tail(t_logits, y_raw, affine, affine_inv, T)
+            else:
+                with torch.no_grad():                                    # sac.py:348-350
+                    t_logits = self.slow_net.logits(x2, self._engines, refresh=False)
+                tail = self._tail(t_logits, y_raw, affine, affine_inv, T)   # sac.py:353-357
         s_logits = self.backbone.logits(x, self._engines, refresh=True)  # sac.py:340
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)               # join: the loss reads the pseudo labels
         if tail is None:
             BT = x.shape[0]
             tail = self._workspace(BT, 1, H, W, dev)
