@@ -47,6 +47,7 @@ struct GemmArgs {
   int relu;
   uint16_t* out_hi; uint16_t* out_lo; float* out_f32; float* out_nchw;
   float* colsum;      // optional [N_total]: += column sums of the final values (BN d(beta) of the producer unit)
+  int split_from;     // pair kernel, TSPLIT instantiation: tiles >= split_from are processed as two 256 x 128 halves
 };
 
 struct WgradArgs {
@@ -611,7 +612,10 @@ struct PairCfgT {
 };
 using PairCfg = PairCfgT<false>;
 
-template <bool STAGED, bool FAST = false>
+// TSPLIT (SACB_TAIL_SPLIT=1, written in round 1, not yet run): the tiles of the last, partial wave are cut into two
+// 256 x 128 halves (MMA N = 128; each CTA feeds 64 of the B rows it loads) so that twice as many clusters share that wave:
+// 397 tiles on 74 clusters = 5 full waves + 27 tiles -> 54 half tiles in one wave of about half the length.
+template <bool STAGED, bool FAST = false, bool TSPLIT = false>
 __global__ void __launch_bounds__(PairCfgT<STAGED>::THREADS, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -676,20 +680,35 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   const int unit0 = (int)cluster_id_x(), unit_step = (int)cluster_count_x();
   const int m_pairs = (a.M_total + 2 * BM - 1) / (2 * BM);
   const int n_tiles = a.N_total / BN;
-  const int total_units = m_pairs * n_tiles;
+  static_assert(!(STAGED && TSPLIT), "the tail split is implemented for the plain epilogue");
+  // work items: tiles, then (TSPLIT) the half tiles of the last partial wave
+  const int total_units = TSPLIT ? a.split_from + 2 * (m_pairs * n_tiles - a.split_from) : m_pairs * n_tiles;
+  // item -> (tile, which half); without TSPLIT an item is a tile
+  auto decode = [&](int item, int& tile, int& hh) -> bool {
+    tile = item; hh = 0;
+    if constexpr (TSPLIT) {
+      if (item >= a.split_from) { const int t = item - a.split_from; tile = a.split_from + (t >> 1); hh = t & 1; return true; }
+    }
+    return false;
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       PipeState ps{0, 0};
       const int pq = a.P * a.Q;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
-        const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+        int tile = unit, hh = 0;
+        bool is_half = false;
+        if constexpr (TSPLIT) is_half = decode(unit, tile, hh);
+        const int m_idx = tile / n_tiles, n_idx = tile - m_idx * n_tiles;
         const int m0 = m_idx * 2 * BM + crank * BM;            // this CTA's 128 rows of the 256-row tile
         const int n_img = m0 / pq;
         const int rem = m0 - n_img * pq;
         const int p = rem / a.Q, q = rem - p * a.Q;
         const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
-        const int brow = n_idx * BN + crank * (BN / 2);        // this CTA's half of the B rows
+        int brow = n_idx * BN + crank * (BN / 2);              // this CTA's half of the B rows
+        // half tile: 64 of the 128 rows the box brings are used by the N = 128 MMA
+        if constexpr (TSPLIT) { if (is_half) brow = n_idx * BN + hh * (BN / 2) + crank * (BN / 4); }
         for (int tap = 0; tap < a.taps; ++tap) {
           const int r = tap / a.S, s = tap - r * a.S;
           const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
@@ -711,8 +730,11 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     if (leader && lane == 0) {
       PipeState ps{0, 0};
       int acc = 0; uint32_t acc_phase = 0;
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc_half = make_idesc_bf16(2 * BM, BN / 2, 0, 0);
       for (int unit = unit0; unit < total_units; unit += unit_step) {
+        uint32_t idesc = idesc_full;
+        if constexpr (TSPLIT) { int tile, hh; if (decode(unit, tile, hh)) idesc = idesc_half; }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -752,12 +774,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
-      const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+      int tile = unit, hh = 0;
+      bool is_half = false;
+      if constexpr (TSPLIT) is_half = decode(unit, tile, hh);
+      const int m_idx = tile / n_tiles, n_idx = tile - m_idx * n_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if constexpr (STAGED)
         epilogue_tile<BN, true>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
                                 n_idx * BN, quad, half, lane, res_buf, res_full, res_empty, &res_phase);
+      else if (TSPLIT && is_half)
+        epilogue_tile<BN / 2>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
+                              n_idx * BN + hh * (BN / 2), quad, half, lane);
       else
         epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM, n_idx * BN,
                           quad, half, lane);
@@ -1208,6 +1236,8 @@ static bool g_no_bn256 = false;       // SACB_NO_BN256=1: cap the N tile at 128 
 // residual planes into shared memory ahead of the epilogue).  Written in round 1 after the GPU budget was spent: compiles,
 // NOT yet run on a B200, therefore off by default.
 static bool g_epi_staged = false;
+// SACB_TAIL_SPLIT=1: half tiles in the last partial wave of the pair kernel (conv_gemm_pair_kernel<.., .., true>); also unverified
+static bool g_tail_split = false;
 
 static void init_once() {
   cudaDriverEntryPointQueryResult q;
@@ -1226,6 +1256,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_NO_BN256")) g_no_bn256 = (e[0] == '1');
   if (const char* e = getenv("SACB_PAIR")) g_pair = (e[0] != '0');
   if (const char* e = getenv("SACB_EPI_STAGED")) g_epi_staged = (e[0] == '1');
+  if (const char* e = getenv("SACB_TAIL_SPLIT")) g_tail_split = (e[0] == '1');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1289,13 +1320,13 @@ static int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUten
   return 0;
 }
 
-template <bool STAGED, bool FAST = false>
+template <bool STAGED, bool FAST = false, bool TSPLIT = false>
 static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                             const CUtensorMap& rh, const CUtensorMap& rl, const GemmArgs& a, cudaStream_t st) {
   using Cfg = PairCfgT<STAGED>;
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<STAGED, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<STAGED, FAST, TSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr_set = true;
   }
   const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
@@ -1306,7 +1337,7 @@ static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED, FAST>, ah, al, bh, bl, rh, rl, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED, FAST, TSPLIT>, ah, al, bh, bl, rh, rl, a));
   g_launches++;
   return 0;
 }
@@ -1396,6 +1427,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.relu = d->relu;
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
   a.colsum = d->colsum;
+  a.split_from = 0;
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1411,6 +1443,17 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
       if (int e = make_tiled_map(&rh, d->add_hi, 2, rd, rs, rb)) return e;
       if (int e = make_tiled_map(&rl, d->add_lo, 2, rd, rs, rb)) return e;
       return fast ? launch_gemm_pair<true, true>(ah, al, bh, bl, rh, rl, a, st) : launch_gemm_pair<true>(ah, al, bh, bl, rh, rl, a, st);
+    }
+    // tail split: worth it when the last wave is at most half full (then all its half tiles still fit in one wave)
+    if (g_tail_split) {
+      const int clusters = g_num_sms / 2;
+      const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
+      const int rem = units % clusters;
+      if (units > clusters && rem > 0 && 2 * rem <= clusters) {
+        a.split_from = units - rem;
+        return fast ? launch_gemm_pair<false, true, true>(ah, al, bh, bl, ah, al, a, st)
+                    : launch_gemm_pair<false, false, true>(ah, al, bh, bl, ah, al, a, st);
+      }
     }
     // tmRh / tmRl are not referenced by these instantiations
     return fast ? launch_gemm_pair<false, true>(ah, al, bh, bl, ah, al, a, st) : launch_gemm_pair<false>(ah, al, bh, bl, ah, al, a, st);

@@ -32,7 +32,7 @@ def funcs(obj):
 
 def norm(name):
     """map an instantiation of the working tree to the name it had in the verified commit (template bools added since)"""
-    n = re.sub(r"conv_gemm_pair_kernel(ILb0ELb0EEEv|E)14CUtensorMap_st(S\d_)+NS_8GemmArgsE", "conv_gemm_pair_kernel<default>", name)
+    n = re.sub(r"conv_gemm_pair_kernel(I(Lb0E)+EEv|E)14CUtensorMap_st(S\d_)+NS_8GemmArgsE", "conv_gemm_pair_kernel<default>", name)
     n = re.sub(r"conv_wgrad_pair_kernel(ILb0EEEv|E)14CUtensorMap_st(S\d_)+NS_9WgradArgsE", "conv_wgrad_pair_kernel<default>", n)
     return re.sub(r"(conv_(gemm|wgrad)_kernelILi\d+ELi\d+E)Lb0E", r"\1", n)
 
