@@ -30,6 +30,7 @@ struct P2PArgs {
   float* grads[P2P_MAXW];
   float* params[P2P_MAXW];
   uint32_t* flags[P2P_MAXW];
+  float* mc_grads; float* mc_params;     // NVLS instantiation: multicast mappings of the same gradient / parameter buffers
   float* mom;
   const int64_t* seg_ranges; const float* seg_lr; const float* seg_wd;
   int nseg, world, rank, first;
@@ -53,6 +54,17 @@ SACB_DEVINL float4 ld_peer_f4(const float* p) {       // relaxed system-scope lo
 SACB_DEVINL void st_peer_f4(float* p, const float4& v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// NVLS (NVLink SHARP): one multimem.ld_reduce returns the sum of the W replicas of an address -- the NVSwitch does the adds --
+// and one multimem.st writes all W replicas, so a rank moves 1/W of the buffer once in each direction instead of W times.
+SACB_DEVINL float4 multimem_ld_reduce_add_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+SACB_DEVINL void multimem_st_f4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 SACB_DEVINL void spin_until(const uint32_t* flag, uint32_t epoch) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
@@ -61,6 +73,7 @@ SACB_DEVINL void spin_until(const uint32_t* flag, uint32_t epoch) {
   }
 }
 
+template <bool NVLS>
 __global__ void __launch_bounds__(512)
 allreduce_sgd_kernel(const P2PArgs a) {
   extern __shared__ int64_t s_seg[];                  // [2*nseg] segment table (begin, end), sorted by begin
@@ -91,11 +104,15 @@ allreduce_sgd_kernel(const P2PArgs a) {
     const int64_t end = s_seg[2 * seg + 1];
     if (i0 >= end) continue;                         // BN running statistics / padding: not an optimiser tensor
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (NVLS) {
+      g = multimem_ld_reduce_add_f4(a.mc_grads + i0);            // sum over the ranks, reduced inside the switch
+    } else {
 #pragma unroll
-    for (int p = 0; p < P2P_MAXW; ++p) {
-      if (p < a.world) {
-        const float4 t = ld_peer_f4(a.grads[p] + i0);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      for (int p = 0; p < P2P_MAXW; ++p) {
+        if (p < a.world) {
+          const float4 t = ld_peer_f4(a.grads[p] + i0);
+          g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
       }
     }
     const float l = a.seg_lr[seg], w = a.seg_wd[seg];
@@ -115,9 +132,13 @@ allreduce_sgd_kernel(const P2PArgs a) {
     }
     *reinterpret_cast<float4*>(a.mom + i0) = make_float4(mm[0], mm[1], mm[2], mm[3]);
     const float4 nv = make_float4(out[0], out[1], out[2], out[3]);
+    if constexpr (NVLS) {
+      multimem_st_f4(a.mc_params + i0, nv);                      // lands in every rank's parameter buffer
+    } else {
 #pragma unroll
-    for (int p = 0; p < P2P_MAXW; ++p)
-      if (p < a.world) st_peer_f4(a.params[p] + i0, nv);
+      for (int p = 0; p < P2P_MAXW; ++p)
+        if (p < a.world) st_peer_f4(a.params[p] + i0, nv);
+    }
   }
 
   // ---- done: the last block of this rank tells every peer, then waits until every peer's slice has landed here
@@ -183,6 +204,8 @@ extern "C" int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream) {
     a.flags[p] = p < d->world ? d->flags[p] : nullptr;
     SACB_REQUIRE(p >= d->world || (a.grads[p] && a.params[p] && a.flags[p]), "sacb_allreduce_sgd: NULL peer pointer");
   }
+  a.mc_grads = d->mc_grads; a.mc_params = d->mc_params;
+  SACB_REQUIRE((d->mc_grads == nullptr) == (d->mc_params == nullptr), "sacb_allreduce_sgd: mc_grads and mc_params go together");
   a.mom = d->mom; a.seg_ranges = d->seg_ranges; a.seg_lr = d->seg_lr; a.seg_wd = d->seg_wd;
   a.nseg = d->nseg; a.world = d->world; a.rank = d->rank; a.first = d->first_step;
   const long long nvec = d->n / 4, per = (nvec + d->world - 1) / d->world;
@@ -195,10 +218,12 @@ extern "C" int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream) {
   const size_t smem = sizeof(int64_t) * 2 * d->nseg;
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(allreduce_sgd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(allreduce_sgd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(allreduce_sgd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  allreduce_sgd_kernel<<<2 * sms, 512, smem, ST>>>(a);
+  if (a.mc_grads) allreduce_sgd_kernel<true><<<2 * sms, 512, smem, ST>>>(a);
+  else allreduce_sgd_kernel<false><<<2 * sms, 512, smem, ST>>>(a);
   g_launches++;
   SACB_CHECK_CUDA(cudaGetLastError());
   return 0;

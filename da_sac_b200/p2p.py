@@ -26,7 +26,8 @@ class AllreduceSgd(C.Structure):
     _fields_ = [("size", C.c_uint32), ("world", C.c_int32), ("rank", C.c_int32),
                 ("grads", C.c_void_p), ("params", C.c_void_p), ("flags", C.c_void_p),
                 ("mom", C.c_void_p), ("seg_ranges", C.c_void_p), ("seg_lr", C.c_void_p), ("seg_wd", C.c_void_p),
-                ("nseg", C.c_int32), ("n", C.c_int64), ("momentum", C.c_float), ("first_step", C.c_int32)]
+                ("nseg", C.c_int32), ("n", C.c_int64), ("momentum", C.c_float), ("first_step", C.c_int32),
+                ("mc_grads", C.c_void_p), ("mc_params", C.c_void_p)]
 
 
 class SymmBuffer(object):
@@ -65,18 +66,56 @@ def _import(handle, device):
     return p.value
 
 
+class TorchSymmBuffer(object):
+    """NVLS variant: the buffer comes from torch.distributed._symmetric_memory (CUDA VMM allocation bound to a multicast
+    object by ``rendezvous``), which provides the peers' unicast pointers AND the multicast pointer; torch is the plumbing
+    here exactly as it is for process groups.  Same duck type as SymmBuffer where P2PContext needs it."""
+
+    def __init__(self, numel, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.device = torch.device(device)
+        try:                                          # older torch versions want the group enabled explicitly
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.t = symm_mem.empty(int(numel), dtype=torch.float32, device=self.device)
+        self.t.zero_()
+        self.hdl = symm_mem.rendezvous(self.t, group)
+        self.ptr = self.t.data_ptr()
+        if not int(self.hdl.multicast_ptr):
+            raise L.SacbError("torch symmetric memory reports no multicast (NVLS) support on this system")
+
+    def tensor(self, dtype, numel):
+        assert dtype == torch.float32 and numel <= self.t.numel()
+        return self.t[:numel]
+
+    def peer_ptrs(self):
+        return [int(p) for p in self.hdl.buffer_ptrs]
+
+    def multicast_ptr(self):
+        return int(self.hdl.multicast_ptr)
+
+
 class P2PContext(object):
-    def __init__(self, backbone, world, rank, device):
+    def __init__(self, backbone, world, rank, device, nvls=False):
         assert 1 <= world <= MAX_WORLD, "sacb_allreduce_sgd supports up to %d ranks (one NVSwitch domain)" % MAX_WORLD
         self.world, self.rank, self.device = world, rank, torch.device(device)
         self.backbone = backbone
+        self.nvls = bool(nvls) and world > 1
         lib = L.lib()
         flat = backbone.ensure_flat(self.device)
         n = flat.total
         assert n % 4 == 0
         self.n = n
-        self._bufs = dict(params=SymmBuffer(4 * n, device), grads=SymmBuffer(4 * n, device),
-                          flags=SymmBuffer(4 * lib.sacb_p2p_flag_words(), device))
+        if self.nvls:
+            # SACB_NVLS=1 (written in round 1, not yet run on a multi-GPU box): multimem.ld_reduce / multimem.st through the
+            # NVSwitch instead of W peer loads / W peer stores per element
+            grp = dist.group.WORLD
+            self._bufs = dict(params=TorchSymmBuffer(n, device, grp), grads=TorchSymmBuffer(n, device, grp),
+                              flags=SymmBuffer(4 * lib.sacb_p2p_flag_words(), device))
+        else:
+            self._bufs = dict(params=SymmBuffer(4 * n, device), grads=SymmBuffer(4 * n, device),
+                              flags=SymmBuffer(4 * lib.sacb_p2p_flag_words(), device))
         # ---- re-home the flat buffers (parameter objects keep their identity; values are carried over)
         p_sym = self._bufs["params"].tensor(torch.float32, n)
         p_sym.copy_(flat.buf)
@@ -91,18 +130,22 @@ class P2PContext(object):
         backbone.mark_dirty()
         torch.cuda.synchronize(self.device)
         # ---- exchange IPC handles, map the peers
-        mine = {k: b.handle() for k, b in self._bufs.items()}
+        mine = {k: b.handle() for k, b in self._bufs.items() if isinstance(b, SymmBuffer)}
         if world > 1:
             allh = [None] * world
             dist.all_gather_object(allh, mine)
         else:
             allh = [mine]
-        self._ptrs = {k: [] for k in mine}
+        self._ptrs = {k: [] for k in self._bufs}
         err = None
         try:
             for r in range(world):
                 for k in mine:
                     self._ptrs[k].append(self._bufs[k].ptr if r == rank else _import(allh[r][k], self.device))
+            for k, b in self._bufs.items():     # NVLS: torch's rendezvous already mapped the peers
+                if isinstance(b, TorchSymmBuffer):
+                    self._ptrs[k] = b.peer_ptrs()
+                    assert len(self._ptrs[k]) == world and self._ptrs[k][rank] == b.ptr
         except L.SacbError as e:                # e.g. no peer access between two GPUs
             err = e
         if world > 1:
@@ -124,5 +167,7 @@ class P2PContext(object):
         d = AllreduceSgd(C.sizeof(AllreduceSgd), self.world, self.rank,
                          C.cast(self._arrays["grads"], C.c_void_p), C.cast(self._arrays["params"], C.c_void_p),
                          C.cast(self._arrays["flags"], C.c_void_p), L.ptr(mom), L.ptr(ranges), L.ptr(lr), L.ptr(wd),
-                         nseg, self.n, momentum, 1 if first_step else 0)
+                         nseg, self.n, momentum, 1 if first_step else 0,
+                         C.c_void_p(self._bufs["grads"].multicast_ptr()) if self.nvls else None,
+                         C.c_void_p(self._bufs["params"].multicast_ptr()) if self.nvls else None)
         L.check(L.lib().sacb_allreduce_sgd(C.byref(d), L.stream()), "sacb_allreduce_sgd")

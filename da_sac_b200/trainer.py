@@ -168,7 +168,8 @@ class TargetStepper(object):
             world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
             rank = dist.get_rank() if world > 1 else 0
         assert self._graph is None, "enable_p2p() must precede capture()"
-        self.optim.p2p = P2PContext(self.net.backbone, world, rank, self.device)
+        import os
+        self.optim.p2p = P2PContext(self.net.backbone, world, rank, self.device, nvls=os.environ.get("SACB_NVLS", "0") == "1")
         self.optim._built = None
         return self.optim.p2p
 

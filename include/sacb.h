@@ -333,6 +333,12 @@ typedef struct SacbAllreduceSgd {
   int64_t n;                    /* elements of the flat buffers (multiple of 4) */
   float momentum;
   int32_t first_step;
+  /* optional NVLS path (both or neither): multicast mappings of the SAME gradient / parameter allocations (one address that
+   * reaches every rank's replica, e.g. torch.distributed._symmetric_memory's multicast_ptr).  The owner rank then reads the sum
+   * of its slice with multimem.ld_reduce (the NVSwitch adds) and writes the new weights with multimem.st.  The summation order
+   * inside the switch is not specified: replicas still agree bit for bit (one owner per element), runs may differ in the last bit. */
+  float* mc_grads;
+  float* mc_params;
 } SacbAllreduceSgd;
 int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream);
 

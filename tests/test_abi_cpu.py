@@ -36,7 +36,7 @@ def test_ctypes_structs_match_the_header_as_gcc_lays_it_out(tmp_path):
     import subprocess
     from da_sac_b200 import lib, p2p
     pairs = [("SacbConvGemm", lib.ConvGemm, "precision"), ("SacbConvWgrad", lib.ConvWgrad, "precision"), ("SacbTail", lib.Tail, "pool_mode"),
-             ("SacbLoss", lib.Loss, "grad_rows"), ("SacbAllreduceSgd", p2p.AllreduceSgd, "first_step")]
+             ("SacbLoss", lib.Loss, "grad_rows"), ("SacbAllreduceSgd", p2p.AllreduceSgd, "mc_params")]
     src = tmp_path / "sz.c"
     body = "".join('  printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (c, c, last) for c, _, last in pairs)
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sacb.h"\nint main(void) {\n' + body + "  return 0;\n}\n")

@@ -38,6 +38,8 @@ def _run_rank(rank, world, device, steps=3):
     net, cfg, st = _make(rank, device)
     bb = net.backbone
     ctx = st.enable_p2p(world, rank)
+    if os.environ.get("SACB_NVLS") == "1" and world > 1:
+        assert ctx.nvls, "SACB_NVLS=1 but the multicast path was not taken"
     flat = bb._flat
     assert flat.buf.data_ptr() == ctx._bufs["params"].ptr and bb._grad.buf.data_ptr() == ctx._bufs["grads"].ptr
     # parameters are still ordinary nn.Parameters aliasing the (re-homed) flat buffer
@@ -139,3 +141,14 @@ def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
     for rank, err, same, msg in res:
         assert msg == "", msg
         assert same and err < 1e-4, (rank, err, same)
+
+
+@pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
+                    reason="NVLS (multimem) exchange not yet verified on a multi-GPU box (set SACB_RUN_UNVERIFIED=1 to run)")
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_allreduce_sgd_world2_nvls_matches_allreduce_then_sgd(monkeypatch):
+    """SACB_NVLS=1: multimem.ld_reduce / multimem.st through the NVSwitch (buffers and multicast mapping from torch symmetric
+    memory).  At world 2 the switch's sum a + b is order-independent, so the result must still equal NCCL all-reduce + sacb_sgd
+    bit for bit and all replicas must agree."""
+    monkeypatch.setenv("SACB_NVLS", "1")
+    test_allreduce_sgd_world2_matches_allreduce_then_sgd()
