@@ -12,7 +12,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = "da_sac_b200/csrc/sacb_gemm.cu"
+SRCS = ("da_sac_b200/csrc/sacb_gemm.cu", "da_sac_b200/csrc/sacb_p2p.cu")
 NVCC = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-c"]
 
 
@@ -34,6 +34,7 @@ def norm(name):
     """map an instantiation of the working tree to the name it had in the verified commit (template bools added since)"""
     n = re.sub(r"conv_gemm_pair_kernel(I(Lb0E)+EEv|E)14CUtensorMap_st(S\d_)+NS_8GemmArgsE", "conv_gemm_pair_kernel<default>", name)
     n = re.sub(r"conv_wgrad_pair_kernel(ILb0EEEv|E)14CUtensorMap_st(S\d_)+NS_9WgradArgsE", "conv_wgrad_pair_kernel<default>", n)
+    n = re.sub(r"allreduce_sgd_kernel(ILb0EEEv|E)NS_7P2PArgsE", "allreduce_sgd_kernel<default>", n)
     return re.sub(r"(conv_(gemm|wgrad)_kernelILi\d+ELi\d+E)Lb0E", r"\1", n)
 
 
@@ -42,21 +43,22 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         csrc = os.path.join(tmp, "da_sac_b200", "csrc"); inc = os.path.join(tmp, "include")
         os.makedirs(csrc); os.makedirs(inc)
-        for path in (SRC, "da_sac_b200/csrc/sacb_common.cuh", "include/sacb.h"):
+        for path in SRCS + ("da_sac_b200/csrc/sacb_common.cuh", "include/sacb.h"):
             with open(os.path.join(tmp, path), "wb") as f:
                 f.write(subprocess.run(["git", "-C", ROOT, "show", "%s:%s" % (commit, path)], capture_output=True, check=True).stdout)
-        old_o, new_o = os.path.join(tmp, "old.o"), os.path.join(tmp, "new.o")
-        subprocess.run(NVCC + [os.path.join(tmp, SRC), "-o", old_o], check=True)
-        subprocess.run(NVCC + [os.path.join(ROOT, SRC), "-o", new_o], check=True)
-        old = {norm(k): v for k, v in funcs(old_o).items()}
         ok = True
-        for k, v in funcs(new_o).items():
-            if "Lb1" in k:
-                print("new       %5d instr  %s" % (len(v), k[:90]))
-                continue
-            same = old.get(norm(k)) == v
-            ok &= same
-            print("%-9s %5d instr  %s" % ("IDENTICAL" if same else "DIFFERENT", len(v), norm(k)[:90]))
+        for src in SRCS:
+            old_o, new_o = os.path.join(tmp, "old.o"), os.path.join(tmp, "new.o")
+            subprocess.run(NVCC + [os.path.join(tmp, src), "-o", old_o], check=True)
+            subprocess.run(NVCC + [os.path.join(ROOT, src), "-o", new_o], check=True)
+            old = {norm(k): v for k, v in funcs(old_o).items()}
+            for k, v in funcs(new_o).items():
+                if "Lb1" in k:
+                    print("new       %5d instr  %s" % (len(v), k[:90]))
+                    continue
+                same = old.get(norm(k)) == v
+                ok &= same
+                print("%-9s %5d instr  %s" % ("IDENTICAL" if same else "DIFFERENT", len(v), norm(k)[:90]))
         print("all default kernels identical to %s" % commit if ok else "MISMATCH against %s" % commit)
         return 0 if ok else 1
 
