@@ -1,4 +1,4 @@
-"""ResNet-101 DeepLabv2 schedule with TRAINING-mode batch norm -- the ABN baseline (cfg.MODEL.BASELINE = True).
+"""Backbone schedules with TRAINING-mode batch norm -- the ABN baseline (cfg.MODEL.BASELINE = True).
 
 The SAC path freezes every BN layer and folds it into the GEMM epilogue (engine.py).  The baseline that precedes it in the
 reference's recipe (/root/reference/models/__init__.py:29 -> freeze_bn = False; train.py:113-138,281-289) trains the backbone
@@ -28,15 +28,13 @@ from . import lib as L
 BN_MOMENTUM = 0.1          # nn.SyncBatchNorm default (the reference passes no momentum, deeplabv2.py:15,28)
 
 
-class ResNet101TrainBNEngine(E.ResNet101Engine):
-    def __init__(self, N, H, W, device):
-        E.ResNet101Engine.__init__(self, N, H, W, device)
-        net = self.net
+class TrainBNMixin(object):
+    """Buffers and per-unit building blocks of training-mode BN, shared by the three backbone schedules."""
+
+    def _init_train_bn(self, units, n_planes):
+        net, N, device = self.net, self.N, self.device
         # pre-BN conv outputs of every BN unit (kept for backward)
         self.zact = {}
-        units = [net["stem"]]
-        for (p, c1, c2, c3, ds) in net["blocks"]:
-            units += [c1, c2, c3] + ([ds] if ds is not None else [])
         self.units = units
         kmax, ktot, pmax = 0, 0, 0
         self.bn_off = {}
@@ -56,7 +54,7 @@ class ResNet101TrainBNEngine(E.ResNet101Engine):
         self.bn_sums_g = torch.empty(2 * kmax, **f64)        # moments of the global batch (after the all-reduce)
         self.bn_coef = torch.empty(3 * kmax, **f32)
         # more scratch planes than the frozen-BN schedule: z of the unit in flight (no-grad passes), dz of bn3 / downsample
-        self._make_pools(self.max_elems, 8, 2)
+        self._make_pools(self.max_elems, n_planes, 2)
 
     # ------------------------------------------------------------------ helpers
     def _world(self):
@@ -123,14 +121,30 @@ class ResNet101TrainBNEngine(E.ResNet101Engine):
         if tab is None or tab[0] != key:
             items, blocks = [], []
             for s, dwraw, dbeta, C_eff, RS, splits in self._fin_pending:
-                items.append(L.FinalizeItem(L.dptr(dwraw), L.dptr(flat.view(s.name + ".weight")), None, None, None, None,
-                                            L.dptr(grad.view(s.name + ".weight")), None, None, None, None, s.K, C_eff, RS, splits))
+                # bias-only convs (VGG fc6 / fc7, the 19-class score convs): d bias = column sums of the gradient, as in the
+                # frozen schedule.  BN units: d bias was zeroed by _wgrad (a bias in front of a training-mode BN has no gradient).
+                bias_only = s.bn is None and s.bias and dbeta is not None
+                items.append(L.FinalizeItem(L.dptr(dwraw), L.dptr(flat.view(s.name + ".weight")), None, None, None,
+                                            L.dptr(dbeta) if bias_only else None,
+                                            L.dptr(grad.view(s.name + ".weight")), None,
+                                            L.dptr(flat.view(s.name + ".bias")) if bias_only else None,
+                                            L.dptr(grad.view(s.name + ".bias")) if bias_only else None, None, s.K, C_eff, RS, splits))
                 blocks.append(s.K)
             tab = self._fin_table = (key, L.item_table(items, blocks, self.device))
         items, begin, n, total = tab[1]
         L.check(L.lib().sacb_wgrad_finalize_batched(L.ptr(items), L.ptr(begin), n, total, C.c_float(E.BN_EPS), L.stream()),
                 "sacb_wgrad_finalize_batched")
         self._fin_pending = []
+
+
+
+class ResNet101TrainBNEngine(TrainBNMixin, E.ResNet101Engine):
+    def __init__(self, N, H, W, device):
+        E.ResNet101Engine.__init__(self, N, H, W, device)
+        units = [self.net["stem"]]
+        for (p, c1, c2, c3, ds) in self.net["blocks"]:
+            units += [c1, c2, c3] + ([ds] if ds is not None else [])
+        self._init_train_bn(units, 8)
 
     # ------------------------------------------------------------------ forward
     def forward(self, flat, wp, x, logits_out, keep):
@@ -267,8 +281,78 @@ class ResNet101TrainBNEngine(E.ResNet101Engine):
         self._finalize_all(flat, wp, grad)
 
 
+class _VGGTrainBN(TrainBNMixin):
+    """The two VGG schedules (engine.VGG16Engine / FCN8sEngine) are chains of ``_unit`` calls forward and of
+    ``_wgrad`` + data-gradient GEMM pairs backward, each gradient having exactly one consumer.  Training-mode BN therefore
+    slots into those two building blocks: ``_unit`` = conv (+ bias) -> batch statistics -> normalise + ReLU, and ``_wgrad``
+    first turns the gradient at the BN output into the gradient at the conv output IN PLACE, so that the parent's following
+    data-gradient GEMM on the same planes already sees dz.  Everything else (pools, ASPP / FCN head wiring, dropout, score
+    fusion) is the parent's verified schedule."""
+
+    def _init_vgg_train_bn(self):
+        units = [s for s in (self.net["specs"][n] for n in self.net["order"]) if s.bn is not None]
+        self._init_train_bn(units, 5)
+        self._flat_cur = None
+
+    def forward(self, flat, wp, x, logits_out, keep):
+        assert not wp.fold_bn, "training-mode BN needs un-folded weight planes (WeightPlanes(fold_bn=False))"
+        self._flat_cur = flat
+        return super().forward(flat, wp, x, logits_out, keep)
+
+    def backward(self, flat, wp, x, dlogits, grad):
+        assert not wp.fold_bn
+        self._flat_cur = flat
+        return super().backward(flat, wp, x, dlogits, grad)
+
+    # ---- forward building blocks
+    def _first_conv_fwd(self, flat, wp, x, out):
+        lib, st, N, stem = L.lib(), L.stream(), self.N, self.net["stem"]
+        kp = self.net["stem_kp"]
+        L.check(lib.sacb_stem_im2col(L.ptr(x), L.ptr(self.stem_a.hi), L.ptr(self.stem_a.lo), N, self.H, self.W,
+                                     stem.hout, stem.wout, stem.R, stem.stride, stem.pad, kp, st), "sacb_stem_im2col")
+        sc, sh = wp.affine(stem.name)                       # fold_bn=False: scale = 1, shift = conv bias
+        wsh, wsl = wp.stem()
+        z = self.zact[stem.name]
+        L.conv_gemm(self.stem_a.hi, self.stem_a.lo, wsh, wsl, (N, stem.hout, stem.wout, kp, stem.K, 1, 1, 1, 0),
+                    scale=sc, shift=sh, out_hi=z.hi, out_lo=z.lo)
+        self._bn_forward(flat, stem, z, N * stem.hout * stem.wout, out, relu=True)
+
+    def _unit(self, wp, s, xin, out, relu, res=None):
+        if s.bn is None:                                    # bias-only conv: the parent's unit (scale = 1, shift = bias)
+            return super()._unit(wp, s, xin, out, relu, res)
+        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+        z = self.zact[s.name]
+        L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), scale=sc, shift=sh, out_hi=z.hi, out_lo=z.lo)    # z = conv + bias
+        self._bn_forward(self._flat_cur, s, z, self.N * s.hout * s.wout, out, relu, res)
+
+    # ---- backward building blocks
+    def _bn_backward_unit(self, flat, grad, s, g):
+        self._bn_backward(flat, grad, s, g, g, self.N * s.hout * s.wout)
+        if s.bias:
+            grad.view(s.name + ".bias").zero_()             # d(conv bias) = sum dz = 0 under training-mode BN
+
+    def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
+        if s.bn is not None:
+            self._bn_backward_unit(flat, grad, s, g)        # g becomes dz: the caller's data-gradient GEMM reads the same planes
+            dbeta = None
+        super()._wgrad(flat, wp, s, xin, g, grad, dbeta)
+
+    def _first_conv_bwd(self, flat, wp, gs, grad, dbeta):
+        self._bn_backward_unit(flat, grad, self.net["stem"], gs)
+        super()._first_conv_bwd(flat, wp, gs, grad, None)
+
+
+class VGG16TrainBNEngine(_VGGTrainBN, E.VGG16Engine):
+    def __init__(self, N, H, W, device):
+        E.VGG16Engine.__init__(self, N, H, W, device)
+        self._init_vgg_train_bn()
+
+
+class FCN8sTrainBNEngine(_VGGTrainBN, E.FCN8sEngine):
+    def __init__(self, N, H, W, device):
+        E.FCN8sEngine.__init__(self, N, H, W, device)
+        self._init_vgg_train_bn()
+
+
 def make_engine(arch, N, H, W, device):
-    if arch != "resnet101":
-        raise NotImplementedError("libsac_b200: training-mode BN (cfg.MODEL.BASELINE, the ABN baseline) is built for "
-                                  "deeplabv2_resnet101 only; '%s' still needs its schedule in engine_abn.py" % arch)
-    return ResNet101TrainBNEngine(N, H, W, device)
+    return {"resnet101": ResNet101TrainBNEngine, "vgg16": VGG16TrainBNEngine, "fcn": FCN8sTrainBNEngine}[arch](N, H, W, device)

@@ -107,12 +107,12 @@ VGG16_CONVS = ((0, 1), (3, 1), (7, 1), (10, 1), (14, 1), (17, 1), (20, 1), (24, 
 VGG16_POOL_AFTER = (3, 10, 20)
 
 
-def vgg16_deeplab_logits(p, x, taps=None):
+def vgg16_deeplab_logits(p, x, taps=None, bn=_bn_eval):
     """DeepLabV2_VGG16._backbone (deeplabv2.py:294-298): vgg16_bn features (conv5 dilation 2, pool4/5 removed,
     :238-260), fc6/fc7 3x3 dilation 4 + ReLU (:262-265), Classifier_Module on 1024 channels (:270)."""
     for idx, dil in VGG16_CONVS:
         x = F.conv2d(x, p["features.%d.weight" % idx], p["features.%d.bias" % idx], 1, dil, dil)
-        x = F.relu(_bn_eval(x, p, "features.%d" % (idx + 1)))
+        x = F.relu(bn(x, p, "features.%d" % (idx + 1)))
         if taps is not None: taps["features.%d" % idx] = x
         if idx in VGG16_POOL_AFTER:
             x = F.max_pool2d(x, 2, 2)
@@ -129,19 +129,19 @@ def vgg16_deeplab_logits(p, x, taps=None):
 FCN_TRUNK = (("block1", (0, 3, 7, 10, 14, 17, 20), (3, 10, 20)), ("block2", (24, 27, 30), (30,)), ("block3", (34, 37, 40), (40,)))
 
 
-def vgg16_fcn8s_logits(p, x):
+def vgg16_fcn8s_logits(p, x, bn=_bn_eval):
     """VGG16_FCN8s._backbone (fcn.py:111-137) with drop_rate = 0 (Dropout2d is the identity): pool3/4/5 features, 7x7 /
     1x1 head, score_pool4 / score_pool3, bilinear x2 (align_corners=True) fusion -> scores at 1/8 resolution."""
     feats = {}
     for blk, convs, pools in FCN_TRUNK:
         for idx in convs:
             x = F.conv2d(x, p["%s.%d.weight" % (blk, idx)], p["%s.%d.bias" % (blk, idx)], 1, 1)
-            x = F.relu(_bn_eval(x, p, "%s.%d" % (blk, idx + 1)))
+            x = F.relu(bn(x, p, "%s.%d" % (blk, idx + 1)))
             if idx in pools:
                 x = F.max_pool2d(x, 2, 2)
         feats[blk] = x
-    h = F.relu(_bn_eval(F.conv2d(feats["block3"], p["vgg_head.0.weight"], p["vgg_head.0.bias"], 1, 3), p, "vgg_head.1"))
-    h = F.relu(_bn_eval(F.conv2d(h, p["vgg_head.4.weight"], p["vgg_head.4.bias"]), p, "vgg_head.5"))
+    h = F.relu(bn(F.conv2d(feats["block3"], p["vgg_head.0.weight"], p["vgg_head.0.bias"], 1, 3), p, "vgg_head.1"))
+    h = F.relu(bn(F.conv2d(h, p["vgg_head.4.weight"], p["vgg_head.4.bias"]), p, "vgg_head.5"))
     score = F.conv2d(h, p["vgg_head.8.weight"], p["vgg_head.8.bias"])
     up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)       # fcn.py:107-109
     score = up(score) + F.conv2d(feats["block2"], p["score_pool4.weight"], p["score_pool4.bias"])
@@ -434,12 +434,14 @@ def sac_target_step(student, teacher, running_conf, batch, T, cfg, optim=None):
 # --------------------------------------------------------------------------
 
 def baseline_forward(params, x, y=None, taps=None):
-    """SAC_Baseline.forward -> DeepLabV2_ResNet101.forward in train() mode with freeze_bn=False (sac.py:34-35,
-    deeplabv2.py:213-227).  Returns (losses, outs, new_stats); ``new_stats`` holds the running statistics after the
+    """SAC_Baseline.forward -> backbone.forward in train() mode with freeze_bn=False (sac.py:34-35, deeplabv2.py:213-227,
+    300-312, fcn.py:139-149; the architecture is recognised from the state_dict keys).  Returns (losses, outs, new_stats); ``new_stats`` holds the running statistics after the
     forward pass (every BN layer updates them, also under torch.no_grad())."""
-    assert "model.conv1.weight" in params, "the ABN baseline oracle covers the ResNet-101 backbone"
     new_stats = OrderedDict()
-    logits = resnet101_logits(params, x, taps=taps, bn=bn_train_recorder(new_stats, taps=taps))
+    bn = bn_train_recorder(new_stats, taps=taps)
+    if "model.conv1.weight" in params: logits = resnet101_logits(params, x, taps=taps, bn=bn)
+    elif "vgg_head.0.weight" in params: logits = vgg16_fcn8s_logits(params, x, bn=bn)       # drop_rate = 0
+    else: logits = vgg16_deeplab_logits(params, x, taps=taps, bn=bn)
     logits_up = F.interpolate(logits, x.shape[-2:], mode="bilinear", align_corners=True)
     if y is None:
         return (logits, logits_up), None, new_stats

@@ -29,15 +29,20 @@ REF = "/root/reference"
 from da_sac_b200 import synth  # noqa: E402
 
 N_SRC, N_TGT, HW = 4, 3, (129, 129)
+ARCH = sys.argv[1] if len(sys.argv) > 1 else "resnet101"          # resnet101 | vgg16 | fcn
+if ARCH != "resnet101":
+    N_SRC, N_TGT, HW = 3, 2, (96, 96)
 
 
 def build_reference_net():
     sys.path.insert(0, REF)
     from core.config import cfg, cfg_from_file, cfg_from_list
-    cfg_from_file(os.path.join(REF, "configs/deeplabv2_resnet101_train.yaml"))
+    cfg_from_file(os.path.join(REF, {"resnet101": "configs/deeplabv2_resnet101_train.yaml", "vgg16": "configs/deeplabv2_vgg16_train.yaml",
+                                     "fcn": "configs/fcn_vgg16_train.yaml"}[ARCH]))
     cfg_from_list(["MODEL.INIT_MODEL", "", "MODEL.BASELINE", "True"])
     from models import get_model
-    net = get_model(cfg.MODEL, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    extra = {"drop_rate": 0.0} if ARCH == "fcn" else {}          # Dropout2d off: the comparison must not depend on the RNG stream
+    net = get_model(cfg.MODEL, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"), **extra)
     sys.path.remove(REF)
     return net, cfg
 
@@ -47,10 +52,22 @@ def main():
     torch.set_num_threads(8)
     net, cfg = build_reference_net()
     assert type(net).__name__ == "SAC_Baseline"
-    net.backbone.load_state_dict(synth.make_backbone_params(seed=123), strict=True)
+    sd0 = {"resnet101": lambda: synth.make_backbone_params(seed=123), "vgg16": lambda: synth.make_vgg16_params(seed=321),
+           "fcn": lambda: synth.make_fcn_params(seed=213)}[ARCH]()
+    net.backbone.load_state_dict(sd0, strict=True)
     net.train()
-    assert net.backbone.model.layer3[5].bn2.training, "BN layers must train in BASELINE mode"
+    bns = [m for m in net.backbone.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
+    assert bns and all(m.training for m in bns), "BN layers must train in BASELINE mode"
     optim = torch.optim.SGD(net.parameter_groups(cfg.MODEL.LR, cfg.MODEL.WEIGHT_DECAY), momentum=cfg.MODEL.MOMENTUM)
+    # VGG16_FCN8s.forward returns logits_up only when labels are given (fcn.py:139-149): record what _backbone returned
+    # (a second call would move the BN running statistics a second time)
+    captured = []
+    if ARCH == "fcn":
+        orig = net.backbone._backbone
+        net.backbone._backbone = lambda inp: (captured.append(orig(inp)) or captured[-1])
+
+    def logits_of(o):
+        return (o["logits"] if "logits" in o else captured[-1]).detach().numpy()
     xs, ys = synth.make_source_batch(N_SRC, HW, seed=0)
     xt, yt = synth.make_source_batch(N_TGT, HW, seed=1)
     out = {}
@@ -59,17 +76,29 @@ def main():
     losses, outs = net(xs.clone(), ys.clone())
     optim.zero_grad()
     losses["loss_ce"].mean().backward()
-    out["src_logits"] = outs["logits"].detach().numpy()
+    out["src_logits"] = logits_of(outs)
     out["src_loss_ce"] = losses["loss_ce"].detach().numpy()
     names, norms = [], []
     for k, p in net.backbone.named_parameters():
         names.append(k); norms.append(p.grad.double().norm().item())
     out["grad_names"] = np.array(names)
     out["src_grad_norms"] = np.array(norms)
-    for k in ("model.conv1.weight", "model.bn1.weight", "model.bn1.bias", "model.layer1.0.conv1.weight", "model.layer1.0.bn3.weight",
-              "model.layer2.0.downsample.0.weight", "model.layer2.0.downsample.1.bias", "model.layer3.5.conv2.weight",
-              "model.layer3.5.bn2.weight", "model.layer3.22.bn3.bias", "model.layer4.2.conv3.weight",
-              "model.layer5.conv2d_list.1.weight", "model.layer5.conv2d_list.1.bias"):
+    GRAD_KEYS = {"resnet101": ("model.conv1.weight", "model.bn1.weight", "model.bn1.bias", "model.layer1.0.conv1.weight", "model.layer1.0.bn3.weight",
+                               "model.layer2.0.downsample.0.weight", "model.layer2.0.downsample.1.bias", "model.layer3.5.conv2.weight",
+                               "model.layer3.5.bn2.weight", "model.layer3.22.bn3.bias", "model.layer4.2.conv3.weight",
+                               "model.layer5.conv2d_list.1.weight", "model.layer5.conv2d_list.1.bias"),
+                 "vgg16": ("features.0.weight", "features.0.bias", "features.1.weight", "features.1.bias", "features.17.weight", "features.18.bias",
+                           "features.39.weight", "features.40.weight", "features.42.weight", "features.42.bias", "features.44.bias",
+                           "classifier.conv2d_list.1.weight", "classifier.conv2d_list.1.bias"),
+                 "fcn": ("block1.0.weight", "block1.1.weight", "block1.1.bias", "block2.27.weight", "block2.27.bias", "block3.40.weight",
+                         "block3.41.bias", "vgg_head.0.weight", "vgg_head.1.weight", "vgg_head.4.bias", "vgg_head.5.bias", "vgg_head.8.weight",
+                         "vgg_head.8.bias", "score_pool4.weight", "score_pool3.bias")}[ARCH]
+    POST_KEYS = {"resnet101": ("model.layer3.5.conv2.weight", "model.layer3.5.bn2.weight", "model.layer5.conv2d_list.1.bias"),
+                 "vgg16": ("features.17.weight", "features.18.weight", "classifier.conv2d_list.1.bias"),
+                 "fcn": ("block2.27.weight", "vgg_head.1.weight", "score_pool4.bias")}[ARCH]
+    NBT_KEY = {"resnet101": "model.layer3.5.bn2.num_batches_tracked", "vgg16": "features.18.num_batches_tracked",
+               "fcn": "vgg_head.1.num_batches_tracked"}[ARCH]
+    for k in GRAD_KEYS:
         g = dict(net.backbone.named_parameters())[k].grad
         out["src_grad::" + k] = (g.flatten()[:60000] if g.numel() > 60000 else g).numpy().copy()
     optim.step()
@@ -77,18 +106,18 @@ def main():
     stat_keys = [k for k in sd if k.endswith("running_mean") or k.endswith("running_var")]
     out["stat_names"] = np.array(stat_keys)
     out["src_stats"] = np.concatenate([sd[k].numpy().ravel() for k in stat_keys])
-    out["src_nbt"] = np.array(int(sd["model.layer3.5.bn2.num_batches_tracked"]))
-    for k in ("model.layer3.5.conv2.weight", "model.layer3.5.bn2.weight", "model.layer5.conv2d_list.1.bias"):
+    out["src_nbt"] = np.array(int(sd[NBT_KEY]))
+    for k in POST_KEYS:
         out["src_post::" + k] = sd[k].flatten()[:60000].numpy().copy()
 
     # ---- ABN target pass (train.py:281-289)
     with torch.no_grad():
         losses_t, outs_t = net(xt.clone(), yt.clone())
-    out["tgt_logits"] = outs_t["logits"].numpy()
+    out["tgt_logits"] = logits_of(outs_t)
     out["tgt_loss_ce"] = losses_t["loss_ce"].numpy()
     sd = net.backbone.state_dict()
     out["tgt_stats"] = np.concatenate([sd[k].numpy().ravel() for k in stat_keys])
-    out["tgt_nbt"] = np.array(int(sd["model.layer3.5.bn2.num_batches_tracked"]))
+    out["tgt_nbt"] = np.array(int(sd[NBT_KEY]))
 
     # ---- evaluation with the adapted statistics
     net.eval()
@@ -98,7 +127,7 @@ def main():
     print("src loss %.6f  tgt loss %.6f  logits absmax %.2f / %.2f / %.2f" % (
         float(out["src_loss_ce"]), float(out["tgt_loss_ce"]), np.abs(out["src_logits"]).max(), np.abs(out["tgt_logits"]).max(),
         np.abs(out["eval_logits"]).max()))
-    path = os.path.join(HERE, "abn_resnet101_tiny.npz")
+    path = os.path.join(HERE, {"resnet101": "abn_resnet101_tiny.npz", "vgg16": "abn_vgg16_tiny.npz", "fcn": "abn_fcn8s_tiny.npz"}[ARCH])
     np.savez_compressed(path, **out)
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 

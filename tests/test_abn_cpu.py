@@ -12,12 +12,14 @@ from da_sac_b200 import synth
 from oracle import sac_oracle as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_SRC, N_TGT, HW = 4, 3, (129, 129)
-
-
-@pytest.fixture(scope="module")
-def abn_golden():
-    return np.load(os.path.join(ROOT, "tests", "golden", "abn_resnet101_tiny.npz"), allow_pickle=False)
+ARCHS = {   # arch -> (golden file, state_dict factory, cfg, (N_SRC, N_TGT, HW), num_batches_tracked key, #BN layers)
+    "resnet101": ("abn_resnet101_tiny.npz", lambda: synth.make_backbone_params(seed=123), synth.ModelCfg, (4, 3, (129, 129)),
+                  "model.layer3.5.bn2.num_batches_tracked", 104),
+    "vgg16": ("abn_vgg16_tiny.npz", lambda: synth.make_vgg16_params(seed=321), synth.ModelCfgVGG16, (3, 2, (96, 96)),
+              "features.18.num_batches_tracked", 13),
+    "fcn": ("abn_fcn8s_tiny.npz", lambda: synth.make_fcn_params(seed=213), synth.ModelCfgFCN, (3, 2, (96, 96)),
+            "vgg_head.1.num_batches_tracked", 15),
+}
 
 
 def rel(a, b):
@@ -29,11 +31,13 @@ def _stats(params, names):
     return torch.cat([params[str(k)].detach().reshape(-1) for k in names])
 
 
-def test_oracle_abn_source_step_target_pass_and_eval_match_reference(abn_golden):
-    g = abn_golden
+@pytest.mark.parametrize("arch", sorted(ARCHS))
+def test_oracle_abn_source_step_target_pass_and_eval_match_reference(arch):
+    fname, make_sd, Cfg, (N_SRC, N_TGT, HW), nbt_key, n_bn = ARCHS[arch]
+    g = np.load(os.path.join(ROOT, "tests", "golden", fname), allow_pickle=False)
     torch.set_num_threads(8)
-    cfg = synth.ModelCfg()
-    student = O.as_leaf_params(synth.make_backbone_params(seed=123))
+    cfg = Cfg()
+    student = O.as_leaf_params(make_sd())
     optim = torch.optim.SGD(O.parameter_groups(student, cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
     xs, ys = synth.make_source_batch(N_SRC, HW, seed=0)
     xt, yt = synth.make_source_batch(N_TGT, HW, seed=1)
@@ -45,28 +49,32 @@ def test_oracle_abn_source_step_target_pass_and_eval_match_reference(abn_golden)
     names = [str(n) for n in g["grad_names"]]
     mine = np.array([student[n].grad.double().norm().item() for n in names])
     gn = g["src_grad_norms"]
-    # the conv biases / gradients that are mathematically zero under training-mode BN do not exist in ResNet (bias=False)
-    assert np.all(np.abs(mine - gn) <= 2e-3 * np.maximum(gn, 1e-9)), np.max(np.abs(mine - gn) / np.maximum(gn, 1e-9))
+    # a conv bias in front of a training-mode BN has a mathematically zero gradient: both sides hold rounding noise there
+    # (VGG convs; ResNet convs have no bias), so those entries are compared absolutely
+    big = gn > 1e-6 * gn.max()
+    assert np.all(np.abs(mine - gn)[big] <= 2e-3 * gn[big]), np.max(np.abs(mine - gn)[big] / gn[big])
+    assert np.all(mine[~big] <= 1e-5 * gn.max())
     for key in g.files:
         if key.startswith("src_grad::"):
             n = key.split("::")[1]
             gr = student[n].grad.flatten()[:60000] if student[n].grad.numel() > 60000 else student[n].grad
-            assert rel(gr.reshape(g[key].shape), g[key])[0] < 2e-3, key
+            if np.abs(g[key]).max() > 1e-6 * gn.max():
+                assert rel(gr.reshape(g[key].shape), g[key])[0] < 2e-3, key
         if key.startswith("src_post::"):
             n = key.split("::")[1]
             assert rel(student[n].detach().flatten()[:60000], g[key])[1] < 1e-6, key
     stat_names = [str(k) for k in g["stat_names"]]
-    assert len(stat_names) == 2 * 104
+    assert len(stat_names) == 2 * n_bn
     l2, mx = rel(_stats(student, stat_names), g["src_stats"])
     assert l2 < 1e-5 and mx < 1e-5, (l2, mx)
-    assert int(student["model.layer3.5.bn2.num_batches_tracked"]) == int(g["src_nbt"]) == 1
+    assert int(student[nbt_key]) == int(g["src_nbt"]) == 1
     # ---- ABN target pass: no gradient, only the running statistics change
     before = {k: v.detach().clone() for k, v in student.items() if k.endswith(".weight") or k.endswith(".bias")}
     losses_t, outs_t = O.baseline_target_pass(student, xt, yt)
     assert rel(outs_t["logits"], g["tgt_logits"])[1] < 1e-4
     assert abs(float(losses_t["loss_ce"]) - float(g["tgt_loss_ce"].reshape(-1)[0])) < 1e-5
     assert rel(_stats(student, stat_names), g["tgt_stats"])[1] < 1e-5
-    assert int(student["model.layer3.5.bn2.num_batches_tracked"]) == int(g["tgt_nbt"]) == 2
+    assert int(student[nbt_key]) == int(g["tgt_nbt"]) == 2
     assert all(torch.equal(before[k], student[k].detach()) for k in before)
     # ---- evaluation with the adapted statistics (frozen-BN path of the same oracle)
     with torch.no_grad():

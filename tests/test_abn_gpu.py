@@ -20,7 +20,6 @@ pytestmark = [pytest.mark.gpu,
                                  reason="ABN-baseline GPU path not yet verified on a B200 (set SACB_RUN_UNVERIFIED=1 to run)")]
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N_SRC, N_TGT, HW = 4, 3, (129, 129)
 EPS, MOM = 1e-5, 0.1
 
 
@@ -101,24 +100,32 @@ def test_bn_kernels_match_torch_fp64(M, Cn, with_res):
     assert torch.equal(gh, dzh) and torch.equal(gl, dzl)
 
 
-@pytest.fixture(scope="module")
-def abn_golden():
-    return np.load(os.path.join(ROOT, "tests", "golden", "abn_resnet101_tiny.npz"), allow_pickle=False)
+ARCHS = {   # arch -> (golden, state_dict factory name, cfg name, (N_SRC, N_TGT, HW), nbt key, probe weight, min launches)
+    "resnet101": ("abn_resnet101_tiny.npz", "make_backbone_params", 123, "ModelCfg", (4, 3, (129, 129)),
+                  "model.layer3.5.bn2.num_batches_tracked", "model.layer3.5.conv2.weight", 800),
+    "vgg16": ("abn_vgg16_tiny.npz", "make_vgg16_params", 321, "ModelCfgVGG16", (3, 2, (96, 96)),
+              "features.18.num_batches_tracked", "features.17.weight", 150),
+    "fcn": ("abn_fcn8s_tiny.npz", "make_fcn_params", 213, "ModelCfgFCN", (3, 2, (96, 96)),
+            "vgg_head.1.num_batches_tracked", "block2.27.weight", 150),
+}
 
 
-def test_abn_iteration_matches_reference_golden(abn_golden):
+@pytest.mark.parametrize("arch", ["resnet101", "vgg16", "fcn"])
+def test_abn_iteration_matches_reference_golden(arch):
     """source step (training BN + SGD) -> no-grad target pass (statistics only) -> eval forward, vs the real reference"""
     from da_sac_b200 import lib as L, synth
     from da_sac_b200.models import get_model
-    g = abn_golden
+    fname, make_sd, seed, cfg_name, (N_SRC, N_TGT, HW), nbt_key, probe, min_launches = ARCHS[arch]
+    g = np.load(os.path.join(ROOT, "tests", "golden", fname), allow_pickle=False)
 
-    class Cfg(synth.ModelCfg):
+    class Cfg(getattr(synth, cfg_name)):
         BASELINE = True
 
     cfg = Cfg()
-    net = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    extra = {"drop_rate": 0.0} if arch == "fcn" else {}
+    net = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"), **extra)
     assert type(net).__name__ == "SAC_Baseline"
-    net.backbone.load_state_dict(synth.make_backbone_params(seed=123))
+    net.backbone.load_state_dict(getattr(synth, make_sd)(seed=seed))
     net.cuda().train()
     optim = torch.optim.SGD(net.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY), momentum=cfg.MOMENTUM)
     xs, ys = [t.cuda() for t in synth.make_source_batch(N_SRC, HW, seed=0)]
@@ -129,20 +136,22 @@ def test_abn_iteration_matches_reference_golden(abn_golden):
     optim.zero_grad()
     losses["loss_ce"].mean().backward()
     torch.cuda.synchronize()
-    assert L.launch_count() - n0 > 800, "the training-BN CUDA path did not run"
+    assert L.launch_count() - n0 > min_launches, "the training-BN CUDA path did not run"
     l2, mx = rel(outs["logits"].detach(), g["src_logits"])
-    print("ABN source logits rel-L2 %.2e max %.2e" % (l2, mx))
+    print(arch, "ABN source logits rel-L2 %.2e max %.2e" % (l2, mx))
     assert l2 < 1e-3 and mx < 1e-3
-    assert abs(float(losses["loss_ce"].detach()) - float(g["src_loss_ce"].reshape(-1)[0])) < 2e-3 * float(g["src_loss_ce"].reshape(-1)[0])
+    ref_loss = float(g["src_loss_ce"].reshape(-1)[0])
+    assert abs(float(losses["loss_ce"].detach()) - ref_loss) < 2e-3 * ref_loss
     params = dict(net.backbone.named_parameters())
     names = [str(n) for n in g["grad_names"]]
     mine = np.array([params[n].grad.double().norm().item() for n in names])
     gn = g["src_grad_norms"]
-    relerr = np.abs(mine - gn) / np.maximum(gn, 1e-9)
-    print("ABN grad-norm max rel err %.2e (%s)" % (relerr.max(), names[int(relerr.argmax())]))
-    assert relerr.max() < 2e-2
+    big = gn > 1e-6 * gn.max()          # conv biases in front of a training-mode BN: zero gradient up to rounding noise
+    relerr = np.abs(mine - gn)[big] / gn[big]
+    print(arch, "ABN grad-norm max rel err %.2e" % relerr.max())
+    assert relerr.max() < 2e-2 and np.all(mine[~big] <= 1e-5 * gn.max())
     for key in g.files:
-        if key.startswith("src_grad::"):
+        if key.startswith("src_grad::") and np.abs(g[key]).max() > 1e-6 * gn.max():
             n = key.split("::")[1]
             gr = params[n].grad
             gr = gr.flatten()[:60000] if gr.numel() > 60000 else gr
@@ -154,20 +163,21 @@ def test_abn_iteration_matches_reference_golden(abn_golden):
     stat_names = [str(k) for k in g["stat_names"]]
     stats = torch.cat([sd[k].reshape(-1) for k in stat_names])
     assert rel(stats, g["src_stats"])[1] < 1e-4
-    assert int(sd["model.layer3.5.bn2.num_batches_tracked"]) == int(g["src_nbt"])
+    assert int(sd[nbt_key]) == int(g["src_nbt"])
     for key in g.files:
         if key.startswith("src_post::"):
             assert rel(sd[key.split("::")[1]].flatten()[:60000], g[key])[1] < 1e-5, key
     # ---- ABN target pass (train.py:281-289): statistics only
-    w_before = net.backbone.model.layer3[5].conv2.weight.detach().clone()
+    w_before = sd[probe].detach().clone()
     with torch.no_grad():
         losses_t, outs_t = net(xt, yt)
     assert rel(outs_t["logits"], g["tgt_logits"])[1] < 1e-3
-    assert abs(float(losses_t["loss_ce"]) - float(g["tgt_loss_ce"].reshape(-1)[0])) < 2e-3 * float(g["tgt_loss_ce"].reshape(-1)[0])
+    ref_loss = float(g["tgt_loss_ce"].reshape(-1)[0])
+    assert abs(float(losses_t["loss_ce"]) - ref_loss) < 2e-3 * ref_loss
     sd = net.backbone.state_dict()
     assert rel(torch.cat([sd[k].reshape(-1) for k in stat_names]), g["tgt_stats"])[1] < 1e-4
-    assert int(sd["model.layer3.5.bn2.num_batches_tracked"]) == int(g["tgt_nbt"])
-    assert torch.equal(w_before, net.backbone.model.layer3[5].conv2.weight.detach())
+    assert int(sd[nbt_key]) == int(g["tgt_nbt"])
+    assert torch.equal(w_before, sd[probe])
     # ---- evaluation with the adapted statistics: the frozen-BN engine
     net.eval()
     logits_e, _ = net(xt)

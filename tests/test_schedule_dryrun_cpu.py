@@ -112,16 +112,34 @@ def test_training_bn_engine_schedule_runs(fake):
     assert logits.shape == (2, 19, 9, 9)
 
 
-def test_training_bn_is_refused_for_backbones_without_a_schedule(fake):
-    from da_sac_b200 import synth
+@pytest.mark.parametrize("arch,n_units", [("vgg16", 13), ("fcn", 15)])
+def test_training_bn_schedules_of_the_vgg_backbones_run(fake, arch, n_units):
+    """the VGG engines get training-mode BN through their _unit / _wgrad building blocks (engine_abn._VGGTrainBN)"""
+    from da_sac_b200 import engine_abn, synth
     from da_sac_b200.models import get_model
+    Base = {"vgg16": synth.ModelCfgVGG16, "fcn": synth.ModelCfgFCN}[arch]
 
-    class Cfg(synth.ModelCfgVGG16):
+    class Cfg(Base):
         BASELINE = True
     net = get_model(Cfg(), 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(torch.randn(1, 3, 64, 64), torch.zeros(1, 64, 64, dtype=torch.long))
+    bb = net.backbone
+    xs, ys = synth.make_source_batch(2, (64, 64), seed=0)
+    losses, outs = net(xs, ys)
+    eng = bb.engine(2, 64, 64)
+    assert type(eng) is {"vgg16": engine_abn.VGG16TrainBNEngine, "fcn": engine_abn.FCN8sTrainBNEngine}[arch]
+    assert len(eng.units) == n_units and not bb._wp.fold_bn
+    assert fake.calls["sacb_bn_moments"] == n_units == fake.calls["sacb_bn_apply"] == fake.calls["sacb_bn_train_finalize"]
+    losses["loss_ce"].mean().backward()
+    assert fake.calls["sacb_bn_moments"] == 2 * n_units and fake.calls["sacb_bn_bwd_apply"] == n_units
+    assert all(p.grad is not None for p in bb.parameters())
+    with torch.no_grad():
+        net(xs, ys)
+    assert fake.calls["sacb_bn_train_finalize"] == 2 * n_units
+    net.eval()
+    before = fake.calls["sacb_bn_moments"]
+    net(xs)
+    assert fake.calls["sacb_bn_moments"] == before and bb._wp.fold_bn
 
 
 @pytest.mark.parametrize("arch", ["resnet101", "vgg16", "fcn"])
