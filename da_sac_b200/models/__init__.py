@@ -1,28 +1,42 @@
-"""Model registry -- drop-in for /root/reference/models/__init__.py:14-41.
+"""Model registry of the B200 drop-in: ``from models import get_model`` keeps working after
+``sys.modules["models"] = da_sac_b200.models``.
 
-``get_model(cfg.MODEL, rank, num_classes=19, criterion=...)`` returns ``SAC`` (or ``SAC_Baseline`` when
-``cfg.BASELINE``) wrapping a B200-native backbone and its momentum copy."""
+Contract taken from /root/reference/models/__init__.py:14-41 and train.py:88-89: ``get_model(cfg.MODEL, rank,
+num_classes=19, criterion=...)`` builds the backbone named by ``cfg.ARCH`` -- twice when the consistency loss is trained,
+the second copy being the momentum (teacher) network -- and wraps it in ``SAC``; with ``cfg.BASELINE`` it returns
+``SAC_Baseline`` around a single backbone whose BN layers train (the ABN baseline).  ``cfg.INIT_MODEL`` is forwarded as
+``pretrained`` when the file exists."""
 import os
-
-from functools import partial
 
 from .deeplabv2 import DeepLabV2_ResNet101, DeepLabV2_VGG16
 from .fcn import VGG16_FCN8s
 from .sac import SAC, SAC_Baseline
 
+# ARCH key -> (backbone class, fixed constructor arguments)
+BACKBONES = {
+    "deeplabv2_resnet101": (DeepLabV2_ResNet101, {}),
+    "deeplabv2_vgg16_bn": (DeepLabV2_VGG16, {"use_bn": True}),
+    "fcn_vgg16_bn": (VGG16_FCN8s, {"use_bn": True}),
+}
+
+
+def _build_backbone(arch, args, kwargs):
+    cls, fixed = BACKBONES[arch]
+    return cls(*args, **dict(kwargs, **fixed))
+
 
 def get_model(cfg, rank, *args, **kwargs):
-    models = {"deeplabv2_resnet101": DeepLabV2_ResNet101, "deeplabv2_vgg16_bn": partial(DeepLabV2_VGG16, use_bn=True),
-              "fcn_vgg16_bn": partial(VGG16_FCN8s, use_bn=True)}
     arch = cfg.ARCH.lower()
-    if arch not in models:
-        raise NotImplementedError("libsac_b200: backbone '%s' is not built yet (SURVEY.md section 8(f)); available: %s"
-                                  % (arch, sorted(models)))
-    if len(cfg.INIT_MODEL) > 0 and os.path.isfile(cfg.INIT_MODEL):
-        kwargs["pretrained"] = cfg.INIT_MODEL
-    kwargs["freeze_bn"] = not cfg.BASELINE
-    backbone = models[arch](*args, **kwargs)
+    if arch not in BACKBONES:
+        raise NotImplementedError("libsac_b200 has no backbone '%s'; available: %s" % (arch, sorted(BACKBONES)))
+    opts = dict(kwargs)
+    snapshot = cfg.INIT_MODEL
+    if snapshot and os.path.isfile(snapshot):
+        opts["pretrained"] = snapshot
+    # the SAC stage trains with frozen BN statistics; only the ABN baseline lets them move (reference: models/__init__.py:29)
+    opts["freeze_bn"] = not cfg.BASELINE
+    student = _build_backbone(arch, args, opts)
     if cfg.BASELINE:
-        return SAC_Baseline(cfg, backbone, rank, **kwargs)
-    slow_copy = models[arch](*args, **kwargs)
-    return SAC(cfg, backbone, slow_copy, rank, **kwargs)
+        return SAC_Baseline(cfg, student, rank, **opts)
+    teacher = _build_backbone(arch, args, opts)
+    return SAC(cfg, student, teacher, rank, **opts)

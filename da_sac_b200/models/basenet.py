@@ -1,22 +1,21 @@
-"""BaseNet: optimiser-group / BN-freezing bookkeeping of the backbones.
+"""BaseNet: what ``train.py`` / ``base_trainer.get_optim`` expect from a backbone besides ``forward``.
 
-Mirrors the public surface of /root/reference/models/basenet.py:12-143
-(``from_scratch_layers``, ``bn_freeze``, ``train()`` keeping frozen BN in eval,
-``parameter_groups(base_lr, wd)`` -> 4 groups with lr multipliers), because
-``train.py:93-94`` and ``base_trainer.get_optim`` consume exactly that."""
+Public surface mirrored from /root/reference/models/basenet.py:12-143: the bookkeeping lists ``from_scratch_layers`` /
+``not_training`` / ``bn_freeze``, ``train()`` that leaves frozen BN layers in eval mode, and ``parameter_groups(base_lr, wd)``
+returning the four optimiser groups (pre-trained weights, pre-trained biases at 2x lr, new weights and new biases at the
+backbone's ``lr_mult`` / ``lr_mult_bias`` factors; weight decay on the weight groups only)."""
 import torch.nn as nn
+
+LEARNABLE = (nn.Linear, nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.SyncBatchNorm, nn.GroupNorm, nn.InstanceNorm2d)
+NORMS = (nn.BatchNorm2d, nn.SyncBatchNorm, nn.GroupNorm)
 
 
 class BaseNet(nn.Module):
-    _trainable = (nn.Linear, nn.Conv2d, nn.ConvTranspose2d, nn.BatchNorm2d, nn.GroupNorm, nn.InstanceNorm2d, nn.SyncBatchNorm)
-    _batchnorm = (nn.BatchNorm2d, nn.SyncBatchNorm, nn.GroupNorm)
-
     def __init__(self):
         super().__init__()
-        self.from_scratch_layers = []
-        self.not_training = []
-        self.bn_freeze = []
+        self.from_scratch_layers, self.not_training, self.bn_freeze = [], [], []
 
+    # learning-rate multipliers (old layers, from-scratch layers); backbones override them
     def lr_mult(self):
         return 1., 1.
 
@@ -24,40 +23,30 @@ class BaseNet(nn.Module):
         return 2., 2.
 
     def _is_learnable(self, layer):
-        return isinstance(layer, BaseNet._trainable)
+        return isinstance(layer, LEARNABLE)
 
     def _from_scratch(self, net):
-        for layer in net.modules():
-            if self._is_learnable(layer):
-                self.from_scratch_layers.append(layer)
+        self.from_scratch_layers.extend(m for m in net.modules() if self._is_learnable(m))
 
     def _freeze_bn(self, net):
-        for layer in net.modules():
-            if isinstance(layer, BaseNet._batchnorm):
-                self.bn_freeze.append(layer)
+        self.bn_freeze.extend(m for m in net.modules() if isinstance(m, NORMS))
 
     def train(self, mode=True):
         super().train(mode)
-        for layer in self.bn_freeze:      # frozen BN: statistics stay in eval mode (basenet.py:97-100)
-            layer.eval()
+        for m in self.bn_freeze:          # frozen statistics: these stay in eval mode whatever the net is told
+            m.eval()
         return self
 
     def parameter_groups(self, base_lr, wd):
-        """[old weights (wd), old biases, new weights x lr_mult (wd), new biases] -- basenet.py:102-139;
-        BN gamma lands in the weight groups, BN beta in the bias groups."""
-        w_old, w_new = self.lr_mult()
-        b_old, b_new = self.lr_mult_bias()
-        groups = ({"params": [], "weight_decay": wd, "lr": w_old * base_lr},
-                  {"params": [], "weight_decay": 0.0, "lr": b_old * base_lr},
-                  {"params": [], "weight_decay": wd, "lr": w_new * base_lr},
-                  {"params": [], "weight_decay": 0.0, "lr": b_new * base_lr})
-        scratch = set(id(m) for m in self.from_scratch_layers)
+        """group index = 2 * is_new + is_bias; BN gamma counts as a weight, BN beta as a bias (as in the reference)"""
+        mult = (self.lr_mult()[0], self.lr_mult_bias()[0], self.lr_mult()[1], self.lr_mult_bias()[1])
+        groups = [{"params": [], "weight_decay": wd if i % 2 == 0 else 0.0, "lr": mult[i] * base_lr} for i in range(4)]
+        new_ids = {id(m) for m in self.from_scratch_layers}
         for m in self.modules():
             if not self._is_learnable(m):
                 continue
-            new = id(m) in scratch
-            if m.weight is not None and m.weight.requires_grad:
-                groups[2 if new else 0]["params"].append(m.weight)
-            if m.bias is not None and m.bias.requires_grad:
-                groups[3 if new else 1]["params"].append(m.bias)
-        return groups
+            base = 2 if id(m) in new_ids else 0
+            for is_bias, p in enumerate((m.weight, m.bias)):
+                if p is not None and p.requires_grad:
+                    groups[base + is_bias]["params"].append(p)
+        return tuple(groups)
