@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: cpu = the reference arm of the contract; cuda = stock PyTorch/cuDNN on the GPU (second baseline)")
     ap.add_argument("--ref-strict-fp32", action="store_true", help="--ref-device cuda: also time with cudnn.allow_tf32 = False")
+    ap.add_argument("--also-fast", action="store_true",
+                    help="after the parity-mode measurement, re-capture and time the step in the fast precision modes "
+                         "(fast_bwd, fast) and report them under 'fast_modes' (separate numbers, never the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -291,6 +294,23 @@ def main():
     run(1, True)
     ms_e2e = timed(args.steps, True)
 
+    fast_modes = None
+    if args.also_fast and L.PRECISION == "parity":
+        # plain bf16 is the "fast mode, reported separately".  Same step, same batch; only the precision field of
+        # the conv descriptors changes, so the graph is re-captured per mode.  The parity numbers above are already taken.
+        fast_modes = {}
+        for mode in ("fast_bwd", "fast"):
+            L.PRECISION = mode
+            stepper._graph = None
+            run(1, False)
+            if use_graph:
+                stepper.capture(dev_batch)
+            run(args.warmup, False)
+            ms_f = timed(args.steps, False)
+            fast_modes[mode] = {"value": crops_per_step * args.steps / (ms_f / 1e3), "unit": "crops/s", "ms_per_step": ms_f / args.steps}
+        L.PRECISION = "parity"
+        stepper._graph = None
+
     value = crops_per_step * args.steps / (ms / 1e3)
     e2e = crops_per_step * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host)
@@ -333,6 +353,8 @@ def main():
             "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline}
+    if fast_modes is not None:
+        line["fast_modes"] = fast_modes
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import sac_oracle as O
