@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash profiles/run_r2_first.sh'
 # Everything lands in gpurun_out/ (r2a_*).  Each step has its own timeout; a trap in an unverified kernel only fails that step.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
-O=gpurun_out
+O=gpurun_out; mkdir -p $O
 # 0. the verified suite must still be green (default path; the unverified tests stay skipped here)
 timeout 150 python -m pytest tests -m gpu -x -q > $O/r2a_pytest_default.log 2>&1; echo "default suite rc=$?"; tail -2 $O/r2a_pytest_default.log
 # 1. unverified paths, one file at a time so that one failure does not hide the others
