@@ -27,6 +27,9 @@ def lib():
         if not os.path.isfile(LIB_PATH):
             raise SacbError("libsac_b200.so not built (run `python -c 'import __graft_entry__ as g; g.build()'`): " + LIB_PATH)
         _lib = C.CDLL(LIB_PATH)
+        if hasattr(_lib, "sacb_emul_marker"):
+            _lib = None
+            raise SacbError("refusing to load a host emulation library (tests/cpu_emul) as libsac_b200: " + LIB_PATH)
         _lib.sacb_last_error.restype = C.c_char_p
         _lib.sacb_launch_count.restype = C.c_int64
         for f in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):

@@ -1,0 +1,17 @@
+// TEST INFRASTRUCTURE: error reporting for the host-emulated kernels (the product's lives in csrc/sacb_api.cu).
+#include "cuda_emul.h"
+
+namespace sacb {
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace sacb
+
+extern "C" const char* sacb_last_error(void) { return sacb::g_err; }
+extern "C" int64_t sacb_launch_count(void) { return (int64_t)sacb::g_launches.load(); }
+extern "C" int sacb_emul_marker(void) { return 1; }   // the product library does not export this symbol
