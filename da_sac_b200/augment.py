@@ -156,8 +156,8 @@ class TargetAugmenter(object):
         return torch.tensor(rows, dtype=torch.float32), torch.cat(A, 0), torch.cat(Ai, 0)
 
     def __call__(self, base_u8, base_mask=None, base_label=None, params=None):
-        assert base_u8.is_cuda and base_u8.dtype == torch.uint8 and base_u8.dim() == 4 and base_u8.shape[-1] == 3, \
-            "base crops: uint8 [G,H,W,3] on the device"
+        assert base_u8.dtype == torch.uint8 and base_u8.dim() == 4 and base_u8.shape[-1] == 3, \
+            "base crops: uint8 [G,H,W,3] on the device"           # "on the device" is enforced by L.ptr below
         G, H, W, _ = base_u8.shape
         assert (H, W) == self.hw
         dev = base_u8.device

@@ -6,8 +6,6 @@
 #include <stdint.h>
 
 #define SACB_DEVINL __device__ __forceinline__
-// kernel launch; tests/cpu_emul/cuda_emul.h gives the same spelling a host meaning (test infrastructure only)
-#define SACB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 
 namespace sacb {
 

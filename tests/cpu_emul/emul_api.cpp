@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE: error reporting for the host-emulated kernels (the product's lives in csrc/sacb_api.cu).
 #include "cuda_emul.h"
+#include "sacb.h"
 
 namespace sacb {
 std::atomic<long long> g_launches{0};
@@ -14,4 +15,5 @@ void set_error(const char* fmt, ...) {
 
 extern "C" const char* sacb_last_error(void) { return sacb::g_err; }
 extern "C" int64_t sacb_launch_count(void) { return (int64_t)sacb::g_launches.load(); }
+extern "C" int sacb_abi_version(void) { return SACB_ABI_VERSION; }
 extern "C" int sacb_emul_marker(void) { return 1; }   // the product library does not export this symbol

@@ -1,0 +1,94 @@
+"""TEST INFRASTRUCTURE: runs the unmodified GPU parity tests in the GPU-less container.
+
+`emulated_gpu()` (a context manager) makes the product's Python layer talk to tests/cpu_emul/_build/libsacb_emul.so instead of
+libsac_b200.so: the streaming kernels execute from their real CUDA source under the host emulation (cuda_emul.h), the two
+tensor-core entry points through the checker's plain-loop model (gemm_model.cpp).  "cuda" tensors are created on the CPU
+(a TorchFunctionMode rewrites device arguments), so a GPU test function can be called as it is.
+
+What a green run here proves: the host-side schedules (engine.py, engine_abn.py, models/) and the streaming kernels'
+indexing / arithmetic.  What it does not prove: anything about the tcgen05 GEMM kernels, streams, graphs, or speed -- the GPU
+suite stays the parity gate.  The product never loads this library (da_sac_b200/lib.py refuses it)."""
+import contextlib
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import torch
+from torch.overrides import TorchFunctionMode
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMUL = os.path.join(HERE, "cpu_emul")
+SO = os.path.join(EMUL, "_build", "libsacb_emul.so")
+
+_lib = None
+
+
+def available():
+    return shutil.which("g++") is not None and shutil.which("make") is not None
+
+
+def emul_lib():
+    global _lib
+    if _lib is None:
+        r = subprocess.run(["make", "-C", EMUL], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lib = C.CDLL(SO)
+        assert lib.sacb_emul_marker() == 1
+        lib.sacb_last_error.restype = C.c_char_p
+        lib.sacb_launch_count.restype = C.c_int64
+        for f in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):
+            getattr(lib, f).restype = C.c_size_t
+        lib.sacb_bn_moments_partial_elems.restype = C.c_size_t
+        lib.sacb_bn_moments_partial_elems.argtypes = [C.c_int64, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def _is_cuda(d):
+    try:
+        return d is not None and not isinstance(d, (bool, int)) and torch.device(d).type == "cuda"
+    except (TypeError, RuntimeError):
+        return False
+
+
+class _CudaToCpu(TorchFunctionMode):
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = dict(kwargs or {})
+        if func in (torch.Tensor.cuda,):
+            return args[0]
+        if _is_cuda(kwargs.get("device")):
+            kwargs["device"] = "cpu"
+        if func is torch.Tensor.to and len(args) > 1 and isinstance(args[1], (str, torch.device)) and _is_cuda(args[1]):
+            args = (args[0], "cpu") + tuple(args[2:])
+        if func is torch.Tensor.pin_memory:
+            return args[0]
+        return func(*args, **kwargs)
+
+
+@contextlib.contextmanager
+def emulated_gpu():
+    from da_sac_b200 import lib as L
+    lib = emul_lib()
+
+    def ptr(t):
+        if t is None:
+            return None
+        assert t.device.type == "cpu" and t.is_contiguous()
+        return C.c_void_p(t.data_ptr())
+
+    saved = {(L, k): getattr(L, k) for k in ("lib", "stream", "ptr", "dptr")}
+    saved[(torch.cuda, "synchronize")] = torch.cuda.synchronize
+    saved[(torch.cuda, "is_current_stream_capturing")] = torch.cuda.is_current_stream_capturing
+    L.lib = lambda: lib
+    L.stream = lambda: C.c_void_p(0)
+    L.ptr = ptr
+    L.dptr = lambda t: None if t is None else t.data_ptr()
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.is_current_stream_capturing = lambda: False
+    try:
+        with _CudaToCpu():
+            yield lib
+    finally:
+        for (obj, k), v in saved.items():
+            setattr(obj, k, v)

@@ -1,0 +1,99 @@
+"""Runs the GPU parity tests -- the SAME test functions, unmodified -- in the GPU-less container on the host emulation library
+(tests/emul_harness.py: streaming kernels from their real CUDA source under tests/cpu_emul/cuda_emul.h, the two tensor-core
+entry points through the checker's plain-loop model).  A green run proves the host-side schedules and the streaming kernels
+against the goldens of the real reference; it says nothing about the tcgen05 kernels, which only `pytest -m gpu` on a B200 can.
+
+Most valuable for code that has not run on a B200 yet (tests/test_abn_gpu.py): its full iteration is executed here.
+
+The default selection keeps the CPU suite within a few minutes; SACB_EMUL_FULL=1 runs everything that can be emulated
+(about 25 minutes on 8 cores, dominated by the 30-step training test)."""
+import importlib
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import emul_harness as E
+
+pytestmark = pytest.mark.skipif(not E.available(), reason="no host toolchain for tests/cpu_emul")
+FULL = os.environ.get("SACB_EMUL_FULL") == "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# (module, test function, parametrisation ids to run by default: None = all, () = only under SACB_EMUL_FULL=1)
+SELECTION = [
+    ("test_conv_gpu", "test_conv_fprop_plain", None),                     # these five check gemm_model.cpp itself (vs torch fp64)
+    ("test_conv_gpu", "test_conv_fprop_fused_epilogue", None),
+    ("test_conv_gpu", "test_conv_fprop_mask_and_add_f32", None),
+    ("test_conv_gpu", "test_conv_aspp_head_nchw", None),
+    ("test_conv_gpu", "test_conv_wgrad", None),
+    ("test_step_gpu", "test_backbone_forward_matches_oracle", None),
+    ("test_step_gpu", "test_tail_labels_bit_exact_on_golden_teacher_logits", None),
+    ("test_step_gpu", "test_two_training_steps_match_reference_golden", None),
+    ("test_step_gpu", "test_vgg16_config1_two_steps_match_reference_golden", None),
+    ("test_step_gpu", "test_backward_matches_reference_given_golden_pseudo_labels", ()),
+    ("test_step_gpu", "test_source_pass_loss_ce_backward_matches_oracle", ()),
+    ("test_step_gpu", "test_fcn8s_two_steps_match_reference_golden", ()),
+    ("test_step_gpu", "test_fcn8s_dropout_train_mode_runs", ()),
+    ("test_step_gpu", "test_joint_source_target_step_matches_oracle", ()),
+    ("test_step_gpu", "test_training_reduces_the_loss_and_teacher_follows", ()),
+    ("test_variants_gpu", "test_tail_variant_labels_and_losses", None),
+    ("test_fractional_gpu", "test_whole_group_tail_unchanged_by_phase_split", None),
+    ("test_augment_gpu", "test_augment_matches_oracle_and_reference_golden", None),
+    ("test_abn_gpu", "test_bn_moments_survive_large_mean", None),
+    ("test_abn_gpu", "test_abn_iteration_matches_reference_golden", None),   # never run on a B200: the reason this file exists
+]
+
+
+def _cases():
+    out = []
+    os.environ.setdefault("SACB_RUN_UNVERIFIED", "1")     # the skipif marks of the gated modules are evaluated at import
+    for mod, fn, ids in SELECTION:
+        f = getattr(importlib.import_module(mod), fn)
+        params = [m for m in getattr(f, "pytestmark", []) if m.name == "parametrize"]
+        if not params:
+            variants = [((), {})]
+        else:
+            assert len(params) == 1, "stacked parametrisations are not handled"
+            names = [n.strip() for n in params[0].args[0].split(",")]
+            variants = [((), dict(zip(names, v if len(names) > 1 else (v,)))) for v in params[0].args[1]]
+        for i, (_, kw) in enumerate(variants):
+            default = ids is None or i in ids
+            out.append(pytest.param(mod, fn, kw, id="%s::%s[%d]" % (mod, fn, i),
+                                    marks=[] if (default or FULL) else [pytest.mark.skip(reason="SACB_EMUL_FULL=1 runs it")]))
+    return out
+
+
+@pytest.fixture(scope="module")
+def emul():
+    torch.set_num_threads(8)
+    with E.emulated_gpu() as lib:
+        yield lib
+
+
+_fixture_cache = {}
+
+
+def _fixture(mod, name, request):
+    if name == "golden":
+        return np.load(os.path.join(ROOT, "tests", "golden", "sac_resnet101_tiny.npz"), allow_pickle=False)
+    if name in ("monkeypatch", "tmp_path"):
+        return request.getfixturevalue(name)
+    key = (mod.__name__, name)
+    if key not in _fixture_cache:                          # module-scoped fixtures of the GPU test modules (e.g. `net`)
+        _fixture_cache[key] = getattr(mod, name).__wrapped__()
+    return _fixture_cache[key]
+
+
+@pytest.mark.parametrize("mod,fn,kw", _cases())
+def test_gpu_test_on_the_emulation_library(emul, request, mod, fn, kw):
+    m = importlib.import_module(mod)
+    f = getattr(m, fn)
+    kw = dict(kw)
+    for name in inspect.signature(f).parameters:
+        if name not in kw:
+            kw[name] = _fixture(m, name, request)
+    n0 = emul.sacb_launch_count()
+    f(**kw)
+    assert emul.sacb_launch_count() > n0, "the test did not reach the library"
