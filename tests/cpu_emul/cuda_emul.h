@@ -27,7 +27,10 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <string>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -78,14 +81,64 @@ namespace cuda_emul {
 
 constexpr size_t STACK_BYTES = 96 * 1024;
 
+// Context switch between the scheduler and a fiber.  glibc's swapcontext makes a system call (signal mask) per switch, which
+// dominated the barrier-heavy kernels; on x86-64 a hand-written switch of the callee-saved registers is used instead.
+#if defined(__x86_64__) && !defined(SACB_EMUL_UCONTEXT)
+extern "C" void sacb_emul_switch(void** save_sp, void* new_sp);
+asm(R"(
+.text
+.weak sacb_emul_switch
+.type sacb_emul_switch,@function
+sacb_emul_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size sacb_emul_switch,.-sacb_emul_switch
+)");
+struct Ctx {
+  void* sp = nullptr;
+  void init(char* stack, size_t bytes, void (*entry)()) {
+    uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+    void** p = (void**)top;
+    *--p = nullptr;                 // return address of `entry` (it never returns)
+    *--p = (void*)entry;            // popped by the `ret` of the first switch
+    for (int i = 0; i < 6; ++i) *--p = nullptr;
+    sp = (void*)p;
+  }
+};
+inline void ctx_switch(Ctx& from, Ctx& to) { sacb_emul_switch(&from.sp, to.sp); }
+#else
+struct Ctx {
+  ucontext_t uc;
+  void init(char* stack, size_t bytes, void (*entry)()) {
+    getcontext(&uc);
+    uc.uc_stack.ss_sp = stack; uc.uc_stack.ss_size = bytes; uc.uc_link = nullptr;
+    makecontext(&uc, entry, 0);
+  }
+};
+inline void ctx_switch(Ctx& from, Ctx& to) { swapcontext(&from.uc, &to.uc); }
+#endif
+
 struct Fiber {
-  ucontext_t ctx;
+  Ctx ctx;
   uint3 tid;
   bool done;
 };
 
 struct BlockState {              // one per OS worker thread: the block it is running
-  ucontext_t sched;
+  Ctx sched;
   std::vector<Fiber> fibers;
   char* stacks = nullptr;
   size_t stacks_n = 0;
@@ -115,7 +168,7 @@ inline void yield() {
   BlockState* bs = t_bs;
   if (bs->direct) die("synchronisation primitive reached in direct mode (the first block of this launch never synchronised)");
   bs->yields++;
-  swapcontext(&bs->fibers[bs->cur].ctx, &bs->sched);
+  ctx_switch(bs->fibers[bs->cur].ctx, bs->sched);
 }
 
 inline void release_block_barrier(BlockState* bs) { bs->bar_count = 0; bs->bar_gen++; bs->progress = true; }
@@ -163,7 +216,7 @@ inline void fiber_entry() {
   bs->warp_live[w]--;
   if (bs->live > 0 && bs->bar_count == bs->live) release_block_barrier(bs);          // exited threads do not hold a barrier
   if (bs->warp_live[w] > 0 && bs->warp_count[w] == bs->warp_live[w]) release_warp_barrier(bs, w);
-  swapcontext(&f.ctx, &bs->sched);
+  ctx_switch(f.ctx, bs->sched);
   die("finished fiber resumed");
 }
 
@@ -184,11 +237,7 @@ inline long run_block_fibers(BlockState* bs, dim3 block) {
     f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
     f.done = false;
     bs->warp_live[t / 32]++;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = bs->stacks + (size_t)t * STACK_BYTES;
-    f.ctx.uc_stack.ss_size = STACK_BYTES;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    f.ctx.init(bs->stacks + (size_t)t * STACK_BYTES, STACK_BYTES, fiber_entry);
   }
   while (bs->live > 0) {
     bs->progress = false;
@@ -197,7 +246,7 @@ inline long run_block_fibers(BlockState* bs, dim3 block) {
       if (f.done) continue;
       bs->cur = t;
       t_threadIdx = f.tid;
-      swapcontext(&bs->sched, &f.ctx);
+      ctx_switch(bs->sched, f.ctx);
     }
     if (!bs->progress) die("deadlock: a barrier is not reached by every live thread of the block / warp");
   }
@@ -264,8 +313,32 @@ inline BlockState& my_block_state() { static thread_local BlockState bs; return 
 inline std::atomic<long long> g_emulated_launches{0};
 inline std::mutex g_launch_mutex;      // one grid at a time
 
+// SACB_EMUL_PROFILE=1: host seconds per kernel name, printed at exit (where the emulation spends its time, nothing more)
+struct Profile {
+  std::mutex m;
+  std::vector<std::pair<std::string, std::pair<double, long>>> rows;
+  bool on = getenv("SACB_EMUL_PROFILE") && getenv("SACB_EMUL_PROFILE")[0] == '1';
+  void add(const char* name, double s) {
+    std::lock_guard<std::mutex> lk(m);
+    for (auto& r : rows) if (r.first == name) { r.second.first += s; r.second.second++; return; }
+    rows.push_back({name, {s, 1}});
+  }
+  ~Profile() {
+    if (!on) return;
+    std::sort(rows.begin(), rows.end(), [](auto& a, auto& b) { return a.second.first > b.second.first; });
+    for (auto& r : rows) fprintf(stderr, "cuda_emul %9.3f s %7ld launches  %s\n", r.second.first, r.second.second, r.first.c_str());
+  }
+};
+inline Profile& profile() { static Profile p; return p; }
+struct ProfileScope {
+  const char* name; std::chrono::steady_clock::time_point t0;
+  explicit ProfileScope(const char* n) : name(n), t0(std::chrono::steady_clock::now()) {}
+  ~ProfileScope() { if (profile().on) profile().add(name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
+};
+
 template <class G, class B, class F>
-void run_grid(G grid_, B block_, size_t smem, bool syncing, F body_fn) {
+void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F body_fn) {
+  ProfileScope prof(name);
   const dim3 grid(grid_), block(block_);
   const std::function<void()> body(body_fn);
   if (block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024) {

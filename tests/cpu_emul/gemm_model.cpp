@@ -47,6 +47,7 @@ int geometry(int H, int W, int pad, int R, int S, int dil, int stride, int P, in
 }  // namespace
 
 extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void*) {
+  cuda_emul::ProfileScope prof("(model) sacb_conv_gemm");
   SACB_REQUIRE(d && d->size == sizeof(SacbConvGemm), "sacb_conv_gemm: bad descriptor size");
   SACB_REQUIRE(d->C % 64 == 0, "sacb_conv_gemm: C=%d must be a multiple of 64", d->C);
   SACB_REQUIRE(d->K % 32 == 0, "sacb_conv_gemm: K=%d must be a multiple of 32", d->K);
@@ -149,6 +150,7 @@ extern "C" int sacb_conv_wgrad_splits(const SacbConvWgrad* d) {
 }
 
 extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void*) {
+  cuda_emul::ProfileScope prof("(model) sacb_conv_wgrad");
   int splits; long long rps;
   if (int e = plan_splits(d, splits, rps)) return e;
   SACB_REQUIRE(d->precision == SACB_PRECISION_BF16X3 || d->precision == SACB_PRECISION_BF16, "sacb_conv_wgrad: unknown precision %d", d->precision);
@@ -161,10 +163,10 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void*) {
   const size_t plane = (size_t)kv * R * S * C;
   // one work item = (split, output row k): private accumulators, no races
   parallel_for((long long)splits * kv, 4, [&](long long i0, long long i1) {
-    std::vector<double> acc((size_t)R * S * C);
+    std::vector<float> acc((size_t)R * S * C);        // fp32 accumulation over one split's pixels, as the tensor core's TMEM
     for (long long it = i0; it < i1; ++it) {
       const int split = (int)(it / kv), k = (int)(it % kv);
-      std::fill(acc.begin(), acc.end(), 0.0);
+      std::fill(acc.begin(), acc.end(), 0.f);
       const long long m0 = split * rps, m1 = m0 + rps < M ? m0 + rps : M;
       for (long long m = m0; m < m1; ++m) {
         const float g = gf[(size_t)m * K + k];
@@ -177,13 +179,14 @@ extern "C" int sacb_conv_wgrad(const SacbConvWgrad* d, void*) {
             const int w = q * d->stride - d->pad + s * d->dil;
             if (w < 0 || w >= W) continue;
             const float* x = &xf[(((size_t)n * H + h) * W + w) * C];
-            double* a = &acc[(size_t)(r * S + s) * C];
-            for (int c = 0; c < C; ++c) a[c] += (double)g * (double)x[c];
+            float* a = &acc[(size_t)(r * S + s) * C];
+#pragma omp simd
+            for (int c = 0; c < C; ++c) a[c] += g * x[c];
           }
         }
       }
       float* out = d->dw + (size_t)split * plane + (size_t)k * R * S * C;
-      for (size_t j = 0; j < (size_t)R * S * C; ++j) out[j] = (float)acc[j];
+      memcpy(out, acc.data(), sizeof(float) * R * S * C);
     }
   });
   sacb::g_launches++;

@@ -106,8 +106,8 @@ def translate(src):
         out.append(src[pos:k0])
         kname = re.match(r"[A-Za-z_]\w*", kernel.split("::")[-1]).group(0)
         assert kname in known, "launch of a kernel not defined in this file: " + kname
-        out.append("cuda_emul::run_grid(%s, %s, %s, %s, [&]() { %s%s; });"
-                   % (cfg[0], cfg[1], cfg[2], "true" if kname in sync else "false", kernel, src[a0:a1]))
+        out.append("cuda_emul::run_grid(\"%s\", %s, %s, %s, %s, [&]() { %s%s; });"
+                   % (kname, cfg[0], cfg[1], cfg[2], "true" if kname in sync else "false", kernel, src[a0:a1]))
         out.append("\n" * (src[k0:a1 + 1].count("\n") - out[-1].count("\n")))      # keep the line numbers of the original
         pos = a1 + 1
     text = "".join(out)
