@@ -77,6 +77,10 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 
+// the CUDA built-ins: real (thread-local) objects, re-loaded by the scheduler whenever a fiber is resumed
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
 namespace cuda_emul {
 
 constexpr size_t STACK_BYTES = 96 * 1024;
@@ -133,54 +137,70 @@ inline void ctx_switch(Ctx& from, Ctx& to) { swapcontext(&from.uc, &to.uc); }
 
 struct Fiber {
   Ctx ctx;
-  uint3 tid;
+  uint3 tid, bid;
+  int cta;                       // rank of the fiber's CTA in its cluster
   bool done;
+  const void* waiting_on = nullptr;   // mbarrier the fiber spins on (deadlock report)
 };
 
-struct BlockState {              // one per OS worker thread: the block it is running
+// One per OS worker thread: the cluster (1..8 CTAs; 1 without a cluster launch) it is running.  Fibers are numbered
+// cta * threads_per_cta + linear thread id, warps = 32 consecutive fibers (threads_per_cta is a multiple of 32 for clusters).
+struct BlockState {
   Ctx sched;
   std::vector<Fiber> fibers;
   char* stacks = nullptr;
   size_t stacks_n = 0;
   int cur = -1;
-  int live = 0, bar_count = 0, bar_gen = 0;
+  int ncta = 1, nthreads = 0;
+  unsigned cluster_id = 0, ncluster = 1;
+  std::vector<int> live, bar_count, bar_gen;             // per CTA
+  int cl_live = 0, cl_count = 0, cl_gen = 0;             // cluster barrier
   std::vector<int> warp_live, warp_count, warp_gen;
   std::vector<uint64_t> slot;
   bool progress = false;
   long yields = 0;
   bool direct = false;           // plain function calls, no fibers
   const std::function<void()>* body = nullptr;
-  std::vector<char> dyn_smem;
+  // dynamic shared memory (1024-byte aligned) and tensor memory ([128 lanes][512 columns] fp32) of every CTA of the cluster
+  std::vector<char*> smem_base; std::vector<std::vector<char>> smem_store; size_t smem_bytes = 0;
+  std::vector<std::vector<float>> tmem; std::vector<int> tmem_next;
   ~BlockState() { free(stacks); }
 };
 
-inline thread_local uint3 t_threadIdx, t_blockIdx;
-inline thread_local dim3 t_blockDim, t_gridDim;
 inline thread_local BlockState* t_bs = nullptr;
 
 [[noreturn]] inline void die(const char* what) {
-  fprintf(stderr, "cuda_emul: %s (block %u,%u,%u thread %u,%u,%u)\n", what, t_blockIdx.x, t_blockIdx.y, t_blockIdx.z,
-          t_threadIdx.x, t_threadIdx.y, t_threadIdx.z);
+  fprintf(stderr, "cuda_emul: %s (block %u,%u,%u thread %u,%u,%u)\n", what, ::blockIdx.x, ::blockIdx.y, ::blockIdx.z,
+          ::threadIdx.x, ::threadIdx.y, ::threadIdx.z);
   abort();
 }
 
 inline void yield() {
   BlockState* bs = t_bs;
-  if (bs->direct) die("synchronisation primitive reached in direct mode (the first block of this launch never synchronised)");
+  if (bs->direct) die("synchronisation primitive reached in direct mode (translate.py classified the kernel as barrier-free)");
   bs->yields++;
   ctx_switch(bs->fibers[bs->cur].ctx, bs->sched);
 }
+inline int my_cta() { return t_bs->fibers[t_bs->cur].cta; }
 
-inline void release_block_barrier(BlockState* bs) { bs->bar_count = 0; bs->bar_gen++; bs->progress = true; }
+inline void release_block_barrier(BlockState* bs, int c) { bs->bar_count[c] = 0; bs->bar_gen[c]++; bs->progress = true; }
 inline void release_warp_barrier(BlockState* bs, int w) { bs->warp_count[w] = 0; bs->warp_gen[w]++; bs->progress = true; }
+inline void release_cluster_barrier(BlockState* bs) { bs->cl_count = 0; bs->cl_gen++; bs->progress = true; }
 
 inline void block_barrier() {
   BlockState* bs = t_bs;
   if (bs->direct) die("__syncthreads in direct mode");
-  const int gen = bs->bar_gen;
+  const int c = my_cta(), gen = bs->bar_gen[c];
   bs->progress = true;
-  if (++bs->bar_count == bs->live) { release_block_barrier(bs); return; }
-  while (bs->bar_gen == gen) yield();
+  if (++bs->bar_count[c] == bs->live[c]) { release_block_barrier(bs, c); return; }
+  while (bs->bar_gen[c] == gen) yield();
+}
+inline void cluster_barrier() {
+  BlockState* bs = t_bs;
+  const int gen = bs->cl_gen;
+  bs->progress = true;
+  if (++bs->cl_count == bs->cl_live) { release_cluster_barrier(bs); return; }
+  while (bs->cl_gen == gen) yield();
 }
 inline void warp_barrier() {
   BlockState* bs = t_bs;
@@ -200,7 +220,8 @@ inline T shfl_xor(T v, int lane_mask) {
   bs->slot[me] = bits;
   warp_barrier();
   T r = v;
-  if (partner < (int)bs->fibers.size() && !bs->fibers[partner].done) memcpy(&r, &bs->slot[partner], sizeof(T));
+  if (partner < (int)bs->fibers.size() && bs->fibers[partner].cta == bs->fibers[me].cta && !bs->fibers[partner].done)
+    memcpy(&r, &bs->slot[partner], sizeof(T));
   warp_barrier();
   return r;
 }
@@ -211,44 +232,84 @@ inline void fiber_entry() {
   Fiber& f = bs->fibers[bs->cur];
   f.done = true;
   bs->progress = true;
-  const int w = bs->cur / 32;
-  bs->live--;
+  const int w = bs->cur / 32, c = f.cta;
+  bs->live[c]--; bs->cl_live--;
   bs->warp_live[w]--;
-  if (bs->live > 0 && bs->bar_count == bs->live) release_block_barrier(bs);          // exited threads do not hold a barrier
+  if (bs->live[c] > 0 && bs->bar_count[c] == bs->live[c]) release_block_barrier(bs, c);   // exited threads do not hold a barrier
   if (bs->warp_live[w] > 0 && bs->warp_count[w] == bs->warp_live[w]) release_warp_barrier(bs, w);
+  if (bs->cl_live > 0 && bs->cl_count == bs->cl_live) release_cluster_barrier(bs);
   ctx_switch(f.ctx, bs->sched);
   die("finished fiber resumed");
 }
 
-// one block, fiber mode; returns the number of yields
-inline long run_block_fibers(BlockState* bs, dim3 block) {
-  const int n = (int)(block.x * block.y * block.z), nw = (n + 31) / 32;
+inline void report_deadlock(BlockState* bs) {
+  fprintf(stderr, "cuda_emul: DEADLOCK in cluster %u -- no live thread can make progress.  Waiting threads:\n", bs->cluster_id);
+  int shown = 0;
+  for (size_t i = 0; i < bs->fibers.size() && shown < 40; ++i) {
+    const Fiber& f = bs->fibers[i];
+    if (f.done) continue;
+    if (f.waiting_on || (i % 32) == 0) {
+      fprintf(stderr, "  cta %d warp %d lane %d: %s %p\n", f.cta, (int)((i % bs->nthreads) / 32), (int)(i % 32),
+              f.waiting_on ? "spins on mbarrier" : "at a block / warp / cluster barrier", f.waiting_on);
+      ++shown;
+    }
+  }
+  abort();
+}
+
+// one cluster of `ncta` CTAs (first block index `b0`, x-major), fiber mode; returns the number of yields
+inline long run_cluster_fibers(BlockState* bs, dim3 grid, dim3 block, long long b0, int ncta) {
+  const int nt = (int)(block.x * block.y * block.z), n = nt * ncta;
+  if (ncta > 1 && nt % 32) die("cluster launches need a multiple of 32 threads per CTA");
+  const int nw = (n + 31) / 32;
   if (bs->stacks_n < (size_t)n) {
     free(bs->stacks);
     bs->stacks = (char*)malloc((size_t)n * STACK_BYTES);
     bs->stacks_n = n;
   }
+  bs->ncta = ncta; bs->nthreads = nt;
   bs->fibers.resize(n);
   bs->slot.assign(n, 0);
   bs->warp_live.assign(nw, 0); bs->warp_count.assign(nw, 0); bs->warp_gen.assign(nw, 0);
-  bs->live = n; bs->bar_count = 0; bs->bar_gen = 0; bs->yields = 0; bs->direct = false;
-  for (int t = 0; t < n; ++t) {
-    Fiber& f = bs->fibers[t];
+  bs->live.assign(ncta, nt); bs->bar_count.assign(ncta, 0); bs->bar_gen.assign(ncta, 0);
+  bs->cl_live = n; bs->cl_count = 0; bs->cl_gen = 0;
+  bs->yields = 0; bs->direct = false;
+  bs->tmem_next.assign(ncta, 0);
+  for (int i = 0; i < n; ++i) {
+    Fiber& f = bs->fibers[i];
+    const int t = i % nt;
+    const long long b = b0 + i / nt;
+    f.cta = i / nt;
     f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-    f.done = false;
-    bs->warp_live[t / 32]++;
-    f.ctx.init(bs->stacks + (size_t)t * STACK_BYTES, STACK_BYTES, fiber_entry);
+    f.bid = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))};
+    f.done = false; f.waiting_on = nullptr;
+    bs->warp_live[i / 32]++;
+    f.ctx.init(bs->stacks + (size_t)i * STACK_BYTES, STACK_BYTES, fiber_entry);
   }
-  while (bs->live > 0) {
+  // SACB_EMUL_SCHED_SEED=s: every pass visits the WARPS in a pseudo-random order and lets a random half of them sit the pass
+  // out, so that producers / consumers / epilogue warps overtake each other differently from run to run (other legal
+  // interleavings of the same mbarrier protocol).  Warps, not threads: the lanes of a warp stay in step as on the device.
+  static const char* seed_env = getenv("SACB_EMUL_SCHED_SEED");
+  uint64_t rng = seed_env ? (uint64_t)atoll(seed_env) * 0x9E3779B97F4A7C15ull + (uint64_t)b0 + 1 : 0;
+  auto next_rand = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  std::vector<int> order(nw);
+  for (int w = 0; w < nw; ++w) order[w] = w;
+  int idle_passes = 0;
+  while (bs->cl_live > 0) {
     bs->progress = false;
-    for (int t = 0; t < n; ++t) {
-      Fiber& f = bs->fibers[t];
-      if (f.done) continue;
-      bs->cur = t;
-      t_threadIdx = f.tid;
-      ctx_switch(bs->sched, f.ctx);
+    if (rng) for (int w = nw - 1; w > 0; --w) std::swap(order[w], order[next_rand() % (uint64_t)(w + 1)]);
+    for (int k = 0; k < nw; ++k) {
+      if (rng && idle_passes == 0 && (next_rand() & 1)) continue;
+      for (int i = order[k] * 32; i < order[k] * 32 + 32 && i < n; ++i) {
+        Fiber& f = bs->fibers[i];
+        if (f.done) continue;
+        bs->cur = i;
+        ::threadIdx = f.tid; ::blockIdx = f.bid;
+        ctx_switch(bs->sched, f.ctx);
+      }
     }
-    if (!bs->progress) die("deadlock: a barrier is not reached by every live thread of the block / warp");
+    if (bs->progress) idle_passes = 0;
+    else if (!rng || ++idle_passes > 1) report_deadlock(bs);      // randomised: one full pass with nobody skipped must also be idle
   }
   return bs->yields;
 }
@@ -258,7 +319,7 @@ inline void run_block_direct(BlockState* bs, dim3 block) {
   for (unsigned z = 0; z < block.z; ++z)
     for (unsigned y = 0; y < block.y; ++y)
       for (unsigned x = 0; x < block.x; ++x) {
-        t_threadIdx = uint3{x, y, z};
+        ::threadIdx = uint3{x, y, z};
         (*bs->body)();
       }
 }
@@ -336,10 +397,10 @@ struct ProfileScope {
   ~ProfileScope() { if (profile().on) profile().add(name, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
 };
 
-template <class G, class B, class F>
-void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F body_fn) {
+// grid of clusters of `cl` CTAs (cl = 1: ordinary launch); clusters are spread over the pool, a cluster's CTAs share an OS thread
+template <class F>
+void run_grid_impl(const char* name, dim3 grid, dim3 block, size_t smem, bool syncing, int cl, F body_fn) {
   ProfileScope prof(name);
-  const dim3 grid(grid_), block(block_);
   const std::function<void()> body(body_fn);
   if (block.x * block.y * block.z == 0 || block.x * block.y * block.z > 1024) {
     fprintf(stderr, "cuda_emul: invalid block size %u x %u x %u\n", block.x, block.y, block.z);
@@ -349,21 +410,31 @@ void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F 
   std::lock_guard<std::mutex> lk(g_launch_mutex);
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   if (nblocks == 0) { fprintf(stderr, "cuda_emul: empty grid\n"); abort(); }
+  if (cl < 1 || nblocks % cl) { fprintf(stderr, "cuda_emul: grid of %lld blocks is not a multiple of the cluster size %d\n", nblocks, cl); abort(); }
+  const long long nclusters = nblocks / cl;
   const char* force = getenv("SACB_EMUL_FIBERS");
-  const bool fibers = syncing || (force && force[0] == '1');
-  auto run_block = [&](BlockState* bs, long long b) {
-    t_blockIdx = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))};
-    if (fibers) run_block_fibers(bs, block);
-    else run_block_direct(bs, block);
-  };
+  const bool fibers = syncing || cl > 1 || (force && force[0] == '1');
   auto setup = [&](BlockState* bs) {
-    t_bs = bs; t_blockDim = block; t_gridDim = grid; bs->body = &body;
-    if (bs->dyn_smem.size() < smem) bs->dyn_smem.resize(smem);
+    t_bs = bs; ::blockDim = block; ::gridDim = grid; bs->body = &body;
+    bs->ncluster = (unsigned)nclusters;
+    if ((int)bs->smem_store.size() < cl) { bs->smem_store.resize(cl); bs->tmem.resize(cl); }
+    bs->smem_base.assign(cl, nullptr); bs->smem_bytes = smem;
+    for (int c = 0; c < cl; ++c) {
+      if (bs->smem_store[c].size() < smem + 1024) bs->smem_store[c].resize(smem + 1024);
+      bs->smem_base[c] = (char*)(((uintptr_t)bs->smem_store[c].data() + 1023) & ~(uintptr_t)1023);
+    }
   };
-  if (nblocks < 4) {                                   // not worth waking the pool
+  auto run_cluster = [&](BlockState* bs, long long c) {
+    bs->cluster_id = (unsigned)c;
+    if (fibers) { run_cluster_fibers(bs, grid, block, c * cl, cl); return; }
+    ::blockIdx = uint3{(unsigned)(c % grid.x), (unsigned)((c / grid.x) % grid.y), (unsigned)(c / ((long long)grid.x * grid.y))};
+    bs->ncta = 1;
+    run_block_direct(bs, block);
+  };
+  if (nclusters < 4) {                                   // not worth waking the pool
     BlockState& bs = my_block_state();
     setup(&bs);
-    for (long long b = 0; b < nblocks; ++b) run_block(&bs, b);
+    for (long long c = 0; c < nclusters; ++c) run_cluster(&bs, c);
   } else {
     std::atomic<long long> next{0};
     const long long chunk = fibers ? 1 : 8;
@@ -371,9 +442,9 @@ void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F 
       BlockState& bs = my_block_state();
       setup(&bs);
       for (;;) {
-        const long long b0 = next.fetch_add(chunk);
-        if (b0 >= nblocks) break;
-        for (long long b = b0; b < b0 + chunk && b < nblocks; ++b) run_block(&bs, b);
+        const long long c0 = next.fetch_add(chunk);
+        if (c0 >= nclusters) break;
+        for (long long c = c0; c < c0 + chunk && c < nclusters; ++c) run_cluster(&bs, c);
       }
       t_bs = nullptr;
     });
@@ -381,12 +452,12 @@ void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F 
   t_bs = nullptr;
   g_emulated_launches++;
 }
+template <class G, class B, class F>
+void run_grid(const char* name, G grid_, B block_, size_t smem, bool syncing, F body_fn) {
+  run_grid_impl(name, dim3(grid_), dim3(block_), smem, syncing, 1, body_fn);
+}
 }  // namespace cuda_emul
 
-#define threadIdx (cuda_emul::t_threadIdx)
-#define blockIdx (cuda_emul::t_blockIdx)
-#define blockDim (cuda_emul::t_blockDim)
-#define gridDim (cuda_emul::t_gridDim)
 static inline void __syncthreads() { cuda_emul::block_barrier(); }
 template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
   if (mask != 0xffffffffu) cuda_emul::die("only full-warp shuffles are emulated");
@@ -394,6 +465,7 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lane_
 }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float sacb_bf16_to_float(uint16_t b) { unsigned u = ((unsigned)b) << 16; float f; memcpy(&f, &u, 4); return f; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
@@ -420,6 +492,10 @@ static inline float __bfloat162float(__nv_bfloat16 h) { return __uint_as_float((
 static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)}; }
 static inline float2 __bfloat1622float2(__nv_bfloat162 h) { return float2{__bfloat162float(h.x), __bfloat162float(h.y)}; }
 
+#ifdef SACB_EMUL_TC
+// tensor-core translation units include the (translated) sacb_common.cuh itself; the PTX wrappers come from cuda_emul_tc.h
+#include "cuda_emul_tc.h"
+#else
 namespace sacb {
 void set_error(const char* fmt, ...);
 // the helpers of sacb_common.cuh the streaming kernels use
@@ -440,3 +516,4 @@ static inline float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((un
   do {                                                                             \
     if (!(cond)) { sacb::set_error(__VA_ARGS__); return -1; }                      \
   } while (0)
+#endif  // SACB_EMUL_TC

@@ -1,0 +1,388 @@
+// TEST INFRASTRUCTURE -- functional model of the Blackwell primitives csrc/sacb_gemm.cu is written in, so that the GEMM kernels'
+// REAL source (warp roles, mbarrier protocol, tile scheduling, descriptors, epilogue) can execute in the GPU-less container.
+//
+// The kernels reach the hardware only through the small SACB_DEVINL wrappers around inline PTX (sacb_common.cuh and the top
+// of sacb_gemm.cu).  translate.py removes every function whose body contains `asm`; this header supplies functions of the same
+// names with the semantics stated below.  Everything is synchronous: a TMA load copies at issue time and then completes its
+// bytes on the mbarrier, an MMA computes at issue time, tcgen05.commit arrives immediately.  So this checks WHAT the protocol
+// computes and that it cannot deadlock under one legal interleaving; it cannot show races that need true asynchrony.
+//
+// Calibration: the semantics here are pinned by the GPU-verified default kernels -- their results under this model must equal
+// the plain-loop model of include/sacb.h (tests/test_emul_tc_cpu.py).  The variants that have not run on a B200 yet use the
+// same primitives in a different orchestration and are then checked the same way.
+//
+//   shared address  : (cta rank << 24) | byte offset from the CTA's 1024-aligned dynamic-smem base
+//   mbarrier        : 64-bit word {tx-count, pending arrivals, init count, phase}; phase completes when pending == 0 and tx == 0;
+//                     try_wait.parity(P) succeeds when the current phase bit != P
+//   TMA tiled       : box copied row by row, out-of-range coordinates read as zero, SWIZZLE_128B = 16-byte chunk index XOR (128-byte row & 7)
+//   TMA im2col      : `pixels` output pixels starting at base pixel (w, h, n), advancing by elementStrides through the
+//                     bounding box [lower, dim - 1 + upper], wrapping W -> H -> N; each pixel reads 64 channels at
+//                     (w + off_w, h + off_h); outside the tensor reads as zero
+//   UMMA smem desc  : start (>>4), SBO (>>4), SWIZZLE_128B, K-major only (MN-major operands -- the wgrad kernels -- are not modelled)
+//   tcgen05.mma     : D[lane = row][column] (+)= sum_k A[row][k] * B[col][k], 16 k per instruction, fp32 accumulation;
+//                     cta_group::2: rows 0..127 / 128..255 from CTA 0 / 1, B rows 0..N/2-1 / N/2..N-1 from CTA 0 / 1, D in both
+//   tcgen05.ld      : 32x32b.x32, the warp may only touch TMEM lanes 32 * (warp % 4) .. + 31 (checked)
+#pragma once
+#include <cxxabi.h>
+#include <dlfcn.h>
+#include <cuda.h>          // CUtensorMap, cuuint64_t, the CU_TENSOR_MAP_* enums, CUresult (driver TYPES only)
+
+#define __grid_constant__
+static inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emul::warp_barrier(); }
+[[noreturn]] static inline void __trap() { cuda_emul::die("__trap()"); }
+
+// ---------------------------------------------------------------- runtime API used by the host side of sacb_gemm.cu
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
+struct cudaLaunchAttributeValue { struct { unsigned x, y, z; } clusterDim; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute* attrs; unsigned numAttrs; };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+enum { cudaEnableDefault = 0 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int bytes) { return bytes <= 227 * 1024 ? cudaSuccess : 1; }
+static inline cudaError_t cudaDriverGetVersion(int* v) { *v = 13020; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+  const char* e = getenv("SACB_EMUL_SMS");          // small SM counts make multi-wave schedules reachable with small problems
+  *v = e ? atoi(e) : 148;
+  return cudaSuccess;
+}
+
+namespace cuda_emul {
+
+// ---------------------------------------------------------------- tensor maps (our own encoding inside the opaque 128 bytes)
+struct EmulMap {
+  uint32_t magic; uint8_t im2col, rank, swizzle, pad0;
+  const char* base;
+  uint32_t dims[4];
+  uint64_t strides[3];           // bytes, dims 1..3
+  uint32_t box[4];
+  uint8_t estr[4];
+  int16_t lower[2], upper[2];
+  uint16_t channels, pixels;
+};
+static_assert(sizeof(EmulMap) <= sizeof(CUtensorMap), "EmulMap must fit the opaque tensor map");
+constexpr uint32_t MAP_MAGIC = 0x7AC0B200u;
+
+inline CUresult encode_tiled(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                             const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                             CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  if (dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || rank < 2 || rank > 3 || il != CU_TENSOR_MAP_INTERLEAVE_NONE ||
+      sw != CU_TENSOR_MAP_SWIZZLE_128B || ((uintptr_t)base & 15) || box[0] * 2 != 128)
+    return CUDA_ERROR_INVALID_VALUE;
+  EmulMap e{}; e.magic = MAP_MAGIC; e.im2col = 0; e.rank = (uint8_t)rank; e.swizzle = 1; e.base = (const char*)base;
+  for (unsigned i = 0; i < rank; ++i) {
+    if (box[i] == 0 || box[i] > 256 || estr[i] != 1) return CUDA_ERROR_INVALID_VALUE;
+    e.dims[i] = (uint32_t)dims[i]; e.box[i] = box[i]; e.estr[i] = 1;
+  }
+  for (unsigned i = 0; i + 1 < rank; ++i) { if (strides[i] % 16) return CUDA_ERROR_INVALID_VALUE; e.strides[i] = strides[i]; }
+  memset(m, 0, sizeof(*m)); memcpy(m, &e, sizeof(e));
+  return CUDA_SUCCESS;
+}
+inline CUresult encode_im2col(CUtensorMap* m, CUtensorMapDataType dt, cuuint32_t rank, void* base, const cuuint64_t* dims,
+                              const cuuint64_t* strides, const int* lower, const int* upper, cuuint32_t channels, cuuint32_t pixels,
+                              const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill) {
+  if (dt != CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 || rank != 4 || il != CU_TENSOR_MAP_INTERLEAVE_NONE || sw != CU_TENSOR_MAP_SWIZZLE_128B ||
+      ((uintptr_t)base & 15) || channels * 2 != 128 || pixels == 0 || pixels > 1024)
+    return CUDA_ERROR_INVALID_VALUE;
+  EmulMap e{}; e.magic = MAP_MAGIC; e.im2col = 1; e.rank = 4; e.swizzle = 1; e.base = (const char*)base;
+  for (int i = 0; i < 4; ++i) { e.dims[i] = (uint32_t)dims[i]; e.estr[i] = (uint8_t)estr[i]; if (estr[i] == 0 || estr[i] > 8) return CUDA_ERROR_INVALID_VALUE; }
+  for (int i = 0; i < 3; ++i) { if (strides[i] % 16) return CUDA_ERROR_INVALID_VALUE; e.strides[i] = strides[i]; }
+  for (int i = 0; i < 2; ++i) {
+    if (lower[i] < -32768 || lower[i] > 32767 || upper[i] < -32768 || upper[i] > 32767) return CUDA_ERROR_INVALID_VALUE;
+    e.lower[i] = (int16_t)lower[i]; e.upper[i] = (int16_t)upper[i];
+  }
+  e.channels = (uint16_t)channels; e.pixels = (uint16_t)pixels;
+  memset(m, 0, sizeof(*m)); memcpy(m, &e, sizeof(e));
+  return CUDA_SUCCESS;
+}
+inline const EmulMap& map_of(const CUtensorMap* m) {
+  const EmulMap* e = reinterpret_cast<const EmulMap*>(m);
+  if (e->magic != MAP_MAGIC) die("tensor map was not produced by the emulated encoders");
+  return *e;
+}
+
+// ---------------------------------------------------------------- shared-memory addresses
+inline uint32_t shared_addr(const void* p) {
+  BlockState* bs = t_bs;
+  const char* q = (const char*)p;
+  for (int k = 0; k < bs->ncta; ++k) {
+    const int c = (my_cta() + k) % bs->ncta;
+    if (q >= bs->smem_base[c] && q < bs->smem_base[c] + bs->smem_bytes) return ((uint32_t)c << 24) | (uint32_t)(q - bs->smem_base[c]);
+  }
+  die("pointer is not in the dynamic shared memory of this cluster");
+}
+inline char* shared_ptr(uint32_t addr) {
+  BlockState* bs = t_bs;
+  const int c = (int)(addr >> 24);
+  const uint32_t off = addr & 0xFFFFFFu;
+  if (c >= bs->ncta || off >= bs->smem_bytes) die("shared::cluster address out of range");
+  return bs->smem_base[c] + off;
+}
+inline char* peer_ptr(const void* p, int cta) { return shared_ptr((shared_addr(p) & 0xFFFFFFu) | ((uint32_t)cta << 24)); }
+inline uint8_t* dyn_smem() { return (uint8_t*)t_bs->smem_base[my_cta()]; }
+// SWIZZLE_128B on a byte address inside shared memory: bits [4,7) ^= bits [7,10)
+inline uint32_t sw128(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+
+// ---------------------------------------------------------------- mbarrier
+struct MBar { int32_t tx; uint16_t pending; uint16_t init : 15, phase : 1; };
+static_assert(sizeof(MBar) == 8, "mbarrier state must fit its 64-bit word");
+inline void mbar_check(MBar* b) {
+  if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->init; }
+  t_bs->progress = true;
+}
+inline void mbar_do_arrive(MBar* b) {
+  if (b->init == 0) die("arrive on an mbarrier that was never initialised");
+  if (b->pending == 0) die("more arrivals than the mbarrier's count in one phase");
+  b->pending--; mbar_check(b);
+}
+inline void mbar_complete_tx(MBar* b, uint32_t bytes) {
+  if (b->init == 0) die("complete_tx on an mbarrier that was never initialised");
+  b->tx -= (int32_t)bytes; mbar_check(b);
+}
+
+// ---------------------------------------------------------------- TMA
+// copy one 128-byte line (64 bf16) of the box to shared row `row` of the tile at shared address `dst` (swizzled); src == nullptr: zeros
+inline void tma_put_line(uint32_t dst, int row, const char* src) {
+  for (int chunk = 0; chunk < 8; ++chunk) {
+    char* d = shared_ptr(sw128(dst + (uint32_t)row * 128u + (uint32_t)chunk * 16u));
+    if (src) memcpy(d, src + chunk * 16, 16); else memset(d, 0, 16);
+  }
+}
+inline void tma_tiled(const CUtensorMap* m, uint32_t dst, MBar* bar, int c0, int c1, int c2) {
+  const EmulMap& e = map_of(m);
+  if (e.im2col) die("tiled TMA load through an im2col tensor map");
+  if (dst & 1023u) die("TMA destination of a SWIZZLE_128B box must be 1024-byte aligned");
+  const int rows = (int)e.box[1];
+  if (e.rank == 3 && e.box[2] != 1) die("3-D boxes deeper than 1 are not modelled");
+  char line[128];
+  for (int r = 0; r < rows; ++r) {
+    const long long y = (long long)c1 + r;
+    const bool row_ok = y >= 0 && y < (long long)e.dims[1] && (e.rank < 3 || (c2 >= 0 && c2 < (int)e.dims[2]));
+    if (!row_ok) { tma_put_line(dst, r, nullptr); continue; }
+    const char* src = e.base + (size_t)y * e.strides[0] + (e.rank == 3 ? (size_t)c2 * e.strides[1] : 0);
+    for (int i = 0; i < 64; ++i) {
+      const long long x = (long long)c0 + i;
+      if (x >= 0 && x < (long long)e.dims[0]) memcpy(line + 2 * i, src + 2 * x, 2); else memset(line + 2 * i, 0, 2);
+    }
+    tma_put_line(dst, r, line);
+  }
+  mbar_complete_tx(bar, (uint32_t)rows * 128u);
+}
+// `row0`: first shared row written (multicast halves write rows [0, pixels) of their own destination)
+inline void tma_im2col(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int w, int h, int n, int off_w, int off_h) {
+  const EmulMap& e = map_of(m);
+  if (!e.im2col) die("im2col TMA load through a tiled tensor map");
+  if (dst & 1023u) die("TMA destination of a SWIZZLE_128B box must be 1024-byte aligned");
+  const int C = (int)e.dims[0], W = (int)e.dims[1], H = (int)e.dims[2], N = (int)e.dims[3];
+  const int w_lo = e.lower[0], h_lo = e.lower[1], w_hi = W - 1 + e.upper[0], h_hi = H - 1 + e.upper[1];
+  if (c < 0 || c + 64 > C) die("im2col load: channel block outside the tensor");
+  for (int px = 0; px < (int)e.pixels; ++px) {
+    const int x = w + off_w, y = h + off_h;
+    const bool ok = n >= 0 && n < N && h <= h_hi && w <= w_hi && x >= 0 && x < W && y >= 0 && y < H;
+    tma_put_line(dst, px, ok ? e.base + (size_t)n * e.strides[2] + (size_t)y * e.strides[1] + (size_t)x * e.strides[0] + (size_t)c * 2 : nullptr);
+    w += e.estr[1];
+    if (w > w_hi) { w = w_lo; h += e.estr[2]; if (h > h_hi) { h = h_lo; n += 1; } }
+  }
+  mbar_complete_tx(bar, (uint32_t)e.pixels * 128u);
+}
+
+// ---------------------------------------------------------------- tensor memory and MMA
+inline float* tmem_of(int cta) {
+  BlockState* bs = t_bs;
+  if (bs->tmem[cta].empty()) bs->tmem[cta].assign(128 * 512, 0.f);
+  return bs->tmem[cta].data();
+}
+inline uint32_t tmem_alloc_cols(int cta, int cols) {
+  BlockState* bs = t_bs;
+  if (cols < 32 || (cols & (cols - 1)) || cols > 512) die("tcgen05.alloc: column count must be a power of two in [32, 512]");
+  if (bs->tmem_next[cta] + cols > 512) die("tcgen05.alloc: tensor memory exhausted");
+  const uint32_t a = (uint32_t)bs->tmem_next[cta];
+  bs->tmem_next[cta] += cols;
+  // poison, so that reading an accumulator no MMA wrote is visible
+  float* t = tmem_of(cta);
+  for (int l = 0; l < 128; ++l) for (int k = 0; k < cols; ++k) t[l * 512 + a + k] = __builtin_nanf("");
+  return a;
+}
+struct SmemDesc { uint32_t start, sbo; };
+inline SmemDesc decode_desc(uint64_t d) {
+  if (((d >> 61) & 7) != 2) die("UMMA descriptor: only SWIZZLE_128B is modelled");
+  if (((d >> 46) & 3) != 1) die("UMMA descriptor: version field must be 1 on sm_100");
+  return SmemDesc{(uint32_t)(d & 0x3FFF) << 4, (uint32_t)((d >> 32) & 0x3FFF) << 4};
+}
+// rows x 16 bf16 of a K-major SWIZZLE_128B operand tile in CTA `cta`
+inline void read_operand(int cta, const SmemDesc& d, int rows, float* out) {
+  for (int r = 0; r < rows; ++r)
+    for (int e = 0; e < 16; ++e) {
+      const uint32_t a = d.start + (uint32_t)(r >> 3) * d.sbo + (uint32_t)(r & 7) * 128u + (uint32_t)e * 2u;
+      uint16_t bits;
+      memcpy(&bits, shared_ptr(((uint32_t)cta << 24) | sw128(a)), 2);
+      out[r * 16 + e] = sacb_bf16_to_float(bits);
+    }
+}
+inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  BlockState* bs = t_bs;
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  if ((idesc >> 15) & 3) die("tcgen05.mma: MN-major operands (the wgrad kernels) are not modelled");
+  if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 1 || ((idesc >> 10) & 7) != 1) die("tcgen05.mma: expected bf16 x bf16 -> f32");
+  if (group == 1 ? (M != 128) : (M != 256)) die("tcgen05.mma: M must be 128 (cta_group::1) or 256 (cta_group::2) here");
+  if (N < 16 || N > 256 || N % 16) die("tcgen05.mma: invalid N");
+  if (group == 2 && (bs->ncta != 2 || my_cta() != 0)) die("cta_group::2 MMA must be issued by CTA 0 of a 2-CTA cluster");
+  if ((tmem_d >> 16) != 0) die("tcgen05.mma: accumulator must start at TMEM lane 0");
+  const uint32_t col0 = tmem_d & 0xFFFF;
+  if (col0 + (uint32_t)N > 512) die("tcgen05.mma: accumulator columns out of range");
+  const SmemDesc da = decode_desc(adesc), db = decode_desc(bdesc);
+  static thread_local std::vector<float> A, B;
+  A.resize(256 * 16); B.resize(256 * 16);
+  const int me = my_cta();
+  if (group == 1) {
+    read_operand(me, da, 128, A.data());
+    read_operand(me, db, N, B.data());
+  } else {
+    read_operand(0, da, 128, A.data()); read_operand(1, da, 128, A.data() + 128 * 16);
+    read_operand(0, db, N / 2, B.data()); read_operand(1, db, N / 2, B.data() + (N / 2) * 16);
+  }
+  for (int row = 0; row < M; ++row) {
+    float* t = tmem_of(group == 1 ? me : row / 128) + (size_t)(row % 128) * 512 + col0;
+    const float* a = A.data() + row * 16;
+    for (int n = 0; n < N; ++n) {
+      const float* b = B.data() + n * 16;
+      float s = 0.f;
+      for (int e = 0; e < 16; ++e) s += a[e] * b[e];
+      t[n] = accumulate ? t[n] + s : s;
+    }
+  }
+  bs->progress = true;
+}
+
+void set_last_kernel(const char* name);      // emul_api.cpp
+}  // namespace cuda_emul
+
+static inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** f, int, cudaDriverEntryPointQueryResult* q) {
+  *f = nullptr;
+  if (!strcmp(name, "cuTensorMapEncodeTiled")) *f = (void*)&cuda_emul::encode_tiled;
+  if (!strcmp(name, "cuTensorMapEncodeIm2col")) *f = (void*)&cuda_emul::encode_im2col;
+  if (q) *q = cudaDriverEntryPointSuccess;
+  return *f ? cudaSuccess : 1;
+}
+template <class... KA, class... A>
+static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(KA...), A&&... args) {
+  int cl = 1;
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) {
+      if (cfg->attrs[i].val.clusterDim.y != 1 || cfg->attrs[i].val.clusterDim.z != 1) return 1;
+      cl = (int)cfg->attrs[i].val.clusterDim.x;
+    }
+  // the instantiation's name, for the profile and for tests that must know WHICH variant ran
+  static thread_local char name[256];
+  Dl_info info;
+  snprintf(name, sizeof(name), "(tcgen05 kernel)");
+  if (dladdr((void*)kernel, &info) && info.dli_sname) {
+    int st = 0;
+    char* dm = abi::__cxa_demangle(info.dli_sname, nullptr, nullptr, &st);
+    if (st == 0 && dm) { snprintf(name, sizeof(name), "%s", dm); if (char* par = strchr(name, '(')) *par = 0; }
+    free(dm);
+  }
+  cuda_emul::set_last_kernel(name);
+  cuda_emul::run_grid_impl(name, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, true, cl, [&]() { kernel(args...); });
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------- the wrappers of sacb_common.cuh / sacb_gemm.cu (same names, same arguments)
+namespace sacb {
+using cuda_emul::MBar;
+inline MBar* as_bar(const void* p) { return reinterpret_cast<MBar*>(const_cast<void*>(p)); }
+inline uint32_t smem_u32(const void* p) { return cuda_emul::shared_addr(p); }
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  cuda_emul::shared_addr(bar);
+  MBar* b = as_bar(bar); b->tx = 0; b->pending = (uint16_t)count; b->init = (uint16_t)count; b->phase = 0;
+  cuda_emul::t_bs->progress = true;
+}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {        // mbarrier.arrive.expect_tx
+  MBar* b = as_bar(bar);
+  if (b->init == 0) cuda_emul::die("expect_tx on an mbarrier that was never initialised");
+  b->tx += (int32_t)bytes; cuda_emul::mbar_do_arrive(b);
+}
+inline void mbar_arrive(uint64_t* bar) { cuda_emul::mbar_do_arrive(as_bar(bar)); }
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return as_bar(bar)->phase != (parity & 1u); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  cuda_emul::BlockState* bs = cuda_emul::t_bs;
+  cuda_emul::Fiber& f = bs->fibers[bs->cur];
+  while (!mbar_try_wait(bar, parity)) { f.waiting_on = bar; cuda_emul::yield(); }
+  f.waiting_on = nullptr;
+  bs->progress = true;
+}
+inline void fence_barrier_init() {}
+inline void fence_proxy_async() {}
+inline void prefetch_tmap(const CUtensorMap* m) { cuda_emul::map_of(m); }
+inline void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) { cuda_emul::tma_tiled(m, smem_u32(dst), as_bar(bar), c0, c1, 0); }
+inline void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) { cuda_emul::tma_tiled(m, smem_u32(dst), as_bar(bar), c0, c1, c2); }
+inline void tma_load_im2col(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int h, int n, uint16_t ow, uint16_t oh) {
+  cuda_emul::tma_im2col(m, smem_u32(dst), as_bar(bar), c, w, h, n, ow, oh);
+}
+inline uint32_t cluster_ctarank() { return (uint32_t)cuda_emul::my_cta(); }
+inline uint32_t cluster_id_x() { return cuda_emul::t_bs->cluster_id; }
+inline uint32_t cluster_count_x() { return cuda_emul::t_bs->ncluster; }
+inline void cluster_sync_all() { cuda_emul::cluster_barrier(); }
+// multicast: the same CTA-relative destination and mbarrier in every CTA of `mask`
+inline void tma_load_2d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  for (int c = 0; c < cuda_emul::t_bs->ncta; ++c)
+    if (mask >> c & 1) cuda_emul::tma_tiled(m, (smem_u32(dst) & 0xFFFFFFu) | ((uint32_t)c << 24), as_bar(cuda_emul::peer_ptr(bar, c)), c0, c1, 0);
+}
+inline void tma_load_im2col_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int h, int n, uint16_t ow, uint16_t oh, uint16_t mask) {
+  for (int k = 0; k < cuda_emul::t_bs->ncta; ++k)
+    if (mask >> k & 1) cuda_emul::tma_im2col(m, (smem_u32(dst) & 0xFFFFFFu) | ((uint32_t)k << 24), as_bar(cuda_emul::peer_ptr(bar, k)), c, w, h, n, ow, oh);
+}
+inline void tc_commit(uint64_t* bar) { cuda_emul::mbar_do_arrive(as_bar(bar)); }
+inline void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  for (int c = 0; c < cuda_emul::t_bs->ncta; ++c) if (mask >> c & 1) cuda_emul::mbar_do_arrive(as_bar(cuda_emul::peer_ptr(bar, c)));
+}
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  cuda_emul::mma_f16(1, tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <int COLS> inline void tmem_alloc(uint32_t* slot) {       // .sync.aligned: the whole warp executes it
+  cuda_emul::warp_barrier();
+  if ((cuda_emul::t_bs->cur & 31) == 0) *slot = cuda_emul::tmem_alloc_cols(cuda_emul::my_cta(), COLS);
+  cuda_emul::warp_barrier();
+}
+template <int COLS> inline void tmem_dealloc(uint32_t) { cuda_emul::warp_barrier(); }
+inline void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+  cuda_emul::BlockState* bs = cuda_emul::t_bs;
+  const int lane = bs->cur & 31, warp = (bs->cur % bs->nthreads) / 32;
+  const uint32_t lane0 = addr >> 16, col = addr & 0xFFFF;
+  if (lane0 != (uint32_t)(32 * (warp % 4))) cuda_emul::die("tcgen05.ld: a warp may only read the TMEM lanes of its own quadrant (32 * (warp % 4))");
+  if (col + 32 > 512) cuda_emul::die("tcgen05.ld: columns out of range");
+  const float* t = cuda_emul::tmem_of(cuda_emul::my_cta()) + (size_t)(lane0 + lane) * 512 + col;
+  memcpy(r, t, 32 * sizeof(float));
+}
+inline void tmem_ld_wait() {}
+inline bool elect_one() { return (cuda_emul::t_bs->cur & 31) == 0; }
+// --- sacb_gemm.cu
+inline void stg256(void* p, const uint32_t (&v)[8]) { if ((uintptr_t)p & 31) cuda_emul::die("st.global.v8: 32-byte alignment"); memcpy(p, v, 32); }
+inline void ldg256(const void* p, uint32_t (&v)[8]) { if ((uintptr_t)p & 31) cuda_emul::die("ld.global.v8: 32-byte alignment"); memcpy(v, p, 32); }
+inline uint4 lds128(const uint8_t* p) { cuda_emul::shared_addr(p); uint4 v; memcpy(&v, p, 16); return v; }
+inline void tma2_load_im2col(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c, int w, int h, int n, uint16_t ow, uint16_t oh) {
+  cuda_emul::tma_im2col(m, smem_u32(dst), as_bar(cuda_emul::shared_ptr(bar_addr)), c, w, h, n, ow, oh);
+}
+inline void tma2_load_3d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1, int c2) {
+  cuda_emul::tma_tiled(m, smem_u32(dst), as_bar(cuda_emul::shared_ptr(bar_addr)), c0, c1, c2);
+}
+inline void tma2_load_2d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
+  cuda_emul::tma_tiled(m, smem_u32(dst), as_bar(cuda_emul::shared_ptr(bar_addr)), c0, c1, 0);
+}
+inline void tc2_commit_mc(uint64_t* bar, uint16_t mask) { tc_commit_mc(bar, mask); }
+inline void tc2_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  cuda_emul::mma_f16(2, tmem_d, adesc, bdesc, idesc, accumulate);
+}
+inline void mbar_arrive_remote(uint64_t* bar, uint32_t cta) { cuda_emul::mbar_do_arrive(as_bar(cuda_emul::peer_ptr(bar, (int)cta))); }
+template <int COLS> inline void tmem2_alloc(uint32_t* slot) {      // cta_group::2: the same columns in both CTAs
+  cuda_emul::warp_barrier();
+  if ((cuda_emul::t_bs->cur & 31) == 0) *slot = cuda_emul::tmem_alloc_cols(cuda_emul::my_cta(), COLS);
+  cuda_emul::warp_barrier();
+}
+template <int COLS> inline void tmem2_dealloc(uint32_t) { cuda_emul::warp_barrier(); }
+}  // namespace sacb

@@ -72,6 +72,40 @@ def syncing_functions(src):
     return sync, set(bodies)
 
 
+STRIP_ALSO = {"mbar_wait", "smem_u32"}      # no asm inside, but it spins without yielding: cuda_emul_tc.h has a fiber-aware one
+
+
+def strip_ptx_wrappers(src):
+    """remove the SACB_DEVINL functions whose body is inline PTX (cuda_emul_tc.h defines functions of the same names)"""
+    removed, out, pos = [], [], 0
+    for m in re.finditer(r"(?:^template\s*<[^>\n]*>\s*\n)?^SACB_DEVINL[^\n(]*?\b([A-Za-z_]\w*)\s*\(", src, flags=re.M):
+        if m.start() < pos:
+            continue
+        e = matching(src, m.end() - 1, "(", ")")
+        rest = re.match(r"\s*\{", src[e:])
+        if not rest:
+            continue
+        b1 = matching(src, e + rest.end() - 1, "{", "}")
+        body = src[e:b1]
+        if re.search(r"\basm\b", body) or m.group(1) in STRIP_ALSO:
+            out.append(src[pos:m.start()])
+            out.append("// [emulation] %s: see cuda_emul_tc.h" % m.group(1) + "\n" * src[m.start():b1].count("\n"))
+            removed.append(m.group(1))
+            pos = b1
+    out.append(src[pos:])
+    return "".join(out), removed
+
+
+def translate_tc(src):
+    """tensor-core translation units (sacb_common.cuh, sacb_gemm.cu): PTX wrappers out, dynamic shared memory from the emulator"""
+    src, removed = strip_ptx_wrappers(src)
+    src = re.sub(r"^#include\s+<(cuda_runtime|cuda_bf16|cuda)\.h>", r"// (\1.h: see cuda_emul.h / cuda_emul_tc.h)", src, flags=re.M)
+    src = re.sub(r"^#define SACB_DEVINL .*$", "// (SACB_DEVINL: see cuda_emul.h)", src, flags=re.M)
+    src = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)cuda_emul::dyn_smem();", src)
+    src = src.replace('#include "sacb_common.cuh"', '#include "sacb_common_emul.h"')
+    return src, removed
+
+
 def translate(src):
     sync, known = syncing_functions(src)
     out, pos = [], 0
@@ -116,8 +150,15 @@ def translate(src):
 
 
 if __name__ == "__main__":
-    with open(sys.argv[1]) as f:
+    tc = "--tc" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "--tc"]
+    with open(args[0]) as f:
         text = f.read()
-    with open(sys.argv[2], "w") as f:
-        f.write('#line 1 "%s"\n' % sys.argv[1])
-        f.write(translate(text))
+    if tc:
+        text, removed = translate_tc(text)
+        sys.stderr.write("translate.py --tc %s: %d PTX wrappers replaced (%s)\n" % (args[0], len(removed), ", ".join(removed)))
+    if "<<<" in text:
+        text = translate(text)
+    with open(args[1], "w") as f:
+        f.write('#line 1 "%s"\n' % args[0])
+        f.write(text)

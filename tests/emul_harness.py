@@ -19,7 +19,7 @@ from torch.overrides import TorchFunctionMode
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 EMUL = os.path.join(HERE, "cpu_emul")
-SO = os.path.join(EMUL, "_build", "libsacb_emul.so")
+SO = os.environ.get("SACB_EMUL_SO") or os.path.join(EMUL, "_build", "libsacb_emul.so")     # an ASan build: see cpu_emul/Makefile
 
 _lib = None
 
@@ -31,8 +31,9 @@ def available():
 def emul_lib():
     global _lib
     if _lib is None:
-        r = subprocess.run(["make", "-C", EMUL], capture_output=True, text=True)
-        assert r.returncode == 0, r.stdout + r.stderr
+        if not os.environ.get("SACB_EMUL_SO"):
+            r = subprocess.run(["make", "-C", EMUL], capture_output=True, text=True)
+            assert r.returncode == 0, r.stdout + r.stderr
         lib = C.CDLL(SO)
         assert lib.sacb_emul_marker() == 1
         lib.sacb_last_error.restype = C.c_char_p
