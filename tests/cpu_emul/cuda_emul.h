@@ -141,6 +141,11 @@ struct Fiber {
   int cta;                       // rank of the fiber's CTA in its cluster
   bool done;
   const void* waiting_on = nullptr;   // mbarrier the fiber spins on (deadlock report)
+  // what the fiber is blocked on, so that the scheduler can skip it without two context switches:
+  // a barrier generation counter (runnable once *gen != gen_seen) or a 64-bit word (runnable once (*word & mask) != value)
+  const int* gen = nullptr; int gen_seen = 0;
+  const uint64_t* word = nullptr; uint64_t mask = 0, value = 0;
+  bool blocked() const { return (gen && *gen == gen_seen) || (word && ((*word & mask) == value)); }
 };
 
 // One per OS worker thread: the cluster (1..8 CTAs; 1 without a cluster launch) it is running.  Fibers are numbered
@@ -193,14 +198,20 @@ inline void block_barrier() {
   const int c = my_cta(), gen = bs->bar_gen[c];
   bs->progress = true;
   if (++bs->bar_count[c] == bs->live[c]) { release_block_barrier(bs, c); return; }
+  Fiber& f = bs->fibers[bs->cur];
+  f.gen = &bs->bar_gen[c]; f.gen_seen = gen;
   while (bs->bar_gen[c] == gen) yield();
+  f.gen = nullptr;
 }
 inline void cluster_barrier() {
   BlockState* bs = t_bs;
   const int gen = bs->cl_gen;
   bs->progress = true;
   if (++bs->cl_count == bs->cl_live) { release_cluster_barrier(bs); return; }
+  Fiber& f = bs->fibers[bs->cur];
+  f.gen = &bs->cl_gen; f.gen_seen = gen;
   while (bs->cl_gen == gen) yield();
+  f.gen = nullptr;
 }
 inline void warp_barrier() {
   BlockState* bs = t_bs;
@@ -208,7 +219,10 @@ inline void warp_barrier() {
   const int w = bs->cur / 32, gen = bs->warp_gen[w];
   bs->progress = true;
   if (++bs->warp_count[w] == bs->warp_live[w]) { release_warp_barrier(bs, w); return; }
+  Fiber& f = bs->fibers[bs->cur];
+  f.gen = &bs->warp_gen[w]; f.gen_seen = gen;
   while (bs->warp_gen[w] == gen) yield();
+  f.gen = nullptr;
 }
 template <class T>
 inline T shfl_xor(T v, int lane_mask) {
@@ -282,7 +296,7 @@ inline long run_cluster_fibers(BlockState* bs, dim3 grid, dim3 block, long long 
     f.cta = i / nt;
     f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
     f.bid = uint3{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y))};
-    f.done = false; f.waiting_on = nullptr;
+    f.done = false; f.waiting_on = nullptr; f.gen = nullptr; f.word = nullptr;
     bs->warp_live[i / 32]++;
     f.ctx.init(bs->stacks + (size_t)i * STACK_BYTES, STACK_BYTES, fiber_entry);
   }
@@ -302,7 +316,7 @@ inline long run_cluster_fibers(BlockState* bs, dim3 grid, dim3 block, long long 
       if (rng && idle_passes == 0 && (next_rand() & 1)) continue;
       for (int i = order[k] * 32; i < order[k] * 32 + 32 && i < n; ++i) {
         Fiber& f = bs->fibers[i];
-        if (f.done) continue;
+        if (f.done || f.blocked()) continue;
         bs->cur = i;
         ::threadIdx = f.tid; ::blockIdx = f.bid;
         ctx_switch(bs->sched, f.ctx);

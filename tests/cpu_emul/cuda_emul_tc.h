@@ -18,7 +18,7 @@
 //   TMA im2col      : `pixels` output pixels starting at base pixel (w, h, n), advancing by elementStrides through the
 //                     bounding box [lower, dim - 1 + upper], wrapping W -> H -> N; each pixel reads 64 channels at
 //                     (w + off_w, h + off_h); outside the tensor reads as zero
-//   UMMA smem desc  : start (>>4), SBO (>>4), SWIZZLE_128B, K-major only (MN-major operands -- the wgrad kernels -- are not modelled)
+//   UMMA smem desc  : start (>>4), LBO (>>4), SBO (>>4), SWIZZLE_128B; K-major (fprop / dgrad) and MN-major (wgrad) operands, see read_operand
 //   tcgen05.mma     : D[lane = row][column] (+)= sum_k A[row][k] * B[col][k], 16 k per instruction, fp32 accumulation;
 //                     cta_group::2: rows 0..127 / 128..255 from CTA 0 / 1, B rows 0..N/2-1 / N/2..N-1 from CTA 0 / 1, D in both
 //   tcgen05.ld      : 32x32b.x32, the warp may only touch TMEM lanes 32 * (warp % 4) .. + 31 (checked)
@@ -178,11 +178,17 @@ inline void tma_im2col(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int
   if (dst & 1023u) die("TMA destination of a SWIZZLE_128B box must be 1024-byte aligned");
   const int C = (int)e.dims[0], W = (int)e.dims[1], H = (int)e.dims[2], N = (int)e.dims[3];
   const int w_lo = e.lower[0], h_lo = e.lower[1], w_hi = W - 1 + e.upper[0], h_hi = H - 1 + e.upper[1];
-  if (c < 0 || c + 64 > C) die("im2col load: channel block outside the tensor");
+  if (c < 0 || c % 8) die("im2col load: channel coordinate must be a non-negative multiple of 8 (16 bytes)");
+  // channels at or beyond C read as zero like any other out-of-range coordinate (the swap-mode wgrad tiles of a 192-channel
+  // tensor start their second box at channel 192; the kernel never stores those rows)
+  const int c_ok = c >= C ? 0 : (C - c < 64 ? C - c : 64);
+  char line[128];
   for (int px = 0; px < (int)e.pixels; ++px) {
     const int x = w + off_w, y = h + off_h;
-    const bool ok = n >= 0 && n < N && h <= h_hi && w <= w_hi && x >= 0 && x < W && y >= 0 && y < H;
-    tma_put_line(dst, px, ok ? e.base + (size_t)n * e.strides[2] + (size_t)y * e.strides[1] + (size_t)x * e.strides[0] + (size_t)c * 2 : nullptr);
+    const bool ok = c_ok > 0 && n >= 0 && n < N && h <= h_hi && w <= w_hi && x >= 0 && x < W && y >= 0 && y < H;
+    const char* src = ok ? e.base + (size_t)n * e.strides[2] + (size_t)y * e.strides[1] + (size_t)x * e.strides[0] + (size_t)c * 2 : nullptr;
+    if (ok && c_ok < 64) { memset(line, 0, 128); memcpy(line, src, (size_t)c_ok * 2); src = line; }
+    tma_put_line(dst, px, src);
     w += e.estr[1];
     if (w > w_hi) { w = w_lo; h += e.estr[2]; if (h > h_hi) { h = h_lo; n += 1; } }
   }
@@ -206,26 +212,40 @@ inline uint32_t tmem_alloc_cols(int cta, int cols) {
   for (int l = 0; l < 128; ++l) for (int k = 0; k < cols; ++k) t[l * 512 + a + k] = __builtin_nanf("");
   return a;
 }
-struct SmemDesc { uint32_t start, sbo; };
+struct SmemDesc { uint32_t start, lbo, sbo; };
 inline SmemDesc decode_desc(uint64_t d) {
   if (((d >> 61) & 7) != 2) die("UMMA descriptor: only SWIZZLE_128B is modelled");
   if (((d >> 46) & 3) != 1) die("UMMA descriptor: version field must be 1 on sm_100");
-  return SmemDesc{(uint32_t)(d & 0x3FFF) << 4, (uint32_t)((d >> 32) & 0x3FFF) << 4};
+  return SmemDesc{(uint32_t)(d & 0x3FFF) << 4, (uint32_t)((d >> 16) & 0x3FFF) << 4, (uint32_t)((d >> 32) & 0x3FFF) << 4};
 }
-// rows x 16 bf16 of a K-major SWIZZLE_128B operand tile in CTA `cta`
-inline void read_operand(int cta, const SmemDesc& d, int rows, float* out) {
-  for (int r = 0; r < rows; ++r)
-    for (int e = 0; e < 16; ++e) {
-      const uint32_t a = d.start + (uint32_t)(r >> 3) * d.sbo + (uint32_t)(r & 7) * 128u + (uint32_t)e * 2u;
-      uint16_t bits;
-      memcpy(&bits, shared_ptr(((uint32_t)cta << 24) | sw128(a)), 2);
-      out[r * 16 + e] = sacb_bf16_to_float(bits);
-    }
+// `count` rows (M or N index) x 16 k of a SWIZZLE_128B operand tile in CTA `cta`, out[row * sr + k * se].
+//   K-major : a row is 128 bytes of K (64 bf16); 8-row groups SBO apart; the descriptor start already points at this k16 slice
+//   MN-major: a 128-byte line holds 64 consecutive M/N elements at ONE k; 8 k-lines form a 1024-byte swizzle atom, atoms along K
+//             are SBO apart, the next 64 M/N elements LBO apart (csrc/sacb_gemm.cu: TMA boxes of [64 pixels][64 channels])
+// read in 16-byte chunks (8 bf16), the granularity of the swizzle
+inline void read_operand(int cta, const SmemDesc& d, int count, bool mn_major, float* out, int sr, int se) {
+  const uint32_t rank = (uint32_t)cta << 24;
+  uint16_t v[8];
+  if (!mn_major) {
+    for (int r = 0; r < count; ++r)
+      for (int c = 0; c < 2; ++c) {
+        memcpy(v, shared_ptr(rank | sw128(d.start + (uint32_t)(r >> 3) * d.sbo + (uint32_t)(r & 7) * 128u + (uint32_t)c * 16u)), 16);
+        for (int j = 0; j < 8; ++j) out[r * sr + (c * 8 + j) * se] = sacb_bf16_to_float(v[j]);
+      }
+  } else {
+    if (count % 8) die("MN-major operand: row count must be a multiple of 8");
+    for (int e = 0; e < 16; ++e)
+      for (int r0 = 0; r0 < count; r0 += 8) {
+        memcpy(v, shared_ptr(rank | sw128(d.start + (uint32_t)(r0 >> 6) * d.lbo + (uint32_t)(e >> 3) * d.sbo + (uint32_t)(e & 7) * 128u +
+                                          (uint32_t)(r0 & 63) * 2u)), 16);
+        for (int j = 0; j < 8; ++j) out[(r0 + j) * sr + e * se] = sacb_bf16_to_float(v[j]);
+      }
+  }
 }
 inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   BlockState* bs = t_bs;
   const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
-  if ((idesc >> 15) & 3) die("tcgen05.mma: MN-major operands (the wgrad kernels) are not modelled");
+  const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 1 || ((idesc >> 10) & 7) != 1) die("tcgen05.mma: expected bf16 x bf16 -> f32");
   if (group == 1 ? (M != 128) : (M != 256)) die("tcgen05.mma: M must be 128 (cta_group::1) or 256 (cta_group::2) here");
   if (N < 16 || N > 256 || N % 16) die("tcgen05.mma: invalid N");
@@ -234,24 +254,25 @@ inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, 
   const uint32_t col0 = tmem_d & 0xFFFF;
   if (col0 + (uint32_t)N > 512) die("tcgen05.mma: accumulator columns out of range");
   const SmemDesc da = decode_desc(adesc), db = decode_desc(bdesc);
-  static thread_local std::vector<float> A, B;
-  A.resize(256 * 16); B.resize(256 * 16);
+  static thread_local std::vector<float> A, Bt;             // A[row][16], Bt[16][N]
+  A.resize(256 * 16); Bt.resize(16 * 256);
   const int me = my_cta();
   if (group == 1) {
-    read_operand(me, da, 128, A.data());
-    read_operand(me, db, N, B.data());
+    read_operand(me, da, 128, a_mn, A.data(), 16, 1);
+    read_operand(me, db, N, b_mn, Bt.data(), 1, N);
   } else {
-    read_operand(0, da, 128, A.data()); read_operand(1, da, 128, A.data() + 128 * 16);
-    read_operand(0, db, N / 2, B.data()); read_operand(1, db, N / 2, B.data() + (N / 2) * 16);
+    read_operand(0, da, 128, a_mn, A.data(), 16, 1); read_operand(1, da, 128, a_mn, A.data() + 128 * 16, 16, 1);
+    read_operand(0, db, N / 2, b_mn, Bt.data(), 1, N); read_operand(1, db, N / 2, b_mn, Bt.data() + N / 2, 1, N);
   }
+  // per output element: acc = (((acc + a0 b0) + a1 b1) + ...) in fp32 -- one legal order; the same for every kernel variant
   for (int row = 0; row < M; ++row) {
     float* t = tmem_of(group == 1 ? me : row / 128) + (size_t)(row % 128) * 512 + col0;
     const float* a = A.data() + row * 16;
-    for (int n = 0; n < N; ++n) {
-      const float* b = B.data() + n * 16;
-      float s = 0.f;
-      for (int e = 0; e < 16; ++e) s += a[e] * b[e];
-      t[n] = accumulate ? t[n] + s : s;
+    if (!accumulate) for (int n = 0; n < N; ++n) t[n] = 0.f;
+    for (int e = 0; e < 16; ++e) {
+      const float ae = a[e];
+      const float* b = Bt.data() + e * N;
+      for (int n = 0; n < N; ++n) t[n] += ae * b[n];
     }
   }
   bs->progress = true;
@@ -310,8 +331,10 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return as_bar(bar)->
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   cuda_emul::BlockState* bs = cuda_emul::t_bs;
   cuda_emul::Fiber& f = bs->fibers[bs->cur];
+  // blocked while the phase bit (top bit of the little-endian state word) still equals `parity`
+  f.word = bar; f.mask = 1ull << 63; f.value = (uint64_t)(parity & 1u) << 63;
   while (!mbar_try_wait(bar, parity)) { f.waiting_on = bar; cuda_emul::yield(); }
-  f.waiting_on = nullptr;
+  f.waiting_on = nullptr; f.word = nullptr;
   bs->progress = true;
 }
 inline void fence_barrier_init() {}

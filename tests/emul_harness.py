@@ -22,6 +22,7 @@ EMUL = os.path.join(HERE, "cpu_emul")
 SO = os.environ.get("SACB_EMUL_SO") or os.path.join(EMUL, "_build", "libsacb_emul.so")     # an ASan build: see cpu_emul/Makefile
 
 _lib = None
+_libs = {}
 
 
 def available():
@@ -46,6 +47,23 @@ def emul_lib():
     return _lib
 
 
+def emul_lib_full():
+    """every kernel from its real source: the streaming units AND sacb_gemm.cu (on the primitive model of cuda_emul_tc.h)"""
+    if "full" not in _libs:
+        emul_lib()                                            # builds all libraries
+        lib = C.CDLL(os.path.join(os.path.dirname(SO), "libsacb_emul_full.so"))
+        assert lib.sacb_emul_marker() == 1
+        lib.sacb_last_error.restype = C.c_char_p
+        lib.sacb_launch_count.restype = C.c_int64
+        lib.sacb_emul_last_kernel.restype = C.c_char_p
+        for f in ("sacb_tail_part_sums_elems", "sacb_tail_probs_elems", "sacb_tail_pooled_elems"):
+            getattr(lib, f).restype = C.c_size_t
+        lib.sacb_bn_moments_partial_elems.restype = C.c_size_t
+        lib.sacb_bn_moments_partial_elems.argtypes = [C.c_int64, C.c_int]
+        _libs["full"] = lib
+    return _libs["full"]
+
+
 def _is_cuda(d):
     try:
         return d is not None and not isinstance(d, (bool, int)) and torch.device(d).type == "cuda"
@@ -68,9 +86,10 @@ class _CudaToCpu(TorchFunctionMode):
 
 
 @contextlib.contextmanager
-def emulated_gpu():
+def emulated_gpu(full=False):
+    """full=False: tensor-core entry points through the formula model (fast); full=True: through the real kernel source"""
     from da_sac_b200 import lib as L
-    lib = emul_lib()
+    lib = emul_lib_full() if full else emul_lib()
 
     def ptr(t):
         if t is None:

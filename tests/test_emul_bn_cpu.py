@@ -20,16 +20,10 @@ EMUL = os.path.join(HERE, "cpu_emul")
 
 @pytest.fixture(scope="module")
 def api():
-    if shutil.which("g++") is None or shutil.which("make") is None:
+    import emul_harness as E
+    if not E.available():
         pytest.skip("no host toolchain")
-    r = subprocess.run(["make", "-C", EMUL], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    lib = C.CDLL(os.path.join(EMUL, "_build", "libsacb_emul.so"))
-    lib.sacb_last_error.restype = C.c_char_p
-    lib.sacb_launch_count.restype = C.c_int64
-    lib.sacb_bn_moments_partial_elems.restype = C.c_size_t
-    lib.sacb_bn_moments_partial_elems.argtypes = [C.c_int64, C.c_int]
-    assert lib.sacb_emul_marker() == 1
+    lib = E.emul_lib()                                         # honours SACB_EMUL_SO (AddressSanitizer build)
 
     def ptr(t):
         if t is None:

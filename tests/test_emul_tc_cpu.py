@@ -62,7 +62,7 @@ def libs(tmp_path_factory):
 
     load("model", "libsacb_emul.so")
     load("base", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS)
-    load("cluster", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS, SACB_CLUSTER="1", SACB_PAIR="0")
+    load("cluster", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS, SACB_CLUSTER="1", SACB_PAIR="0", SACB_NO_BN256="1")
     load("nopair", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS, SACB_PAIR="0")
     load("staged", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS, SACB_EPI_STAGED="1")
     load("tsplit", "libsacb_emul_tc.so", SACB_EMUL_SMS=SMS, SACB_TAIL_SPLIT="1")
@@ -184,6 +184,55 @@ def test_fast_precision_instantiations_compute_hi_times_hi(libs, which, geom):
     assert not close(got["f32"], full["f32"], 1e-4)            # and it really is the lower-precision path
 
 
+def wgrad(lib, geom, seed=0, k_valid=None, precision=0, splits=0):
+    """sum of the split-K partial planes (the two libraries split differently; sacb_wgrad_finalize adds the planes in order)"""
+    N, H, W, Cc, K, R, s, d, pad = geom
+    P, Q = L.conv_out_hw(H, W, R, s, d, pad)
+    torch.manual_seed(seed)
+    xh, xl = split(torch.randn(N, H, W, Cc))
+    gh, gl = split(torch.randn(N, P, Q, K))
+    kv = K if k_valid is None else k_valid
+    desc = L.ConvWgrad(C.sizeof(L.ConvWgrad), N, H, W, Cc, K, kv, R, R, s, d, pad, P, Q, p(xh), p(xl), p(gh), p(gl), None, splits, precision)
+    n = lib.sacb_conv_wgrad_splits(C.byref(desc))
+    assert n > 0, lib.sacb_last_error()
+    dw = torch.full((n, kv, R * R, Cc), float("nan"))          # every element of every plane must be written
+    desc.dw = p(dw)
+    assert lib.sacb_conv_wgrad(C.byref(desc), None) == 0, lib.sacb_last_error()
+    return dw.sum(0), n
+
+
+WGRAD = [   # (library, geometry, k_valid, splits, expected kernel); MN-major operands, split-K planes
+    ("base", (2, 17, 17, 64, 64, 3, 1, 1, 1), None, 0, "conv_wgrad_kernel<64, 1, false>"),
+    ("base", (2, 17, 17, 128, 128, 3, 1, 2, 2), None, 3, "conv_wgrad_kernel<128, 1, false>"),
+    ("base", (2, 19, 23, 64, 128, 3, 2, 1, 1), None, 0, "conv_wgrad_kernel<64, 1, false>"),            # stride 2, ragged
+    ("base", (2, 9, 9, 128, 768, 1, 1, 1, 0), 19, 0, "conv_wgrad_kernel<64, 1, false>"),                # swap: few output channels (ASPP)
+    ("base", (1, 20, 20, 256, 256, 3, 1, 2, 2), None, 0, "conv_wgrad_pair_kernel<false>"),
+    ("base", (1, 33, 33, 512, 256, 1, 1, 1, 0), None, 4, "conv_wgrad_pair_kernel<false>"),
+    ("nopair", (1, 20, 20, 256, 256, 3, 1, 1, 1), None, 2, "conv_wgrad_kernel<256, 1, false>"),
+    ("cluster", (2, 17, 17, 256, 128, 3, 1, 1, 1), None, 0, "conv_wgrad_kernel<128, 2, false>"),        # multicast row operand
+    ("base", (2, 17, 17, 192, 64, 1, 1, 1, 0), None, 0, "conv_wgrad_kernel<64, 1, false>"),             # swap + a channel box past C
+]
+
+
+@pytest.mark.parametrize("which,geom,kv,splits,kernel", WGRAD)
+def test_verified_wgrad_kernels_on_the_primitive_model_match_the_formula_model(libs, which, geom, kv, splits, kernel):
+    ref, _ = wgrad(libs["model"], geom, k_valid=kv)
+    got, n = wgrad(libs[which], geom, k_valid=kv, splits=splits)
+    assert libs[which].sacb_emul_last_kernel().decode().endswith(kernel), libs[which].sacb_emul_last_kernel()
+    assert splits == 0 or n <= splits
+    assert close(got, ref, 2e-5)
+
+
+@pytest.mark.parametrize("which,geom", [("base", (2, 17, 17, 64, 64, 1, 1, 1, 0)), ("base", (3, 33, 33, 256, 128, 3, 1, 2, 2)),
+                                        ("base", (2, 17, 17, 512, 256, 1, 1, 1, 0)), ("nopair", (1, 20, 20, 256, 256, 3, 1, 1, 1))])
+def test_fast_precision_wgrad_instantiations_compute_hi_times_hi(libs, which, geom):
+    ref, _ = wgrad(libs["model"], geom, precision=1)
+    got, _ = wgrad(libs[which], geom, precision=1)
+    assert "true" in libs[which].sacb_emul_last_kernel().decode()
+    assert close(got, ref, 2e-5)
+    assert not close(got, wgrad(libs[which], geom, precision=0)[0], 1e-4)
+
+
 def test_randomised_warp_schedules_do_not_change_results_or_deadlock(libs):
     """other legal interleavings of the mbarrier protocol: the scheduler visits warps in random order / lets half of them idle"""
     import subprocess, sys
@@ -192,7 +241,7 @@ import sys, os
 sys.path.insert(0, %r); sys.path.insert(0, %r)
 os.environ["SACB_RUN_UNVERIFIED"] = "1"
 import torch, pytest
-sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", %r, "-k", "staging_variant or tail_split_variant"]))
+sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", %r, "-k", "staging_variant or tail_split_variant or wgrad_kernels"]))
 ''' % (os.path.dirname(E.HERE), E.HERE, os.path.abspath(__file__))
     for seed in ("1", "7"):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SACB_EMUL_SCHED_SEED=seed), capture_output=True, text=True,
