@@ -169,6 +169,13 @@ struct BlockState {
   // dynamic shared memory (1024-byte aligned) and tensor memory ([128 lanes][512 columns] fp32) of every CTA of the cluster
   std::vector<char*> smem_base; std::vector<std::vector<char>> smem_store; size_t smem_bytes = 0;
   std::vector<std::vector<float>> tmem; std::vector<int> tmem_next;
+  // SACB_EMUL_ASYNC=1 (cuda_emul_tc.h): TMA copies land a random number of scheduler passes after they were issued and MMAs
+  // execute only when a tcgen05.commit forces them -- the latest the hardware may legally be
+  struct Deferred { int due; std::function<void()> op; const void* bar; };
+  std::vector<Deferred> late_tma;                        // timed: a thread is already waiting on the barrier
+  std::vector<Deferred> lazy_tma;                        // nobody observes the barrier yet: lands when somebody first looks at it
+  std::vector<std::function<void()>> late_mma;
+  int pass = 0;
   ~BlockState() { free(stacks); }
 };
 
@@ -309,8 +316,16 @@ inline long run_cluster_fibers(BlockState* bs, dim3 grid, dim3 block, long long 
   std::vector<int> order(nw);
   for (int w = 0; w < nw; ++w) order[w] = w;
   int idle_passes = 0;
+  bs->late_tma.clear(); bs->lazy_tma.clear(); bs->late_mma.clear(); bs->pass = 0;
   while (bs->cl_live > 0) {
     bs->progress = false;
+    bs->pass++;
+    if (!bs->late_tma.empty()) {                           // asynchronous copies whose time has come (issue order preserved per due pass)
+      std::vector<BlockState::Deferred> todo;
+      todo.swap(bs->late_tma);
+      for (auto& d : todo) { if (d.due <= bs->pass) { d.op(); bs->progress = true; } else bs->late_tma.push_back(std::move(d)); }
+      if (!bs->late_tma.empty()) bs->progress = true;      // something is still in flight: not a deadlock
+    }
     if (rng) for (int w = nw - 1; w > 0; --w) std::swap(order[w], order[next_rand() % (uint64_t)(w + 1)]);
     for (int k = 0; k < nw; ++k) {
       if (rng && idle_passes == 0 && (next_rand() & 1)) continue;

@@ -143,6 +143,39 @@ inline void mbar_complete_tx(MBar* b, uint32_t bytes) {
   b->tx -= (int32_t)bytes; mbar_check(b);
 }
 
+// ---------------------------------------------------------------- asynchrony (SACB_EMUL_ASYNC=1)
+// Default: every asynchronous operation completes at issue.  SACB_EMUL_ASYNC=1 pushes them to the other legal extreme:
+//   * a TMA load neither copies nor completes its bytes until some thread LOOKS at its mbarrier (try_wait); if a thread is
+//     already waiting on that barrier when the load is issued, it lands 1..6 scheduler passes later;
+//   * an MMA reads its operands and writes TMEM only when the next tcgen05.commit of its thread forces it.
+// A kernel that reads a TMA destination without waiting on the barrier, refills a stage before the empty barrier, or reads an
+// accumulator before the commit arrived then computes WRONG RESULTS (or trips a protocol check) here.  tests/test_emul_tc_cpu.py
+// proves that with mutated kernels (a wait removed) before it trusts a green run of the real ones.
+inline bool async_mode() { static const bool on = getenv("SACB_EMUL_ASYNC") && getenv("SACB_EMUL_ASYNC")[0] == '1'; return on; }
+inline uint32_t async_rand() { static thread_local uint32_t x = 2463534242u; x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; }
+template <class F> inline void tma_issue(const void* bar, F op) {
+  if (!async_mode()) { op(); return; }
+  BlockState* bs = t_bs;
+  bool observed = false;
+  for (const Fiber& f : bs->fibers) if (!f.done && f.word == (const uint64_t*)bar) { observed = true; break; }
+  if (observed) bs->late_tma.push_back(BlockState::Deferred{bs->pass + 1 + (int)(async_rand() % 6), std::function<void()>(op), bar});
+  else bs->lazy_tma.push_back(BlockState::Deferred{0, std::function<void()>(op), bar});
+  bs->progress = true;
+}
+inline void tma_observe(const void* bar) {                 // a thread looks at `bar`: everything in flight towards it lands now
+  BlockState* bs = t_bs;
+  if (bs->lazy_tma.empty()) return;
+  std::vector<BlockState::Deferred> todo;
+  todo.swap(bs->lazy_tma);
+  for (auto& d : todo) { if (d.bar == bar) d.op(); else bs->lazy_tma.push_back(std::move(d)); }
+}
+inline void mma_flush() {                                  // tcgen05.commit: all prior MMAs of this thread complete before the arrive
+  BlockState* bs = t_bs;
+  std::vector<std::function<void()>> todo;
+  todo.swap(bs->late_mma);
+  for (auto& f : todo) f();
+}
+
 // ---------------------------------------------------------------- TMA
 // copy one 128-byte line (64 bf16) of the box to shared row `row` of the tile at shared address `dst` (swizzled); src == nullptr: zeros
 inline void tma_put_line(uint32_t dst, int row, const char* src) {
@@ -151,7 +184,7 @@ inline void tma_put_line(uint32_t dst, int row, const char* src) {
     if (src) memcpy(d, src + chunk * 16, 16); else memset(d, 0, 16);
   }
 }
-inline void tma_tiled(const CUtensorMap* m, uint32_t dst, MBar* bar, int c0, int c1, int c2) {
+inline void tma_tiled_now(const CUtensorMap* m, uint32_t dst, MBar* bar, int c0, int c1, int c2) {
   const EmulMap& e = map_of(m);
   if (e.im2col) die("tiled TMA load through an im2col tensor map");
   if (dst & 1023u) die("TMA destination of a SWIZZLE_128B box must be 1024-byte aligned");
@@ -172,7 +205,7 @@ inline void tma_tiled(const CUtensorMap* m, uint32_t dst, MBar* bar, int c0, int
   mbar_complete_tx(bar, (uint32_t)rows * 128u);
 }
 // `row0`: first shared row written (multicast halves write rows [0, pixels) of their own destination)
-inline void tma_im2col(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int w, int h, int n, int off_w, int off_h) {
+inline void tma_im2col_now(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int w, int h, int n, int off_w, int off_h) {
   const EmulMap& e = map_of(m);
   if (!e.im2col) die("im2col TMA load through a tiled tensor map");
   if (dst & 1023u) die("TMA destination of a SWIZZLE_128B box must be 1024-byte aligned");
@@ -193,6 +226,18 @@ inline void tma_im2col(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int
     if (w > w_hi) { w = w_lo; h += e.estr[2]; if (h > h_hi) { h = h_lo; n += 1; } }
   }
   mbar_complete_tx(bar, (uint32_t)e.pixels * 128u);
+}
+
+// the tensor map is a kernel parameter (by value, on the issuing fiber's stack): a deferred copy keeps its own copy of it
+inline void tma_tiled(const CUtensorMap* m, uint32_t dst, MBar* bar, int c0, int c1, int c2) {
+  map_of(m);
+  const CUtensorMap mc = *m;
+  tma_issue(bar, [=]() { tma_tiled_now(&mc, dst, bar, c0, c1, c2); });
+}
+inline void tma_im2col(const CUtensorMap* m, uint32_t dst, MBar* bar, int c, int w, int h, int n, int off_w, int off_h) {
+  map_of(m);
+  const CUtensorMap mc = *m;
+  tma_issue(bar, [=]() { tma_im2col_now(&mc, dst, bar, c, w, h, n, off_w, off_h); });
 }
 
 // ---------------------------------------------------------------- tensor memory and MMA
@@ -242,21 +287,20 @@ inline void read_operand(int cta, const SmemDesc& d, int count, bool mn_major, f
       }
   }
 }
-inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+inline void mma_f16_now(int group, int me, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   BlockState* bs = t_bs;
   const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
   const bool a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 1 || ((idesc >> 10) & 7) != 1) die("tcgen05.mma: expected bf16 x bf16 -> f32");
   if (group == 1 ? (M != 128) : (M != 256)) die("tcgen05.mma: M must be 128 (cta_group::1) or 256 (cta_group::2) here");
   if (N < 16 || N > 256 || N % 16) die("tcgen05.mma: invalid N");
-  if (group == 2 && (bs->ncta != 2 || my_cta() != 0)) die("cta_group::2 MMA must be issued by CTA 0 of a 2-CTA cluster");
+  if (group == 2 && (bs->ncta != 2 || me != 0)) die("cta_group::2 MMA must be issued by CTA 0 of a 2-CTA cluster");
   if ((tmem_d >> 16) != 0) die("tcgen05.mma: accumulator must start at TMEM lane 0");
   const uint32_t col0 = tmem_d & 0xFFFF;
   if (col0 + (uint32_t)N > 512) die("tcgen05.mma: accumulator columns out of range");
   const SmemDesc da = decode_desc(adesc), db = decode_desc(bdesc);
   static thread_local std::vector<float> A, Bt;             // A[row][16], Bt[16][N]
   A.resize(256 * 16); Bt.resize(16 * 256);
-  const int me = my_cta();
   if (group == 1) {
     read_operand(me, da, 128, a_mn, A.data(), 16, 1);
     read_operand(me, db, N, b_mn, Bt.data(), 1, N);
@@ -278,6 +322,12 @@ inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, 
   bs->progress = true;
 }
 
+inline void mma_f16(int group, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const int me = my_cta();
+  if (!async_mode()) { mma_f16_now(group, me, tmem_d, adesc, bdesc, idesc, accumulate); return; }
+  t_bs->late_mma.push_back([=]() { mma_f16_now(group, me, tmem_d, adesc, bdesc, idesc, accumulate); });
+  t_bs->progress = true;
+}
 void set_last_kernel(const char* name);      // emul_api.cpp
 }  // namespace cuda_emul
 
@@ -327,7 +377,7 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {        // mbarrier.a
   b->tx += (int32_t)bytes; cuda_emul::mbar_do_arrive(b);
 }
 inline void mbar_arrive(uint64_t* bar) { cuda_emul::mbar_do_arrive(as_bar(bar)); }
-inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return as_bar(bar)->phase != (parity & 1u); }
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { cuda_emul::tma_observe(bar); return as_bar(bar)->phase != (parity & 1u); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   cuda_emul::BlockState* bs = cuda_emul::t_bs;
   cuda_emul::Fiber& f = bs->fibers[bs->cur];
@@ -358,8 +408,9 @@ inline void tma_load_im2col_mc(const CUtensorMap* m, uint64_t* bar, void* dst, i
   for (int k = 0; k < cuda_emul::t_bs->ncta; ++k)
     if (mask >> k & 1) cuda_emul::tma_im2col(m, (smem_u32(dst) & 0xFFFFFFu) | ((uint32_t)k << 24), as_bar(cuda_emul::peer_ptr(bar, k)), c, w, h, n, ow, oh);
 }
-inline void tc_commit(uint64_t* bar) { cuda_emul::mbar_do_arrive(as_bar(bar)); }
+inline void tc_commit(uint64_t* bar) { cuda_emul::mma_flush(); cuda_emul::mbar_do_arrive(as_bar(bar)); }
 inline void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  cuda_emul::mma_flush();
   for (int c = 0; c < cuda_emul::t_bs->ncta; ++c) if (mask >> c & 1) cuda_emul::mbar_do_arrive(as_bar(cuda_emul::peer_ptr(bar, c)));
 }
 inline void tc_fence_before() {}

@@ -28,7 +28,7 @@ SELECTION = [
     ("test_conv_gpu", "test_conv_fprop_mask_and_add_f32", None),
     ("test_conv_gpu", "test_conv_aspp_head_nchw", None),
     ("test_conv_gpu", "test_conv_wgrad", None),
-    ("test_step_gpu", "test_backbone_forward_matches_oracle", None),
+    ("test_step_gpu", "test_backbone_forward_matches_oracle", ()),               # by default on the real kernel source, below
     ("test_step_gpu", "test_tail_labels_bit_exact_on_golden_teacher_logits", None),
     ("test_step_gpu", "test_two_training_steps_match_reference_golden", None),
     ("test_step_gpu", "test_vgg16_config1_two_steps_match_reference_golden", None),
@@ -72,14 +72,24 @@ def emul():
         yield lib
 
 
+@pytest.fixture(scope="module")
+def emul_full():
+    """every kernel from its real source, the tcgen05 / TMA GEMM kernels included (tests/cpu_emul/cuda_emul_tc.h)"""
+    torch.set_num_threads(8)
+    with E.emulated_gpu(full=True) as lib:
+        yield lib
+
+
 _fixture_cache = {}
 
 
-def _fixture(mod, name, request):
+def _fixture(mod, name, request, fresh=False):
     if name == "golden":
         return np.load(os.path.join(ROOT, "tests", "golden", "sac_resnet101_tiny.npz"), allow_pickle=False)
     if name in ("monkeypatch", "tmp_path"):
         return request.getfixturevalue(name)
+    if fresh:                                              # e.g. a `net` no earlier test has trained
+        return getattr(mod, name).__wrapped__()
     key = (mod.__name__, name)
     if key not in _fixture_cache:                          # module-scoped fixtures of the GPU test modules (e.g. `net`)
         _fixture_cache[key] = getattr(mod, name).__wrapped__()
@@ -97,3 +107,59 @@ def test_gpu_test_on_the_emulation_library(emul, request, mod, fn, kw):
     n0 = emul.sacb_launch_count()
     f(**kw)
     assert emul.sacb_launch_count() > n0, "the test did not reach the library"
+
+
+# ---------------------------------------------------------------- the same, with NO formula model: sacb_gemm.cu's real kernels
+FULL_SELECTION = [   # (module, function, parametrisation index or None, runs by default)
+    ("test_step_gpu", "test_backbone_forward_matches_oracle", None, True),
+    ("test_step_gpu", "test_two_training_steps_match_reference_golden", None, False),      # 913 launches, 77 s on 8 cores
+    ("test_step_gpu", "test_vgg16_config1_two_steps_match_reference_golden", None, False),
+    ("test_abn_gpu", "test_abn_iteration_matches_reference_golden", 1, False),      # vgg16
+]
+
+
+@pytest.mark.parametrize("mod,fn,idx,default", FULL_SELECTION)
+def test_gpu_test_on_the_real_kernel_source_of_everything(request, mod, fn, idx, default):
+    if not (default or FULL):
+        pytest.skip("SACB_EMUL_FULL=1 runs it")
+    lib = request.getfixturevalue("emul_full")
+    m = importlib.import_module(mod)
+    f = getattr(m, fn)
+    kw = {}
+    if idx is not None:
+        mark = [x for x in f.pytestmark if x.name == "parametrize"][0]
+        names = [n.strip() for n in mark.args[0].split(",")]
+        v = mark.args[1][idx]
+        kw = dict(zip(names, v if len(names) > 1 else (v,)))
+    for name in inspect.signature(f).parameters:
+        if name not in kw:
+            kw[name] = _fixture(m, name, request, fresh=True)
+    n0 = lib.sacb_launch_count()
+    f(**kw)
+    assert lib.sacb_launch_count() > n0
+    assert b"conv_" in lib.sacb_emul_last_kernel()             # a tcgen05 kernel instantiation was launched through the primitive model
+
+
+SWITCH_STEP = r'''
+import sys, os
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import emul_harness as E, test_step_gpu as G
+golden = np.load(os.path.join(%r, "tests", "golden", "sac_resnet101_tiny.npz"), allow_pickle=False)
+with E.emulated_gpu(full=True) as lib:
+    G.test_two_training_steps_match_reference_golden(G.net.__wrapped__(), golden)
+print("OK")
+'''
+
+
+@pytest.mark.skipif(not FULL, reason="SACB_EMUL_FULL=1 runs it")
+@pytest.mark.parametrize("switch", ["SACB_EPI_STAGED", "SACB_TAIL_SPLIT"])
+def test_two_training_steps_with_an_unverified_kernel_variant_switched_on(switch):
+    """the whole SAC step (every kernel from real source) with the residual-staging epilogue / the tail split in the loop, vs the
+    real reference's golden; SACB_EMUL_SMS=8 so that the small problem has partial last waves"""
+    import subprocess, sys
+    env = dict(os.environ, SACB_EMUL_SMS="8")
+    env[switch] = "1"
+    r = subprocess.run([sys.executable, "-c", SWITCH_STEP % (ROOT, os.path.join(ROOT, "tests"), ROOT)], env=env, capture_output=True,
+                       text=True, timeout=3000)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-3000:]

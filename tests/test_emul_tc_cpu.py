@@ -25,6 +25,7 @@ from da_sac_b200 import lib as L
 
 pytestmark = pytest.mark.skipif(not E.available(), reason="no host toolchain for tests/cpu_emul")
 BUILD = os.path.join(E.EMUL, "_build")
+ROOT = os.path.dirname(E.HERE)
 SMS = "8"            # 4 clusters of 2: multi-wave schedules with small problems
 
 
@@ -243,7 +244,64 @@ os.environ["SACB_RUN_UNVERIFIED"] = "1"
 import torch, pytest
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", %r, "-k", "staging_variant or tail_split_variant or wgrad_kernels"]))
 ''' % (os.path.dirname(E.HERE), E.HERE, os.path.abspath(__file__))
-    for seed in ("1", "7"):
-        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SACB_EMUL_SCHED_SEED=seed), capture_output=True, text=True,
-                           timeout=1200)
-        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    envs = [dict(SACB_EMUL_SCHED_SEED="1"),
+            dict(SACB_EMUL_ASYNC="1", SACB_EMUL_SCHED_SEED="3")]    # + TMA lands as late as legal, MMAs run at their commit
+    if os.environ.get("SACB_EMUL_FULL") == "1":
+        envs += [dict(SACB_EMUL_SCHED_SEED="7"), dict(SACB_EMUL_ASYNC="1")]
+    for env in envs:
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, str(env) + r.stdout[-3000:] + r.stderr[-2000:]
+
+
+MUTANTS = [   # (name, text to find in the translated kernel source, replacement, switch that selects the kernel, must be caught without SACB_EMUL_ASYNC)
+    ("mma_skips_full_barrier", "          mbar_wait(&full_bar[ps.stage], ps.phase);\n          tc_fence_after();\n          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);",
+     "          tc_fence_after();\n          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);", "SACB_NONE", True),
+    ("epilogue_skips_residual_full_barrier", "          mbar_wait(res_full, *res_phase);\n", "", "SACB_EPI_STAGED", False),
+    ("residual_producer_skips_empty_barrier", "          mbar_wait(res_empty, ph ^ 1);\n", "", "SACB_EPI_STAGED", True),
+]
+MUTANT_CHECK = r'''
+import sys, os
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ctypes as C, torch
+import test_emul_tc_cpu as T
+def load(path):
+    lib = C.CDLL(path); lib.sacb_last_error.restype = C.c_char_p; lib.sacb_emul_last_kernel.restype = C.c_char_p
+    return lib
+os.environ["SACB_EMUL_SMS"] = "8"
+os.environ[sys.argv[3]] = "1"
+ref, mut = load(sys.argv[1]), load(sys.argv[2])
+geom = (3, 33, 33, 256, 1024, 1, 1, 1, 0)
+a = T.run(ref, geom, epi="res"); b = T.run(mut, geom, epi="res")
+print("IDENTICAL" if torch.equal(a["f32"], b["f32"]) and torch.equal(a["hi"], b["hi"]) else "DIFFERENT")
+'''
+
+
+@pytest.mark.parametrize("name,find,repl,switch,caught_sync", MUTANTS)
+def test_the_checker_has_teeth_a_removed_wait_is_caught(libs, tmp_path, name, find, repl, switch, caught_sync):
+    if switch == "SACB_NONE" and os.environ.get("SACB_EMUL_FULL") != "1":
+        pytest.skip("SACB_EMUL_FULL=1 runs it (the two mutants of the never-run staged variant run by default)")
+    """before a green run of the real kernels is trusted: the same kernels with ONE mbarrier wait removed must fail on the
+    emulation -- wrong results, a protocol violation or a deadlock report.  The second mutant (the epilogue reads the staged
+    residual without waiting for the TMA) is only visible with asynchronous TMA, which is why SACB_EMUL_ASYNC exists."""
+    import subprocess, sys
+    tc = os.path.join(BUILD, "tc")
+    src = open(os.path.join(tc, "sacb_gemm.cpp")).read()
+    assert src.count(find) >= 1, "mutation site not found: the kernel source changed, update MUTANTS"
+    cpp = str(tmp_path / (name + ".cpp"))
+    open(cpp, "w").write(src.replace(find, repl))
+    so = str(tmp_path / (name + ".so"))
+    cc = ["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-w", "-fno-strict-aliasing", "-ffp-contract=off",
+          "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "da_sac_b200", "csrc"), "-I" + tc, "-I/usr/local/cuda/include",
+          "-I" + E.EMUL, "-DSACB_EMUL_TC", "-include", "cuda_emul.h", "-shared", cpp, os.path.join(E.EMUL, "emul_api.cpp"), "-o", so, "-ldl"]
+    r = subprocess.run(cc, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = str(tmp_path / "ref.so")
+    shutil.copy(os.path.join(BUILD, "libsacb_emul_tc.so"), ref)
+    verdict = {}
+    for asyn in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", MUTANT_CHECK % (ROOT, E.HERE), ref, so, switch], env=dict(os.environ, SACB_EMUL_ASYNC=asyn),
+                           capture_output=True, text=True, timeout=600)
+        verdict[asyn] = r.returncode != 0 or "IDENTICAL" not in r.stdout
+        print(name, "async=" + asyn, "rc", r.returncode, r.stdout.strip()[-40:], [l for l in r.stderr.splitlines() if "cuda_emul" in l][:1])
+    assert verdict["1"], "the mutant was NOT caught with asynchronous TMA / MMA"
+    assert verdict["0"] == caught_sync
