@@ -305,3 +305,16 @@ def test_the_checker_has_teeth_a_removed_wait_is_caught(libs, tmp_path, name, fi
         print(name, "async=" + asyn, "rc", r.returncode, r.stdout.strip()[-40:], [l for l in r.stderr.splitlines() if "cuda_emul" in l][:1])
     assert verdict["1"], "the mutant was NOT caught with asynchronous TMA / MMA"
     assert verdict["0"] == caught_sync
+
+
+@pytest.mark.parametrize("variant,cases", [(None, 60), ("SACB_EPI_STAGED", 30), ("SACB_TAIL_SPLIT", 40)])
+def test_random_geometries(libs, variant, cases):
+    """tests/cpu_emul/fuzz_gemm.py: random shapes / strides / dilations / paddings / epilogues / k_valid / split-K / precision;
+    verified kernels vs the formula model, the never-run variants bit for bit vs the default kernels (run in a subprocess: the
+    variant switch and the SM count are read once per loaded library)"""
+    import subprocess, sys
+    cmd = [sys.executable, os.path.join(E.EMUL, "fuzz_gemm.py"), "--seed", "1", "--cases", str(cases)] + (["--variant", variant] if variant else [])
+    r = subprocess.run(cmd, env=dict(os.environ, SACB_EMUL_SMS=SMS), capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    if variant:
+        assert int(r.stdout.split(" ran the variant")[0].split()[-1]) >= 5      # the variant's instantiation was really exercised
