@@ -3,6 +3,12 @@
 The product path has NO fallback: if the shared library is missing or a call
 fails, an exception is raised (``SacbError``).  PyTorch is used only for device
 memory and streams; the structs below carry raw device pointers.
+
+There is no CPU route either: the host-emulation libraries of tests/cpu_emul
+(test infrastructure for the GPU-less build container) export ``sacb_emul_marker``
+and ``lib()`` refuses to load anything that does -- also through ``SACB_LIB`` --
+and ``ptr()`` rejects tensors that are not on a CUDA device.  Only the tests swap
+``lib`` / ``ptr`` for the emulation (tests/emul_harness.py).
 """
 import ctypes as C
 import os

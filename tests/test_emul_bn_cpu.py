@@ -82,9 +82,14 @@ def test_argument_errors(api):
     assert b"go together" in api.lib.sacb_last_error()
 
 
-def test_product_loader_refuses_the_emulation_library(api, monkeypatch):
+@pytest.mark.parametrize("name", ["libsacb_emul.so", "libsacb_emul_tc.so", "libsacb_emul_full.so"])
+def test_product_loader_refuses_the_emulation_libraries(api, monkeypatch, name):
+    """no CPU route into the product: da_sac_b200.lib (hence models/, bench.py, smoke()) rejects anything built from tests/cpu_emul,
+    also when SACB_LIB points at it"""
+    import emul_harness as E
     from da_sac_b200 import lib as L
-    monkeypatch.setattr(L, "LIB_PATH", os.path.join(EMUL, "_build", "libsacb_emul.so"))
+    monkeypatch.setattr(L, "LIB_PATH", os.path.join(os.path.dirname(E.SO), name))
     monkeypatch.setattr(L, "_lib", None)
     with pytest.raises(L.SacbError, match="emulation"):
         L.lib()
+    assert L._lib is None
