@@ -24,7 +24,7 @@ import emul_harness as E
 from da_sac_b200 import lib as L
 
 pytestmark = pytest.mark.skipif(not E.available(), reason="no host toolchain for tests/cpu_emul")
-BUILD = os.path.join(E.EMUL, "_build")
+BUILD = os.path.dirname(E.SO)                  # follows SACB_EMUL_SO (AddressSanitizer build)
 ROOT = os.path.dirname(E.HERE)
 SMS = "8"            # 4 clusters of 2: multi-wave schedules with small problems
 
