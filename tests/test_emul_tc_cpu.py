@@ -244,10 +244,9 @@ os.environ["SACB_RUN_UNVERIFIED"] = "1"
 import torch, pytest
 sys.exit(pytest.main(["-x", "-q", "-p", "no:cacheprovider", %r, "-k", "staging_variant or tail_split_variant or wgrad_kernels"]))
 ''' % (os.path.dirname(E.HERE), E.HERE, os.path.abspath(__file__))
-    envs = [dict(SACB_EMUL_SCHED_SEED="1"),
-            dict(SACB_EMUL_ASYNC="1", SACB_EMUL_SCHED_SEED="3")]    # + TMA lands as late as legal, MMAs run at their commit
+    envs = [dict(SACB_EMUL_ASYNC="1", SACB_EMUL_SCHED_SEED="3")]    # random warp order + TMA as late as legal, MMAs at their commit
     if os.environ.get("SACB_EMUL_FULL") == "1":
-        envs += [dict(SACB_EMUL_SCHED_SEED="7"), dict(SACB_EMUL_ASYNC="1")]
+        envs += [dict(SACB_EMUL_SCHED_SEED="1"), dict(SACB_EMUL_SCHED_SEED="7"), dict(SACB_EMUL_ASYNC="1")]
     for env in envs:
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=1200)
         assert r.returncode == 0, str(env) + r.stdout[-3000:] + r.stderr[-2000:]
@@ -307,7 +306,7 @@ def test_the_checker_has_teeth_a_removed_wait_is_caught(libs, tmp_path, name, fi
     assert verdict["0"] == caught_sync
 
 
-@pytest.mark.parametrize("variant,cases", [(None, 60), ("SACB_EPI_STAGED", 30), ("SACB_TAIL_SPLIT", 40)])
+@pytest.mark.parametrize("variant,cases", [(None, 40), ("SACB_EPI_STAGED", 16), ("SACB_TAIL_SPLIT", 30)])
 def test_random_geometries(libs, variant, cases):
     """tests/cpu_emul/fuzz_gemm.py: random shapes / strides / dilations / paddings / epilogues / k_valid / split-K / precision;
     verified kernels vs the formula model, the never-run variants bit for bit vs the default kernels (run in a subprocess: the
@@ -317,4 +316,4 @@ def test_random_geometries(libs, variant, cases):
     r = subprocess.run(cmd, env=dict(os.environ, SACB_EMUL_SMS=SMS), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     if variant:
-        assert int(r.stdout.split(" ran the variant")[0].split()[-1]) >= 5      # the variant's instantiation was really exercised
+        assert int(r.stdout.split(" ran the variant")[0].split()[-1]) >= 3      # the variant's instantiation was really exercised
