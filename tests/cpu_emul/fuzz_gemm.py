@@ -80,8 +80,8 @@ def main(argv=None):
                 if a.variant:
                     ok = torch.equal(x["f32"], y["f32"]) and torch.equal(x["hi"], y["hi"]) and torch.equal(x["lo"], y["lo"]) and \
                         (y["colsum"] is None or T.close(y["colsum"], x["colsum"], 1e-5))
-                    hit += ("true" in tc.sacb_emul_last_kernel().decode().split("pair_kernel")[-1]) and prec == 0 or \
-                        tc.sacb_emul_last_kernel() != ref.sacb_emul_last_kernel()
+                    f = T.template_flags(tc)
+                    hit += bool(f.get("STAGED") or f.get("TSPLIT"))
                 else:
                     ok = T.close(y["f32"], x["f32"], 3e-5) and (y["nchw"] is None or T.close(y["nchw"], x["nchw"], 3e-5)) and \
                         (y["hi"] is None or T.close(y["hi"].float() + y["lo"].float(), x["hi"].float() + x["lo"].float(), 3e-5)) and \

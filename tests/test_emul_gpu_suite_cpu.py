@@ -49,7 +49,9 @@ SELECTION = [
 
 def _cases():
     out = []
-    os.environ.setdefault("SACB_RUN_UNVERIFIED", "1")     # the skipif marks of the gated modules are evaluated at import
+    # NB: nothing here may touch SACB_RUN_UNVERIFIED -- this module is also IMPORTED (collected, then deselected) by
+    # `pytest -m gpu` on the GPU box, and the gates of the not-yet-verified GPU tests must stay shut there.  Calling a test
+    # function directly ignores its module's skipif mark, so the variable is not needed.
     for mod, fn, ids in SELECTION:
         f = getattr(importlib.import_module(mod), fn)
         params = [m for m in getattr(f, "pytestmark", []) if m.name == "parametrize"]
