@@ -1,0 +1,29 @@
+"""The GPU box collects EVERY module under tests/ (`pytest tests -m gpu`): importing the CPU-side modules must not open the gates
+of the GPU tests that have not been verified on a B200 yet (SACB_RUN_UNVERIFIED), or a round-end run would execute them."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PROBE = r'''
+import os, sys, pytest
+import _pytest.skipping as S
+class P:
+    def pytest_collection_finish(self, session):
+        gated = [i for i in session.items if any(m.name == "skipif" for m in i.iter_markers())]
+        shut = sum(1 for i in gated if S.evaluate_skip_marks(i) is not None)
+        print("RESULT env=%r selected=%d gated=%d shut=%d" % (os.environ.get("SACB_RUN_UNVERIFIED"), len(session.items), len(gated), shut))
+pytest.main(["tests", "-m", "gpu", "--collect-only", "-q", "-p", "no:cacheprovider"], plugins=[P()])
+'''
+
+
+def test_collecting_the_gpu_suite_leaves_the_unverified_gates_shut():
+    env = {k: v for k, v in os.environ.items() if k != "SACB_RUN_UNVERIFIED"}
+    r = subprocess.run([sys.executable, "-c", PROBE], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")]
+    assert line, r.stdout[-2000:] + r.stderr[-2000:]
+    f = dict(kv.split("=") for kv in line[0].split()[1:])
+    assert f["env"] == "None", "a test module sets SACB_RUN_UNVERIFIED at import"
+    assert int(f["gated"]) >= 20 and f["gated"] == f["shut"], line[0]
+    assert int(f["selected"]) - int(f["gated"]) >= 41          # the verified suite (profiles/pytest_gpu_r1q.log) is still all there
