@@ -65,6 +65,11 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device(t):
+    """True for a CUDA tensor (the tests' host emulation swaps this together with ptr / stream)"""
+    return t.is_cuda
+
+
 def launch_count():
     return int(lib().sacb_launch_count())
 

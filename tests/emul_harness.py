@@ -85,6 +85,21 @@ class _CudaToCpu(TorchFunctionMode):
         return func(*args, **kwargs)
 
 
+class _FakeStream(object):
+    """torch.cuda.Stream stand-in: the emulation runs everything in program order, so fork / join are no-ops.  What this lets
+    a test execute is the HOST logic of a multi-stream path (which engine, which buffers, which order), not its concurrency."""
+    cuda_stream = 0
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, ev):
+        pass
+
+    def synchronize(self):
+        pass
+
+
 @contextlib.contextmanager
 def emulated_gpu(full=False):
     """full=False: tensor-core entry points through the formula model (fast); full=True: through the real kernel source"""
@@ -97,13 +112,19 @@ def emulated_gpu(full=False):
         assert t.device.type == "cpu" and t.is_contiguous()
         return C.c_void_p(t.data_ptr())
 
-    saved = {(L, k): getattr(L, k) for k in ("lib", "stream", "ptr", "dptr")}
+    saved = {(L, k): getattr(L, k) for k in ("lib", "stream", "ptr", "dptr", "on_device")}
+    for k in ("Stream", "current_stream", "stream"):
+        saved[(torch.cuda, k)] = getattr(torch.cuda, k)
     saved[(torch.cuda, "synchronize")] = torch.cuda.synchronize
     saved[(torch.cuda, "is_current_stream_capturing")] = torch.cuda.is_current_stream_capturing
     L.lib = lambda: lib
     L.stream = lambda: C.c_void_p(0)
     L.ptr = ptr
     L.dptr = lambda t: None if t is None else t.data_ptr()
+    L.on_device = lambda t: True
+    torch.cuda.Stream = _FakeStream
+    torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.is_current_stream_capturing = lambda: False
     try:

@@ -166,3 +166,15 @@ def test_two_training_steps_with_an_unverified_kernel_variant_switched_on(switch
     r = subprocess.run([sys.executable, "-c", SWITCH_STEP % (ROOT, os.path.join(ROOT, "tests"), ROOT)], env=env, capture_output=True,
                        text=True, timeout=3000)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_two_training_steps_with_the_two_stream_schedule(emul, monkeypatch, request):
+    """SACB_TWO_STREAM=1 (models/sac.py: teacher forward + tail issued on a side stream with its OWN engine, joined before the
+    loss) has not run on a GPU.  Streams do not exist here -- fork / join are no-ops -- but the host logic does: the second
+    engine, its workspaces and plane pools, the order of the calls.  Two full training steps must still match the golden."""
+    from da_sac_b200.models import sac as S
+    m = importlib.import_module("test_step_gpu")
+    monkeypatch.setattr(S, "_TWO_STREAM", True)
+    net = _fixture(m, "net", request, fresh=True)
+    m.test_two_training_steps_match_reference_golden(net, _fixture(m, "golden", request))
+    assert net[0]._engines_teacher, "the teacher did not get its own engine: the two-stream branch was not taken"
