@@ -168,13 +168,25 @@ def test_two_training_steps_with_an_unverified_kernel_variant_switched_on(switch
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_two_training_steps_with_the_two_stream_schedule(emul, monkeypatch, request):
+@pytest.mark.parametrize("arch", ["vgg16", "resnet101"])
+def test_two_training_steps_with_the_two_stream_schedule(emul, monkeypatch, request, arch):
     """SACB_TWO_STREAM=1 (models/sac.py: teacher forward + tail issued on a side stream with its OWN engine, joined before the
     loss) has not run on a GPU.  Streams do not exist here -- fork / join are no-ops -- but the host logic does: the second
     engine, its workspaces and plane pools, the order of the calls.  Two full training steps must still match the golden."""
+    if arch == "resnet101" and not FULL:
+        pytest.skip("SACB_EMUL_FULL=1 runs it")
     from da_sac_b200.models import sac as S
     m = importlib.import_module("test_step_gpu")
     monkeypatch.setattr(S, "_TWO_STREAM", True)
-    net = _fixture(m, "net", request, fresh=True)
-    m.test_two_training_steps_match_reference_golden(net, _fixture(m, "golden", request))
-    assert net[0]._engines_teacher, "the teacher did not get its own engine: the two-stream branch was not taken"
+    made = []
+    init = S.SAC.__init__
+
+    def spy(self, *a, **k):
+        init(self, *a, **k)
+        made.append(self)
+    monkeypatch.setattr(S.SAC, "__init__", spy)
+    if arch == "vgg16":
+        m.test_vgg16_config1_two_steps_match_reference_golden()
+    else:
+        m.test_two_training_steps_match_reference_golden(_fixture(m, "net", request, fresh=True), _fixture(m, "golden", request))
+    assert made and made[-1]._engines_teacher, "the teacher did not get its own engine: the two-stream branch was not taken"
