@@ -287,7 +287,7 @@ print("IDENTICAL" if torch.equal(a["f32"], b["f32"]) and torch.equal(a["hi"], b[
 '''
 
 
-@pytest.mark.parametrize("name,find,repl,switch,caught_sync", MUTANTS)
+@pytest.mark.parametrize("name,find,repl,switch,caught_sync", MUTANTS, ids=[m[0] for m in MUTANTS])
 def test_the_checker_has_teeth_a_removed_wait_is_caught(libs, tmp_path, name, find, repl, switch, caught_sync):
     if switch == "SACB_NONE" and os.environ.get("SACB_EMUL_FULL") != "1":
         pytest.skip("SACB_EMUL_FULL=1 runs it (the two mutants of the never-run staged variant run by default)")
