@@ -93,11 +93,37 @@ class _FakeStream(object):
     def wait_stream(self, other):
         pass
 
+    def __init__(self, *a, **k):
+        pass
+
     def wait_event(self, ev):
         pass
 
+    def record_event(self, ev=None):
+        return ev
+
     def synchronize(self):
         pass
+
+
+class _FakeEvent(object):
+    """torch.cuda.Event stand-in: records host time, so elapsed_time is host milliseconds (meaningless as a measurement)"""
+
+    def __init__(self, enable_timing=False, **kw):
+        self.t = None
+
+    def record(self, stream=None):
+        import time
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return max((other.t - self.t) * 1e3, 1e-3)
+
+    def synchronize(self):
+        pass
+
+    def query(self):
+        return True
 
 
 @contextlib.contextmanager
@@ -113,7 +139,7 @@ def emulated_gpu(full=False):
         return C.c_void_p(t.data_ptr())
 
     saved = {(L, k): getattr(L, k) for k in ("lib", "stream", "ptr", "dptr", "on_device")}
-    for k in ("Stream", "current_stream", "stream"):
+    for k in ("Stream", "current_stream", "stream", "Event", "set_device", "max_memory_allocated"):
         saved[(torch.cuda, k)] = getattr(torch.cuda, k)
     saved[(torch.cuda, "synchronize")] = torch.cuda.synchronize
     saved[(torch.cuda, "is_current_stream_capturing")] = torch.cuda.is_current_stream_capturing
@@ -125,6 +151,9 @@ def emulated_gpu(full=False):
     torch.cuda.Stream = _FakeStream
     torch.cuda.current_stream = lambda *a, **k: _FakeStream()
     torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.Event = _FakeEvent
+    torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.max_memory_allocated = lambda *a, **k: 0
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.is_current_stream_capturing = lambda: False
     try:

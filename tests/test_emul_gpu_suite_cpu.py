@@ -200,3 +200,31 @@ def test_driver_smoke_entry_point_on_the_real_kernel_source(emul_full, monkeypat
     n0 = emul_full.sacb_launch_count()
     G.smoke()
     assert emul_full.sacb_launch_count() - n0 > 300
+
+
+@pytest.mark.parametrize("extra", [["--arch", "vgg16"], [], ["--also-fast"]], ids=["vgg16", "resnet101", "resnet101_also_fast"])
+def test_bench_main_on_the_emulation_prints_a_complete_line(emul, monkeypatch, capsys, extra):
+    """bench.py is what the driver runs at the end of every round, and parts of it were edited after the last GPU call (re-measure
+    on throttling, clocks.remeasured, precision mode in the line).  Its whole main() -- argument handling, TargetStepper, staging /
+    prefetch, timed regions, clock sampler, roofline table, JSON line -- executes here on a tiny configuration with stand-in
+    events and streams (eager launches; the CUDA-graph capture and the default-size cpu_baseline leg are not reachable here).
+    The numbers mean nothing; the keys and the absence of a Python error do."""
+    import json
+    import runpy
+    if "--arch" not in extra and not FULL:
+        pytest.skip("SACB_EMUL_FULL=1 runs it")
+    argv = ["bench.py", "--groups", "1", "--group-size", "2", "--crop", "64", "64", "--steps", "2", "--warmup", "3", "--no-graph"] + extra
+    monkeypatch.setattr("sys.argv", argv)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    runpy.run_path(os.path.join(ROOT, "bench.py"), run_name="__main__")
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["gpu_launches"] > 100
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert "remeasured" in line["clocks"] and "workload" in line["config"] and line["config"]["precision_mode"] == "parity"
+    if "--also-fast" in extra:
+        assert set(line["fast_modes"]) == {"fast_bwd", "fast"}
