@@ -399,6 +399,9 @@ class Pool {
   int pending_ = 0;
 };
 
+// set by the multi-rank helper of emul_api.cpp: this OS thread plays one rank; its launches run on this thread alone (no pool,
+// no launch mutex), so that the ranks' kernels really run concurrently and synchronise through their flag words
+inline thread_local bool t_inline_launch = false;
 inline BlockState& my_block_state() { static thread_local BlockState bs; return bs; }
 inline std::atomic<long long> g_emulated_launches{0};
 inline std::mutex g_launch_mutex;      // one grid at a time
@@ -436,7 +439,8 @@ void run_grid_impl(const char* name, dim3 grid, dim3 block, size_t smem, bool sy
     abort();
   }
   if (smem > 227 * 1024) { fprintf(stderr, "cuda_emul: %zu bytes of dynamic shared memory\n", smem); abort(); }
-  std::lock_guard<std::mutex> lk(g_launch_mutex);
+  std::unique_lock<std::mutex> lk(g_launch_mutex, std::defer_lock);
+  if (!t_inline_launch) lk.lock();
   const long long nblocks = (long long)grid.x * grid.y * grid.z;
   if (nblocks == 0) { fprintf(stderr, "cuda_emul: empty grid\n"); abort(); }
   if (cl < 1 || nblocks % cl) { fprintf(stderr, "cuda_emul: grid of %lld blocks is not a multiple of the cluster size %d\n", nblocks, cl); abort(); }
@@ -460,7 +464,7 @@ void run_grid_impl(const char* name, dim3 grid, dim3 block, size_t smem, bool sy
     bs->ncta = 1;
     run_block_direct(bs, block);
   };
-  if (nclusters < 4) {                                   // not worth waking the pool
+  if (nclusters < 4 || t_inline_launch) {               // not worth waking the pool / this thread is one emulated rank
     BlockState& bs = my_block_state();
     setup(&bs);
     for (long long c = 0; c < nclusters; ++c) run_cluster(&bs, c);
@@ -494,6 +498,10 @@ template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int lane_
 }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline long long clock64() { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline void __nanosleep(unsigned) { if (cuda_emul::t_bs && !cuda_emul::t_bs->direct) { cuda_emul::t_bs->progress = true; cuda_emul::yield(); } }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline float sacb_bf16_to_float(uint16_t b) { unsigned u = ((unsigned)b) << 16; float f; memcpy(&f, &u, 4); return f; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }

@@ -460,3 +460,40 @@ template <int COLS> inline void tmem2_alloc(uint32_t* slot) {      // cta_group:
 }
 template <int COLS> inline void tmem2_dealloc(uint32_t) { cuda_emul::warp_barrier(); }
 }  // namespace sacb
+
+// ---------------------------------------------------------------- sacb_p2p.cu: peer memory, system-scope flags, multimem
+// The ranks of one exchange are OS threads of this process (emul_api.cpp: sacb_emul_allreduce_sgd_world); "peer" pointers are
+// ordinary pointers.  A multicast address is a key into a registry of its replicas: multimem.ld_reduce adds them in rank
+// order (the NVSwitch's order is unspecified), multimem.st writes all of them.
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaMalloc(void** p, size_t bytes) { return posix_memalign(p, 256, bytes ? bytes : 256) ? 2 : cudaSuccess; }
+static inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+namespace cuda_emul {
+struct Multicast { const char* base; size_t bytes; int world; char* replica[8]; };
+Multicast* find_multicast(const void* p);           // emul_api.cpp
+}
+namespace sacb {
+inline void st_release_sys(uint32_t* p, uint32_t v) { std::atomic_ref<uint32_t>(*p).store(v, std::memory_order_release); }
+inline uint32_t ld_acquire_sys(const uint32_t* p) { return std::atomic_ref<uint32_t>(*const_cast<uint32_t*>(p)).load(std::memory_order_acquire); }
+inline float4 ld_peer_f4(const float* p) { float4 v; memcpy(&v, p, 16); return v; }
+inline void st_peer_f4(float* p, const float4& v) { memcpy(p, &v, 16); }
+inline float4 multimem_ld_reduce_add_f4(const float* mc) {
+  cuda_emul::Multicast* m = cuda_emul::find_multicast(mc);
+  if (!m) cuda_emul::die("multimem.ld_reduce on an address that is not a registered multicast mapping");
+  const size_t off = (const char*)mc - m->base;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < m->world; ++r) { float4 t; memcpy(&t, m->replica[r] + off, 16); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+  return s;
+}
+inline void multimem_st_f4(float* mc, const float4& v) {
+  cuda_emul::Multicast* m = cuda_emul::find_multicast(mc);
+  if (!m) cuda_emul::die("multimem.st on an address that is not a registered multicast mapping");
+  const size_t off = (const char*)mc - m->base;
+  for (int r = 0; r < m->world; ++r) memcpy(m->replica[r] + off, &v, 16);
+}
+}  // namespace sacb

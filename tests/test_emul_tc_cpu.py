@@ -332,3 +332,64 @@ def test_random_geometries(libs, variant, cases):
     assert r.returncode == 0 and " 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     if variant:
         assert int(r.stdout.split(" ran the variant")[0].split()[-1]) >= 5      # the variant's instantiation was really exercised
+
+
+# ---------------------------------------------------------------- the peer-memory gradient exchange (csrc/sacb_p2p.cu), several ranks in one process
+@pytest.mark.parametrize("world,nvls", [(1, False), (2, False), (4, False), (8, False), (2, True), (4, True)])
+def test_fused_allreduce_sgd_kernel_with_emulated_ranks(world, nvls):
+    """allreduce_sgd_kernel<NVLS> from its real source: every rank is an OS thread running its own launch, peers are plain
+    pointers, the epoch flags are real acquire / release traffic between the threads; multimem.ld_reduce / multimem.st go through
+    a registry of replicas (sum in rank order).  Two optimiser steps; every replica of the parameters must equal, bit for bit,
+    the mean gradient pushed through the emulated sacb_sgd kernel, and momentum must be touched on the owner's slice only.
+    The plain instantiation is GPU-verified (tests/test_p2p_gpu.py); the NVLS one has not run on hardware yet."""
+    from da_sac_b200 import p2p as P
+    E.emul_lib()
+    lib = C.CDLL(os.path.join(BUILD, "libsacb_emul_full.so"))
+    lib.sacb_last_error.restype = C.c_char_p
+    n, segs = 40000, [(0, 10000), (10000, 25003), (30000, 39998)]             # a ragged end, a gap that is not an optimiser tensor
+    nseg = len(segs)
+    ranges = torch.tensor([v for s in segs for v in s], dtype=torch.int64)
+    lr = torch.tensor([1e-2, 2e-2, 1e-1]); wd = torch.tensor([5e-4, 0.0, 5e-4])
+    torch.manual_seed(world * 2 + nvls)
+    p0 = torch.randn(n)
+    params = [p0.clone() for _ in range(world)]
+    grads = [torch.empty(n) for _ in range(world)]
+    moms = [torch.zeros(n) for _ in range(world)]
+    flags = [torch.zeros(lib.sacb_p2p_flag_words(), dtype=torch.int32) for _ in range(world)]
+    ref_p, ref_m = p0.clone(), torch.zeros(n)
+    arr = lambda ts: (C.c_void_p * world)(*[t.data_ptr() for t in ts])
+    ga, pa, fa = arr(grads), arr(params), arr(flags)
+    mc_g = mc_p = None
+    if nvls:
+        mc_g, mc_p = torch.empty(n), torch.empty(n)                           # address ranges standing for the multicast mappings
+        lib.sacb_emul_clear_multicast()
+        assert lib.sacb_emul_register_multicast(p(mc_g), C.c_size_t(4 * n), world, ga) == 0
+        assert lib.sacb_emul_register_multicast(p(mc_p), C.c_size_t(4 * n), world, pa) == 0
+    fn = C.cast(lib.sacb_allreduce_sgd, C.c_void_p)
+    for step in range(2):
+        for g in grads:
+            g.normal_()
+        descs = [P.AllreduceSgd(C.sizeof(P.AllreduceSgd), world, r, C.cast(ga, C.c_void_p), C.cast(pa, C.c_void_p), C.cast(fa, C.c_void_p),
+                                p(moms[r]), p(ranges), p(lr), p(wd), nseg, n, 0.9, 1 if step == 0 else 0, p(mc_g), p(mc_p)) for r in range(world)]
+        dp = (C.c_void_p * world)(*[C.addressof(d) for d in descs])
+        assert lib.sacb_emul_run_ranks(fn, dp, world) == 0, lib.sacb_last_error()
+        # reference: sum in rank order, times 1/world, then the emulated sacb_sgd kernel
+        gsum = torch.zeros(n)
+        for g in grads:
+            gsum = gsum + g
+        gmean = gsum * torch.tensor(1.0 / world, dtype=torch.float32)
+        assert lib.sacb_sgd(p(ref_p), p(gmean), p(ref_m), p(ranges), p(lr), p(wd), nseg, C.c_float(0.9), 1 if step == 0 else 0, None) == 0
+        for r in range(world):
+            assert torch.equal(params[r], ref_p), "step %d: replica %d differs from all-reduce + SGD" % (step, r)
+        per = (n // 4 + world - 1) // world * 4
+        inside = torch.zeros(n, dtype=torch.bool)
+        for b, e in segs:
+            inside[b:e] = True       # (the <= 3 padding floats after a ragged tensor end share its last float4: the fused kernel
+                                     #  stores momentum there, sacb_sgd does not; no tensor lives there)
+        for r in range(world):
+            lo, hi = min(per * r, n), min(per * (r + 1), n)
+            own = torch.zeros(n, dtype=torch.bool); own[lo:hi] = True
+            assert torch.equal(moms[r][own & inside], ref_m[own & inside])
+            assert not moms[r][~own].any()                                    # momentum outside the owner's slice is never touched
+        assert all(int(f[2 * 8]) == step + 1 for f in flags)                  # FLAG_EPOCH advanced on every rank
+    assert torch.equal(ref_p[25004:30000], p0[25004:30000])                   # the gap between the segments is not an optimiser tensor
