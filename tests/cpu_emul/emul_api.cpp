@@ -30,7 +30,9 @@ extern "C" const char* sacb_emul_last_kernel(void) { return cuda_emul::g_last_ke
 #include <thread>
 #include <vector>
 namespace cuda_emul {
+#ifndef SACB_EMUL_TC      // (cuda_emul_tc.h has the same definition when this file is compiled together with a tensor-core unit)
 struct Multicast { const char* base; size_t bytes; int world; char* replica[8]; };
+#endif
 static std::vector<Multicast> g_multicast;
 Multicast* find_multicast(const void* p) {
   for (auto& m : g_multicast) if ((const char*)p >= m.base && (const char*)p < m.base + m.bytes) return &m;
