@@ -138,7 +138,23 @@ def emulated_gpu(full=False):
         assert t.device.type == "cpu" and t.is_contiguous()
         return C.c_void_p(t.data_ptr())
 
+    from da_sac_b200 import p2p as P2P
     saved = {(L, k): getattr(L, k) for k in ("lib", "stream", "ptr", "dptr", "on_device")}
+    saved[(P2P.SymmBuffer, "tensor")] = P2P.SymmBuffer.tensor
+    saved[(torch.cuda, "device")] = torch.cuda.device
+
+    def symm_tensor(self, dtype, numel):
+        """host view of a sacb_symm_alloc buffer (the product builds it through __cuda_array_interface__)"""
+        import numpy as np
+        npdt = {torch.float32: np.float32, torch.uint32: np.uint32, torch.int32: np.int32}[dtype]
+        assert numel * np.dtype(npdt).itemsize <= self.nbytes
+        a = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(self.nbytes,))[:numel * np.dtype(npdt).itemsize].view(npdt)
+        t = torch.from_numpy(a)
+        if dtype == torch.uint32:
+            t = t.view(torch.uint32) if t.dtype != torch.uint32 else t
+        assert t.data_ptr() == self.ptr
+        t._symm_owner = self
+        return t
     for k in ("Stream", "current_stream", "stream", "Event", "set_device", "max_memory_allocated"):
         saved[(torch.cuda, k)] = getattr(torch.cuda, k)
     saved[(torch.cuda, "synchronize")] = torch.cuda.synchronize
@@ -148,6 +164,8 @@ def emulated_gpu(full=False):
     L.ptr = ptr
     L.dptr = lambda t: None if t is None else t.data_ptr()
     L.on_device = lambda t: True
+    P2P.SymmBuffer.tensor = symm_tensor
+    torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
     torch.cuda.Stream = _FakeStream
     torch.cuda.current_stream = lambda *a, **k: _FakeStream()
     torch.cuda.stream = lambda s: contextlib.nullcontext()

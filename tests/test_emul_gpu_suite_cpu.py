@@ -228,3 +228,31 @@ def test_bench_main_on_the_emulation_prints_a_complete_line(emul, monkeypatch, c
     assert "remeasured" in line["clocks"] and "workload" in line["config"] and line["config"]["precision_mode"] == "parity"
     if "--also-fast" in extra:
         assert set(line["fast_modes"]) == {"fast_bwd", "fast"}
+
+
+def test_target_stepper_with_the_fused_peer_memory_exchange(emul):
+    """TargetStepper.enable_p2p() -- the path bench.py takes at N > 1 -- at world 1 on the emulation: P2PContext re-homes the flat
+    parameter / gradient buffers into sacb_symm_alloc memory, exports / imports the handles, and every step ends in
+    allreduce_sgd_kernel instead of sacb_sgd.  p2p.py was edited after the last multi-GPU run (NVLS plumbing): two training steps
+    must leave exactly the parameters FusedSGD leaves."""
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import TargetStepper
+    batch = synth.make_target_batch(1, 2, (64, 64), seed=0)
+    res, epochs = [], None
+    for use_p2p in (False, True):
+        cfg = synth.ModelCfgVGG16()
+        net = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+        net.backbone.load_state_dict(synth.make_vgg16_params(seed=321))
+        net.train()
+        st = TargetStepper(net, cfg, 2, torch.device("cpu"))
+        ctx = st.enable_p2p(1, 0) if use_p2p else None
+        for _ in range(2):
+            st.step(tuple(t.clone() for t in batch), read_losses=True)
+        res.append(torch.cat([q.detach().reshape(-1).clone() for q in net.backbone.parameters()]))
+        if ctx is not None:
+            assert st.optim.p2p is ctx and not ctx.nvls
+            epochs = int(ctx._bufs["flags"].tensor(torch.int32, emul.sacb_p2p_flag_words())[16])      # FLAG_EPOCH
+    assert epochs == 2, "the fused exchange kernel did not run once per step"
+    # (bit-identical on the real kernel source; the formula model's column sums are added in a run-dependent order)
+    assert ((res[0] - res[1]).abs().max() / res[0].abs().max()).item() < 1e-5
