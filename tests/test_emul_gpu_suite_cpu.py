@@ -68,14 +68,14 @@ def _cases():
     return out
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture          # function scope on purpose: the two libraries must never be patched in at the same time
 def emul():
     torch.set_num_threads(8)
     with E.emulated_gpu() as lib:
         yield lib
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture
 def emul_full():
     """every kernel from its real source, the tcgen05 / TMA GEMM kernels included (tests/cpu_emul/cuda_emul_tc.h)"""
     torch.set_num_threads(8)
