@@ -264,7 +264,10 @@ class DeepLabV2_VGG16(_EngineBackbone):
         layers += [fc6, nn.ReLU(inplace=True), fc7, nn.ReLU(inplace=True)]
         self.features = nn.Sequential(*layers)
         if pretrained is not None:
-            raise NotImplementedError("loading torchvision vgg16_bn snapshots is done through load_state_dict on this module")
+            # deeplabv2.py:248-250 loads a torchvision vgg16_bn snapshot into the un-modified VGG and then drops pool4 (index 33)
+            # and pool5 (43) from ``features``, so the conv5 modules 34 / 37 / 40 (+ their BN) move down by one
+            print("VGG16: Loading snapshot: ", pretrained)
+            load_torchvision_vgg16_bn(torch.load(pretrained), {"features": self.features}, lambda i: ("features", i if i < 33 else i - 1))
         self.classifier = _Classifier(1024, (6, 12, 18, 24), num_classes)
         if freeze_bn:
             self._freeze_bn(self)
@@ -272,6 +275,37 @@ class DeepLabV2_VGG16(_EngineBackbone):
         self._from_scratch(fc6)
         self._from_scratch(fc7)
         self._init_engine_state(freeze_bn)
+
+
+def load_torchvision_vgg16_bn(sd, containers, where):
+    """Copy the ``features.N.*`` tensors of a torchvision ``vgg16_bn`` state dict (what ``vgg.load_state_dict(torch.load(
+    pretrained))`` consumes in deeplabv2.py:249 / fcn.py:39) into the parameter containers of a B200 backbone.
+    ``where(N) -> (container name, index inside it)``.  Like the reference's strict load, every ``features`` tensor must find
+    its place and every conv / BN of the trunk must be covered; the ``classifier.*`` (fc) entries of the snapshot are required to
+    exist as torchvision writes them, and are dropped exactly as the reference drops ``vgg.classifier``."""
+    want = {}
+    for key, v in sd.items():
+        parts = key.split(".")
+        if parts[0] == "classifier":
+            continue
+        if parts[0] != "features" or len(parts) != 3:
+            raise RuntimeError("unexpected key in vgg16_bn snapshot: %s" % key)
+        name, idx = where(int(parts[1]))
+        want["%s.%d.%s" % (name, idx, parts[2])] = v
+    have = {}
+    for name, seq in containers.items():
+        for k, t in seq.state_dict().items():
+            have["%s.%s" % (name, k)] = t
+    trunk = {k for k in have if int(k.split(".")[1]) <= 41 or k.split(".")[0] != "features"}    # fc6 / fc7 (42, 44) are new layers
+    missing = sorted(k for k in trunk if k not in want)
+    extra = sorted(k for k in want if k not in have)
+    if missing or extra:
+        raise RuntimeError("vgg16_bn snapshot does not match: missing %s, unexpected %s" % (missing[:4], extra[:4]))
+    with torch.no_grad():
+        for k in trunk:
+            if have[k].shape != want[k].shape:
+                raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(want[k].shape), tuple(have[k].shape)))
+            have[k].copy_(want[k])
 
 
 class _UpsampleFn(torch.autograd.Function):

@@ -8,7 +8,7 @@ from collections import OrderedDict
 import torch
 import torch.nn as nn
 
-from .deeplabv2 import _EngineBackbone, _bn
+from .deeplabv2 import _EngineBackbone, _bn, load_torchvision_vgg16_bn
 from .. import engine as E
 
 
@@ -21,8 +21,6 @@ class VGG16_FCN8s(_EngineBackbone):
         assert num_classes == E.NUM_CLASSES, "libsac_b200 kernels are built for 19 classes"
         self.criterion = criterion
         self.drop_rate = drop_rate
-        if pretrained is not None:
-            raise NotImplementedError("load torchvision vgg16_bn snapshots through load_state_dict on block1..3")
         for blk, convs, pools in E.FCN_BLOCKS:
             mods = OrderedDict()
             for (idx, cin, cout) in convs:
@@ -32,6 +30,14 @@ class VGG16_FCN8s(_EngineBackbone):
                 if idx in pools:
                     mods[str(idx + 3)] = nn.MaxPool2d(2, 2)
             setattr(self, blk, nn.Sequential(mods))
+        if pretrained is not None:
+            # fcn.py:27-39: block1 / block2 / block3 are slices [:24] / [24:34] / [34:] of vgg.features and keep torchvision's
+            # module indices, so ``features.N`` lands in the block that holds index N
+            print("VGG16-FCN8s: Loading snapshot: ", pretrained)
+            load_torchvision_vgg16_bn(torch.load(pretrained), {b: getattr(self, b) for b in ("block1", "block2", "block3")},
+                                      lambda i: ("block1" if i < 24 else ("block2" if i < 34 else "block3"), i))
+        else:
+            print("VGG16-FCN8s: Initialising from scratch")
         self.vgg_head = nn.Sequential(
             nn.Conv2d(512, 4096, 7, padding=3), _bn(4096), nn.ReLU(inplace=True), nn.Dropout2d(p=drop_rate),
             nn.Conv2d(4096, 4096, 1), _bn(4096), nn.ReLU(inplace=True), nn.Dropout2d(p=drop_rate),

@@ -92,8 +92,20 @@ class FusedSGD(object):
         self._built = None
         self.steps = 0
         self.p2p = None        # p2p.P2PContext: step() then also performs the gradient all-reduce (one fused kernel)
+        self.frozen = False    # set by TargetStepper.capture(): device tensors are referenced by a CUDA graph from then on
 
-    def _build(self):
+    def _build(self, mom=None):
+        flat = self.backbone._flat
+        ranges, lr, wd = self._tables()
+        dev = flat.buf.device
+        self._built = dict(flat=flat, flat_ptr=flat.buf.data_ptr(), ranges_host=ranges,
+                           ranges=torch.tensor(ranges, dtype=torch.int64, device=dev),
+                           lr=torch.tensor(lr, dtype=torch.float32, device=dev),
+                           wd=torch.tensor(wd, dtype=torch.float32, device=dev), n=len(lr),
+                           mom=torch.zeros_like(flat.buf) if mom is None else mom)
+
+    def _tables(self):
+        """(ranges, lr, wd) host lists over the optimiser tensors in flat-buffer order"""
         bb = self.backbone
         flat = bb._flat
         by_id = {}
@@ -108,15 +120,21 @@ class FusedSGD(object):
             if id(p) not in by_id: continue
             o, n, _, _ = flat.offs[key]
             ranges += [o, o + n]; lr.append(by_id[id(p)][0]); wd.append(by_id[id(p)][1])
-        dev = flat.buf.device
-        self._built = dict(flat=flat, ranges=torch.tensor(ranges, dtype=torch.int64, device=dev),
-                           lr=torch.tensor(lr, dtype=torch.float32, device=dev),
-                           wd=torch.tensor(wd, dtype=torch.float32, device=dev), n=len(lr),
-                           mom=torch.zeros_like(flat.buf))
+        return ranges, lr, wd
 
     def set_lr(self, param_groups):
+        """New learning rates / weight decays (the reference rebuilds nothing either: ``base_trainer`` pokes
+        ``param_group["lr"]``).  The momentum buffer, the segment table and the device tensors that a captured CUDA graph
+        reads through raw pointers all stay where they are; only their contents change."""
         self.param_groups = param_groups
-        self._built = None
+        b = self._built
+        if b is None:
+            return
+        ranges, lr, wd = self._tables()
+        if len(lr) != b["n"] or ranges != b["ranges_host"]:
+            raise ValueError("FusedSGD.set_lr: the set of optimised tensors changed; build a new FusedSGD instead")
+        b["lr"].copy_(torch.tensor(lr, dtype=torch.float32), non_blocking=False)
+        b["wd"].copy_(torch.tensor(wd, dtype=torch.float32), non_blocking=False)
 
     def zero_grad(self):
         for g in self.param_groups:
@@ -125,10 +143,14 @@ class FusedSGD(object):
 
     def step(self):
         bb = self.backbone
-        if self._built is None or self._built["flat"] is not bb._flat:
-            mom = self._built["mom"] if self._built is not None and self._built["flat"] is bb._flat else None
-            self._build()
-            if mom is not None: self._built["mom"] = mom
+        b = self._built
+        if b is None or b["flat"] is not bb._flat or b["flat_ptr"] != bb._flat.buf.data_ptr():
+            # first step, or the flat parameter buffer moved (e.g. re-homed into peer memory by enable_p2p): the layout is
+            # the same, so the momentum accumulated so far is carried over
+            assert not self.frozen, "the flat parameter buffer changed after the step was captured into a CUDA graph"
+            mom = b["mom"] if (b is not None and b["mom"].numel() == bb._flat.buf.numel()
+                               and b["mom"].device == bb._flat.buf.device) else None
+            self._build(mom)
         b = self._built
         if self.p2p is not None:
             # gradient mean over ranks + SGD + weight broadcast in ONE kernel over NVLink peer memory (sacb_allreduce_sgd)
@@ -170,7 +192,6 @@ class TargetStepper(object):
         assert self._graph is None, "enable_p2p() must precede capture()"
         import os
         self.optim.p2p = P2PContext(self.net.backbone, world, rank, self.device, nvls=os.environ.get("SACB_NVLS", "0") == "1")
-        self.optim._built = None
         return self.optim.p2p
 
     def stage_host(self, batch):
@@ -189,6 +210,8 @@ class TargetStepper(object):
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._staging = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host_batch)
             self._staging_free = None
+        assert all(d.shape == s_.shape and d.dtype == s_.dtype for d, s_ in zip(self._staging, host_batch)), \
+            "prefetch(): batch shapes / dtypes differ from the first prefetched batch"
         cs = self._copy_stream
         if self._staging_free is not None:
             cs.wait_event(self._staging_free)               # the previous step has finished reading the staging buffers
@@ -224,10 +247,17 @@ class TargetStepper(object):
     def capture(self, example_batch):
         """Capture one steady-state step (no teacher update) into a CUDA graph: the whole step is a fixed kernel
         schedule, so replaying it removes ~900 launches' worth of host work per step. Steps that update the
-        teacher (every NET_MOMENTUM_ITER) still run eagerly. Call after at least one eager step."""
+        teacher (every NET_MOMENTUM_ITER) still run eagerly. Call after at least one eager step.
+        The two warm-up passes that stream capture needs are real steps on ``example_batch``; parameters, momentum,
+        ``running_conf`` and the step counters are snapshotted before and restored afterwards, so capturing does not train."""
         assert self.iter > 0, "run an eager step first (teacher initialisation, workspace allocation)"
+        bb = self.net.backbone
         self._static = tuple(t.clone() for t in example_batch)
         src = tuple(t.clone() for t in example_batch)
+        if self.optim._built is None:
+            self.optim._build()
+        snap = (bb._flat.buf.clone(), self.optim._built["mom"].clone(), self.net.running_conf.clone(), self.optim.steps, self.iter)
+        self.optim.steps = max(self.optim.steps, 1)      # the captured kernel is the steady-state one (momentum buffer in use)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -242,7 +272,14 @@ class TargetStepper(object):
             self._graph_losses = self._eager(self._static, False)
         self._graph_launches = L.launch_count() - n0      # kernel nodes of ours inside the graph
         self._graph = g
-        self.iter += 2
+        self.optim.frozen = True
+        bb._flat.buf.copy_(snap[0]); self.optim._built["mom"].copy_(snap[1]); self.net.running_conf.copy_(snap[2])
+        bb.mark_dirty()
+        self.optim.steps, self.iter = snap[3], snap[4]
+        if self.optim.steps == 0:
+            # a graph captured before any optimiser step would have baked first_step=1 in; the momentum buffer is zero
+            # then, and buf = 0.9 * 0 + d == d, so the steady-state kernel gives the same first update
+            self.optim.steps = 1
         return g
 
     def step(self, batch, update_teacher=None, read_losses=False, prefetch_next=None):
@@ -258,7 +295,7 @@ class TargetStepper(object):
                 self._release_staging()
             self._graph.replay()
             self.launches += self._graph_launches
-            v = self._graph_losses
+            v = self._graph_losses.clone()                                          # the next replay overwrites the static output
         else:
             if staged is not None:
                 batch = tuple(t.clone() for t in staged)                            # y is mutated in place (sac.py:338)

@@ -4,9 +4,8 @@
 (2) one iteration of the reference's BASELINE recipe -- source step with SGD, no-grad target pass, eval forward -- against the
     golden vectors produced by the REAL reference (tests/golden/make_golden_abn.py).
 
-These tests were written after round 1's GPU budget was spent: the kernels compile and the oracle for this mode is pinned on
-the CPU (tests/test_abn_cpu.py), but this file has not run on a B200 yet.  Until it has, it only runs when
-SACB_RUN_UNVERIFIED=1 is set, so that an untested path cannot turn the parity gate of the verified SAC path red.
+First run on a B200 in round 2 (7 passed, profiles/r2a_test_abn_gpu.log); the oracle for this mode is pinned on the CPU
+(tests/test_abn_cpu.py).
 """
 import os
 
@@ -18,9 +17,7 @@ import torch.nn.functional as F
 import bn_kernel_checks as K
 from bn_kernel_checks import join, rel, split  # noqa: F401
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
-                                 reason="ABN-baseline GPU path not yet verified on a B200 (set SACB_RUN_UNVERIFIED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EPS, MOM = 1e-5, 0.1

@@ -25,5 +25,5 @@ def test_collecting_the_gpu_suite_leaves_the_unverified_gates_shut():
     assert line, r.stdout[-2000:] + r.stderr[-2000:]
     f = dict(kv.split("=") for kv in line[0].split()[1:])
     assert f["env"] == "None", "a test module sets SACB_RUN_UNVERIFIED at import"
-    assert int(f["gated"]) >= 20 and f["gated"] == f["shut"], line[0]
-    assert int(f["selected"]) - int(f["gated"]) >= 41          # the verified suite (profiles/pytest_gpu_r1q.log) is still all there
+    assert f["gated"] == f["shut"], line[0]
+    assert int(f["selected"]) - int(f["gated"]) >= 62          # the verified suite (round 1: 41; un-gated in round 2: ABN 7, staged 1, tail split 1, fast modes 12)

@@ -2,17 +2,15 @@
 fprop + BN affine + residual + ReLU of the 1x1 expand layers and the dgrad-with-skip-gradient form, against fp64, and
 bit-identical to the default kernel (same MMA order, same epilogue arithmetic -- only where the residual is read from differs).
 
-The switch is read once per process, so the check runs in a subprocess.  Written after round 1's GPU budget was spent: not yet
-run on a B200, therefore gated behind SACB_RUN_UNVERIFIED=1 like tests/test_abn_gpu.py."""
+The switch is read once per process, so the check runs in a subprocess.  Green on a B200 since round 2
+(profiles/r2a_test_staged_epilogue_gpu.log)."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
-                                 reason="residual-staging pair kernel not yet verified on a B200 (set SACB_RUN_UNVERIFIED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -2,16 +2,14 @@
 wave run as two 256 x 128 halves (MMA N = 128).  Same k order per output element, so the planes must be bit-identical to the
 default kernel's; also checked against fp64.  The switch is read once per process -> subprocesses.
 
-Written after round 1's GPU budget was spent: not yet run on a B200, gated behind SACB_RUN_UNVERIFIED=1."""
+Green on a B200 since round 2 (profiles/r2a_test_tail_split_gpu.log); the switch stays off by default because it measured slower."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
-                                 reason="tail-split pair kernel not yet verified on a B200 (set SACB_RUN_UNVERIFIED=1 to run)")]
+pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
