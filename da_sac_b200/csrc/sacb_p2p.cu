@@ -12,6 +12,7 @@
 // Every wait is bounded and traps instead of hanging the GPU.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "sacb_common.cuh"
 #include "../../include/sacb.h"
@@ -24,7 +25,10 @@ constexpr int FLAG_ARRIVE = 0;                 // [MAXW]  peer p -> "my gradient
 constexpr int FLAG_DONE = P2P_MAXW;            // [MAXW]  peer p -> "my slice of epoch e is stored in your parameters"
 constexpr int FLAG_EPOCH = 2 * P2P_MAXW;       // completed epochs of THIS rank
 constexpr int FLAG_BLOCKS = 2 * P2P_MAXW + 1;  // blocks of the running kernel that finished their share
-constexpr long long SPIN_LIMIT = 40LL * 1000 * 1000 * 1000;   // ~20 s of SM clocks, then trap
+// A rank that waits for a peer gives up (trap, never a silent hang) after SACB_P2P_TIMEOUT_S seconds of SM clocks: default
+// 600 s, the order of NCCL's watchdog, so that ordinary rank skew -- a checkpoint write on rank 0, a dataloader stall at an epoch
+// boundary, a debugger -- does not kill the context.
+constexpr double SPIN_CLOCK_HZ = 2.0e9;
 
 struct P2PArgs {
   float* grads[P2P_MAXW];
@@ -36,6 +40,7 @@ struct P2PArgs {
   int nseg, world, rank, first;
   long long vec_lo, vec_hi;      // this rank's slice in float4 units
   float mu, inv_world;
+  long long spin_limit;          // SM clocks a cross-rank wait may take before the kernel traps
 };
 
 SACB_DEVINL void st_release_sys(uint32_t* p, uint32_t v) {
@@ -65,11 +70,11 @@ SACB_DEVINL float4 multimem_ld_reduce_add_f4(const float* mc) {
 SACB_DEVINL void multimem_st_f4(float* mc, const float4& v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-SACB_DEVINL void spin_until(const uint32_t* flag, uint32_t epoch) {
+SACB_DEVINL void spin_until(const uint32_t* flag, uint32_t epoch, long long spin_limit) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > SPIN_LIMIT) { printf("sacb allreduce_sgd: peer flag timeout (epoch %u)\n", epoch); __trap(); }
+    if (clock64() - t0 > spin_limit) { printf("sacb allreduce_sgd: peer flag timeout (epoch %u)\n", epoch); __trap(); }
   }
 }
 
@@ -88,7 +93,7 @@ allreduce_sgd_kernel(const P2PArgs a) {
     __threadfence_system();
     st_release_sys(a.flags[threadIdx.x] + FLAG_ARRIVE + a.rank, epoch);
   }
-  if (threadIdx.x < a.world) spin_until(my_flags + FLAG_ARRIVE + threadIdx.x, epoch);
+  if (threadIdx.x < a.world) spin_until(my_flags + FLAG_ARRIVE + threadIdx.x, epoch, a.spin_limit);
   __syncthreads();
 
   // ---- reduce-scatter + SGD + all-gather on this rank's slice
@@ -151,7 +156,7 @@ allreduce_sgd_kernel(const P2PArgs a) {
   if (threadIdx.x < a.world) {
     __threadfence_system();
     st_release_sys(a.flags[threadIdx.x] + FLAG_DONE + a.rank, epoch);
-    spin_until(my_flags + FLAG_DONE + threadIdx.x, epoch);
+    spin_until(my_flags + FLAG_DONE + threadIdx.x, epoch, a.spin_limit);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -212,6 +217,12 @@ extern "C" int sacb_allreduce_sgd(const SacbAllreduceSgd* d, void* stream) {
   a.vec_lo = per * d->rank < nvec ? per * d->rank : nvec;
   a.vec_hi = a.vec_lo + per < nvec ? a.vec_lo + per : nvec;
   a.mu = d->momentum; a.inv_world = 1.f / (float)d->world;
+  static double timeout_s = -1.0;
+  if (timeout_s < 0) {
+    const char* e = getenv("SACB_P2P_TIMEOUT_S");
+    timeout_s = (e && atof(e) > 0) ? atof(e) : 600.0;
+  }
+  a.spin_limit = (long long)(timeout_s * SPIN_CLOCK_HZ);
   int dev = 0, sms = 148;
   SACB_CHECK_CUDA(cudaGetDevice(&dev));
   SACB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -777,9 +777,20 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   const int C = d->C, HW = d->H * d->W, CP = (C + 3) / 4 * 4, CP2 = (C + 1 + 3) / 4 * 4;
   const int nb = (HW + 255) / 256;
   dim3 gridB(nb, d->BT), gridG(nb, d->BT / d->T);
-  SACB_REQUIRE(d->phase >= 0 && d->phase <= 2, "sacb_teacher_tail: phase must be 0, 1 or 2");
+  SACB_REQUIRE(d->phase >= 0 && d->phase <= 3, "sacb_teacher_tail: phase must be 0, 1, 2 or 3");
+  if (d->phase == 3) {
+    // diagnostics only: `pooled` (and `probs` when pooling is off) still hold this forward's normalised reference-frame
+    // probabilities; warp them back once more to materialise `refined` (sac.py:309-311).  conf / idx / peaks are rewritten with
+    // the values they already hold (atomicMax onto itself); running_conf, thresholds, labels and conf_mean are not touched and no
+    // exchange between ranks is needed.
+    SACB_REQUIRE(d->refined != nullptr, "sacb_teacher_tail: phase 3 materialises `refined`");
+    tail_refine_kernel<C_><<<gridB, 256, 0, ST>>>(d->pooled, d->affine_inv, d->conf, d->idx, reinterpret_cast<int*>(d->peaks),
+                                                 d->refined, d->T, C, CP2, d->H, d->W, d->pool_mode == 2 ? d->probs : nullptr, CP);
+    LAUNCHED();
+    return 0;
+  }
   SACB_REQUIRE(d->pool_mode >= 0 && d->pool_mode <= 2, "sacb_teacher_tail: pool_mode must be 0 (avg), 1 (min-entropy) or 2 (off)");
-  SACB_REQUIRE(d->pool_mode == 0 || d->phase == 0, "sacb_teacher_tail: fractional groups need the average pool");
+  SACB_REQUIRE(d->pool_mode == 0 || d->phase == 0 || d->phase == 3, "sacb_teacher_tail: fractional groups need the average pool");
   if (d->phase != 2) {
     tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
     LAUNCHED();

@@ -138,8 +138,9 @@ class _StudentLossFn(torch.autograd.Function):
         L.check(L.lib().sacb_student_loss_fwd(C.byref(desc), L.stream()), "sacb_student_loss_fwd")
         ctx.sac, ctx.logits, ctx.y, ctx.tail = sac, logits, y, tail
         ctx.set_materialize_grads(False)
-        both = keep["losses"].clone()
-        return both[0:1], both[1:2]
+        # two independent tensors, not two views of one: train.py:243-245 all-reduces and divides every loss IN PLACE, which
+        # autograd refuses for "the output of a function that returns multiple views"
+        return keep["losses"][0:1].clone(), keep["losses"][1:2].clone()
 
     @staticmethod
     def backward(ctx, g_ce, g_self):
@@ -219,7 +220,7 @@ class SAC(SAC_Baseline):
                 losses=torch.empty(2, **f32), scratch=torch.empty(2, device=dev, dtype=torch.float64))
         return self._ws[key]
 
-    def _tail(self, teacher_logits, y_raw, affine, affine_inv, T, refined=None):
+    def _tail(self, teacher_logits, y_raw, affine, affine_inv, T, refined=None, refine_only=False):
         BT, Cn, h, w = teacher_logits.shape
         H, W = y_raw.shape[-2:]
         # fractional group (sac.py:243-245, _gather :198-216): this rank holds T0 < T views of ONE group; the other
@@ -238,6 +239,11 @@ class SAC(SAC_Baseline):
                           L.ptr(ws["probs"]), L.ptr(ws["pooled"]), L.ptr(ws["part_sums"]), L.ptr(ws["peaks"]),
                           L.ptr(ws["conf"]), L.ptr(ws["idx"]), L.ptr(ws["labels"]), L.ptr(ws["conf_mean"]),
                           L.ptr(ws["thresholds"]), L.ptr(refined), phase, self._pool_mode)
+        if refine_only:
+            # lazy net_outs["teacher_refined"]: one more warp of the pooled probabilities this forward left in the workspace;
+            # no running_conf update, no label rewrite, no exchange between ranks
+            L.check(L.lib().sacb_teacher_tail(C.byref(desc(3)), L.stream()), "sacb_teacher_tail(refined)")
+            return ws
         if T0 == T or self._pool_mode == 2:
             L.check(L.lib().sacb_teacher_tail(C.byref(desc(0)), L.stream()), "sacb_teacher_tail")
             return ws
@@ -298,6 +304,12 @@ class SAC(SAC_Baseline):
             return logits, upsample(logits, *x.shape[-2:])
         if reset_teacher:
             self.slow_init[0] = False
+        # the kernels read raw device memory: labels as int64 (what the loaders produce and nn.CrossEntropyLoss demands of the
+        # reference), images / affine matrices as fp32 (converted below where needed)
+        if y.dtype != torch.int64:
+            raise TypeError("SAC.forward: y must be int64 (got %s)" % y.dtype)
+        if use_teacher and (x2 is None or affine is None or affine_inv is None or T is None):
+            raise ValueError("SAC.forward(use_teacher=True) needs x2, affine, affine_inv and T")
         y_raw = y.clone()                                                # keeps the -1 padding marker for the kernels
         y.masked_fill_(y == -1, 255)                                     # in-place on the caller's tensor (sac.py:337-338)
         losses = {}
@@ -338,19 +350,32 @@ class SAC(SAC_Baseline):
         outs.lazy("logits_up", lambda: upsample(s_logits.detach(), H, W))
         if use_teacher:
             losses["self_ce"] = self_ce                                  # sac.py:360-361
-            outs["teacher_conf"] = tail["conf"]
+            # the tail's buffers are workspace that the next forward overwrites; what net_outs hands out are copies, made when
+            # (and if) a caller reads them -- the reference returns fresh tensors (sac.py:362-371)
+            outs.lazy("teacher_conf", lambda: tail["conf"].clone())
             outs["running_conf"] = self.running_conf
             outs.lazy("teacher_labels", lambda: tail["labels"].long())
             outs.lazy("teacher_init", lambda: upsample(t_logits, H, W))
 
             def _refined():
                 r = torch.empty(x.shape[0], E.NUM_CLASSES, H, W, device=dev)
-                saved = self.running_conf.clone(); was = self.training
-                self.training = False                                     # do not update running_conf twice
-                self._tail(t_logits, y_raw, affine, affine_inv, T, refined=r)
-                self.training = was; self.running_conf.copy_(saved)
+                self._tail(t_logits, y_raw, affine, affine_inv, T, refined=r, refine_only=True)
                 return r
             outs.lazy("teacher_refined", _refined)
+            if self._pool_mode != 2:
+                # diagnostics of _refine (sac.py:292-296; read by base_trainer._visualise :171-173 only): the masked teacher
+                # probabilities and the clean frames warped to the reference frame.  Visualisation path, not the hot path: plain
+                # torch ops on the up-sampled teacher logits, produced on first access.
+                def _aligned(t):
+                    grid = torch.nn.functional.affine_grid(affine.float(), size=t.size(), align_corners=False)
+                    return torch.nn.functional.grid_sample(t, grid, align_corners=False)
+
+                def _teacher_aligned():
+                    p = torch.softmax(upsample(t_logits, H, W), 1)
+                    p *= 1 - (y_raw == -1)[:, None].type_as(p)
+                    return _aligned(p)
+                outs.lazy("teacher_aligned", _teacher_aligned)
+                outs.lazy("frames_aligned", lambda: _aligned(x2.float()))
             losses["teacher_diff"] = self._momentum_update(False)        # sac.py:374
         return losses, outs
 

@@ -176,6 +176,7 @@ class TargetStepper(object):
         self.iter = 0
         self._pinned = None
         self._graph = None
+        self._graph_upd = None
         self._static = None
         self._graph_losses = None
         self._graph_launches = 0
@@ -244,43 +245,65 @@ class TargetStepper(object):
         self.optim.step()                                                           # train.py:233
         return torch.cat([losses["loss_ce"].detach(), losses["self_ce"].detach(), losses["teacher_diff"].detach()])
 
-    def capture(self, example_batch):
-        """Capture one steady-state step (no teacher update) into a CUDA graph: the whole step is a fixed kernel
-        schedule, so replaying it removes ~900 launches' worth of host work per step. Steps that update the
-        teacher (every NET_MOMENTUM_ITER) still run eagerly. Call after at least one eager step.
-        The two warm-up passes that stream capture needs are real steps on ``example_batch``; parameters, momentum,
-        ``running_conf`` and the step counters are snapshotted before and restored afterwards, so capturing does not train."""
+    def capture(self, example_batch, teacher_update_graph=True):
+        """Capture the step into CUDA graphs: the whole step is a fixed kernel schedule, so replaying it removes ~900
+        launches' worth of host work per step.  Two graphs: the steady-state step and (``teacher_update_graph``) the step
+        that also applies the teacher EMA (every NET_MOMENTUM_ITER-th, train.py:294).  Call after at least one eager step.
+        The warm-up passes that stream capture needs are real steps on ``example_batch``; student / teacher parameters,
+        momentum, ``running_conf`` and the step counters are snapshotted before and restored afterwards, so capturing does
+        not train."""
         assert self.iter > 0, "run an eager step first (teacher initialisation, workspace allocation)"
-        bb = self.net.backbone
+        bb, tn = self.net.backbone, self.net.slow_net
         self._static = tuple(t.clone() for t in example_batch)
         src = tuple(t.clone() for t in example_batch)
         if self.optim._built is None:
             self.optim._build()
-        snap = (bb._flat.buf.clone(), self.optim._built["mom"].clone(), self.net.running_conf.clone(), self.optim.steps, self.iter)
+        snap = (bb._flat.buf.clone(), self.optim._built["mom"].clone(), self.net.running_conf.clone(), tn._flat.buf.clone(),
+                self.optim.steps, self.iter)
         self.optim.steps = max(self.optim.steps, 1)      # the captured kernel is the steady-state one (momentum buffer in use)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                for d, s_ in zip(self._static, src): d.copy_(s_)
-                self._eager(self._static, False)
-        torch.cuda.current_stream().wait_stream(side)
-        for d, s_ in zip(self._static, src): d.copy_(s_)
-        g = torch.cuda.CUDAGraph()
-        n0 = L.launch_count()
-        with torch.cuda.graph(g):
-            self._graph_losses = self._eager(self._static, False)
-        self._graph_launches = L.launch_count() - n0      # kernel nodes of ours inside the graph
-        self._graph = g
+
+        def one(update):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    for d, s_ in zip(self._static, src): d.copy_(s_)
+                    self._eager(self._static, update)
+            torch.cuda.current_stream().wait_stream(side)
+            for d, s_ in zip(self._static, src): d.copy_(s_)
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(g):
+                losses = self._eager(self._static, update)
+            return g, losses, L.launch_count() - n0       # kernel nodes of ours inside the graph
+
+        self._graph, self._graph_losses, self._graph_launches = one(False)
+        self._graph_upd = one(True) if teacher_update_graph else None
         self.optim.frozen = True
         bb._flat.buf.copy_(snap[0]); self.optim._built["mom"].copy_(snap[1]); self.net.running_conf.copy_(snap[2])
-        bb.mark_dirty()
-        self.optim.steps, self.iter = snap[3], snap[4]
+        tn._flat.buf.copy_(snap[3])
+        bb.mark_dirty(); tn.mark_dirty()
+        with torch.no_grad():
+            tn._planes(False)            # the steady-state graph does not re-derive the teacher's weight planes
+        self.optim.steps, self.iter = snap[4], snap[5]
         if self.optim.steps == 0:
             # a graph captured before any optimiser step would have baked first_step=1 in; the momentum buffer is zero
             # then, and buf = 0.9 * 0 + d == d, so the steady-state kernel gives the same first update
             self.optim.steps = 1
-        return g
+        return self._graph
+
+    def drop_graphs(self):
+        self._graph = self._graph_upd = None
+        self.optim.frozen = False
+
+    def suspend_graphs(self):
+        """eager launches for a while (per-launch profiling); returns the token for ``resume_graphs``"""
+        tok = (self._graph, getattr(self, "_graph_upd", None))
+        self._graph = self._graph_upd = None
+        return tok
+
+    def resume_graphs(self, tok):
+        self._graph, self._graph_upd = tok
 
     def step(self, batch, update_teacher=None, read_losses=False, prefetch_next=None):
         """one Trainer._step_target(train=True); ``batch`` may live on the device or in pinned host memory.
@@ -288,14 +311,17 @@ class TargetStepper(object):
         if update_teacher is None:
             update_teacher = (self.iter % self.cfg.NET_MOMENTUM_ITER == 0)          # train.py:294
         staged = None if batch[0].is_cuda else self._take_prefetched(batch)
-        if self._graph is not None and not update_teacher:
+        graph = None
+        if self._graph is not None:
+            graph = (self._graph, self._graph_losses, self._graph_launches) if not update_teacher else getattr(self, "_graph_upd", None)
+        if graph is not None:
             for d, s_ in zip(self._static, batch if staged is None else staged):
                 d.copy_(s_, non_blocking=True)                                      # H2D when ``batch`` is pinned host memory
             if staged is not None:
                 self._release_staging()
-            self._graph.replay()
-            self.launches += self._graph_launches
-            v = self._graph_losses.clone()                                          # the next replay overwrites the static output
+            graph[0].replay()
+            self.launches += graph[2]
+            v = graph[1].clone()                                                    # the next replay overwrites the static output
         else:
             if staged is not None:
                 batch = tuple(t.clone() for t in staged)                            # y is mutated in place (sac.py:338)

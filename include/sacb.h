@@ -216,7 +216,9 @@ typedef struct SacbTail {
   float* refined;                /* optional [BT,C,H,W] teacher_refined, NULL to skip */
   /* fractional groups (train.py:185-209, sac.py:198-216: a group's T views spread over several ranks, here T = the
    * views THIS rank holds): 0 = whole tail; 1 = stop after writing the un-normalised reference-frame sums to `pooled`
-   * (the caller sum-reduces `pooled` over the ranks sharing the group); 2 = resume: normalise `pooled`, labels. */
+   * (the caller sum-reduces `pooled` over the ranks sharing the group); 2 = resume: normalise `pooled`, labels;
+   * 3 = diagnostics after 0 or 2 of the same forward: only warp `pooled` back once more into `refined` (net_outs
+   * "teacher_refined"); running_conf, thresholds, labels and conf_mean are left alone and no exchange is needed. */
   int32_t phase;
   /* MODEL.CONF_POOL / CONF_POOL_ON (core/config.py:150-151): 0 = avg_pool (sac.py:238-269, default), 1 = minentropy_pool
    * (sac.py:218-236: every view receives the distribution of the group's lowest-entropy view), 2 = pooling off
