@@ -400,10 +400,15 @@ def main():
         p0, m0, g0, steps0 = bb._flat.buf.clone(), b_["mom"].clone(), bb._grad.buf.clone(), opt.steps
         opt.step()                                               # (a) fused
         torch.cuda.synchronize()
-        p_fused = bb._flat.buf.clone()
-        bb._flat.buf.copy_(p0); b_["mom"].copy_(m0); opt.steps = steps0
+        barrier()
+        p_fused, m_fused = bb._flat.buf.clone(), b_["mom"].clone()
+        # (b) NCCL + sacb_sgd from the same state.  The fused kernel keeps the momentum SHARDED (ZeRO-1: a rank only ever touches
+        # the slice it owns, the rest of its buffer stays zero), so the full momentum is the sum of the ranks' buffers.
+        m_full = m0.clone()
+        dist.all_reduce(m_full)
+        bb._flat.buf.copy_(p0); b_["mom"].copy_(m_full); opt.steps = steps0
         gref = g0.clone()
-        allreduce_mean_(gref)                                    # (b) NCCL + sacb_sgd on private copies of the same state
+        allreduce_mean_(gref)
         import ctypes as C
         L.check(L.lib().sacb_sgd(L.ptr(bb._flat.buf), L.ptr(gref), L.ptr(b_["mom"]), L.ptr(b_["ranges"]), L.ptr(b_["lr"]), L.ptr(b_["wd"]),
                                  b_["n"], C.c_float(opt.momentum), 1 if steps0 == 0 else 0, L.stream()), "sacb_sgd")
@@ -425,8 +430,8 @@ def main():
         note("exchange check: %s" % exchange_check)
         assert replicas_equal, "replicas diverged after the fused exchange"
         assert bit_exact or (world > 2 and stats[1].item() < 1e-6), "fused exchange differs from NCCL all-reduce + SGD: %s" % exchange_check
-        # continue from the fused result (identical on all ranks); momentum of step (b) == momentum of step (a) up to the same bound
-        bb._flat.buf.copy_(p_fused); opt.steps = steps0 + 1
+        # continue from the fused result (identical on all ranks) with the fused kernel's own (sharded) momentum
+        bb._flat.buf.copy_(p_fused); b_["mom"].copy_(m_fused); opt.steps = steps0 + 1
         bb.mark_dirty()
         barrier()
 

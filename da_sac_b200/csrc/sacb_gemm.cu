@@ -829,6 +829,343 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
   if (warp == 1) tmem2_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair fprop / dgrad for the EPILOGUE-BOUND layers (1x1 expand convs: short K loop, 4 bytes of output -- and up to 6 bytes
+// of residual / mask input -- per accumulator element; profiles/r2c_*: the default epilogue sat 45 % of its samples on the first
+// use of the residual LDG and spent 44 % of its instructions on the shuffle transposes that make the STGs line-coalesced).
+//   * residual / ReLU-mask planes are PREFETCHED into registers one 32-channel chunk ahead -- the first chunk of a tile while
+//     the warp still waits for the accumulator, the first chunk of the NEXT tile during the last chunk of this one -- so every
+//     epilogue warp keeps 4 KB (6 KB with a mask) of loads in flight all the time;
+//   * outputs leave through shared memory and TMA: each epilogue warp packs its 32 rows x 64 channels into a SWIZZLE_128B slab
+//     (conflict-free 16-byte STS) and one elected lane issues cp.async.bulk.tensor stores (SASS: UTMASTG) for the hi and the lo
+//     plane -- full 128-byte lines, no lane transposes, no LSU store traffic; rows past M are clipped by the tensor map.
+// Main loop, barrier protocol and arithmetic (order of operations included) are those of conv_gemm_pair_kernel: the planes
+// are bit-identical to the default kernel's (tests/test_staged_epilogue_gpu.py).  Two operand stages (enough for <= 8
+// k-blocks per tile) + 64 KB of store slabs.
+// ------------------------------------------------------------------------------------------------
+SACB_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+SACB_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+SACB_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+SACB_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+SACB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+constexpr uint32_t SLAB_PLANE_BYTES = 32 * 64 * 2;                 // [32 rows][64 channels] bf16 = one warp, one plane, one piece
+constexpr uint32_t SLAB_BYTES = 2 * SLAB_PLANE_BYTES;              // hi + lo
+struct Pair2Cfg {
+  static constexpr uint32_t B_BYTES = (PAIR_BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = 2;
+  static constexpr int TMEM_COLS = 2 * PAIR_BN;
+  static constexpr size_t OPER_BYTES = (size_t)STAGES * STAGE_BYTES;
+  static constexpr size_t SLABS = (size_t)EPI_WARPS * SLAB_BYTES;
+  static constexpr size_t SMEM = OPER_BYTES + SLABS + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
+};
+
+// one 32-channel chunk of residual / mask planes of one row, as loaded (bf16 pairs)
+template <bool RES, bool MASK>
+struct ChunkPref {
+  uint32_t h[RES ? 16 : 1], l[RES ? 16 : 1], m[MASK ? 16 : 1];
+};
+template <bool RES, bool MASK>
+SACB_DEVINL void prefetch_chunk(const GemmArgs& a, int m, int c0, ChunkPref<RES, MASK>& p) {
+  if (m < a.M_total) {
+    const size_t row = (size_t)m * a.N_total + c0;
+    if constexpr (RES) {
+      uint32_t t[8];
+      ldg256(a.add_hi + row, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.h[j] = t[j];
+      ldg256(a.add_hi + row + 16, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.h[8 + j] = t[j];
+      ldg256(a.add_lo + row, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.l[j] = t[j];
+      ldg256(a.add_lo + row + 16, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.l[8 + j] = t[j];
+    }
+    if constexpr (MASK) {
+      uint32_t t[8];
+      ldg256(a.mask_hi + row, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.m[j] = t[j];
+      ldg256(a.mask_hi + row + 16, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) p.m[8 + j] = t[j];
+    }
+  } else {
+    if constexpr (RES) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { p.h[j] = 0u; p.l[j] = 0u; }
+    }
+    if constexpr (MASK) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p.m[j] = 0u;
+    }
+  }
+}
+
+// fused math of one chunk (same operations in the same order as epilogue_row) -> packed words into the warp's slab
+template <bool RES, bool MASK>
+SACB_DEVINL void epilogue2_chunk(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
+                                 float* __restrict__ s_colsum, uint32_t (&r)[32], const ChunkPref<RES, MASK>& pf, int m, int c0,
+                                 int lane, uint8_t* slab_hi_row, uint8_t* slab_lo_row, int e) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  if (a.scale) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * i);
+      const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * i);
+      v[4 * i + 0] = fmaf(v[4 * i + 0], sc.x, sh.x); v[4 * i + 1] = fmaf(v[4 * i + 1], sc.y, sh.y);
+      v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
+    }
+  }
+  if constexpr (RES) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float h0 = bf16_bits_to_float(pf.h[j] & 0xFFFF), h1 = bf16_bits_to_float(pf.h[j] >> 16);
+      const float l0 = bf16_bits_to_float(pf.l[j] & 0xFFFF), l1 = bf16_bits_to_float(pf.l[j] >> 16);
+      v[2 * j] += h0 + l0; v[2 * j + 1] += h1 + l1;
+    }
+  }
+  if (a.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if constexpr (MASK) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float m0 = bf16_bits_to_float(pf.m[j] & 0xFFFF), m1 = bf16_bits_to_float(pf.m[j] >> 16);
+      v[2 * j] = m0 > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = m1 > 0.f ? v[2 * j + 1] : 0.f;
+    }
+  }
+  // 32 channels = four 16-byte chunks of the row's 128-byte line, positions 4e .. 4e+3 XOR-swizzled by (row & 7)
+  const int sw = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_pack(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], ph[j], pl[j]);
+    const int pos = ((4 * e + i) ^ sw) << 4;
+    sts128(slab_hi_row + pos, ph[0], ph[1], ph[2], ph[3]);
+    sts128(slab_lo_row + pos, pl[0], pl[1], pl[2], pl[3]);
+  }
+  if (a.colsum) {                          // uniform across the warp
+    if (m >= a.M_total) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    }
+    const float cs = warp_colsum32(v, lane);
+    atomicAdd(&s_colsum[c0 + lane], cs);
+  }
+}
+
+template <bool RES, bool MASK, bool FAST = false>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                       const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+                       const GemmArgs a) {
+  using Cfg = Pair2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = PAIR_BN;
+  constexpr size_t BAR_OFF = Cfg::OPER_BYTES + Cfg::SLABS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* slabs = smem + Cfg::OPER_BYTES;                        // 1024-byte aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(smem + BAR_OFF + 256);
+  float* s_shift = s_scale + MAX_AFFINE;
+  float* s_colsum = s_shift + MAX_AFFINE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmOh); prefetch_tmap(&tmOl);
+  }
+  if (a.scale) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
+  }
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) s_colsum[i] = 0.f;
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem2_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int k_blocks = a.taps * a.kc_blocks;
+  const int unit0 = (int)cluster_id_x(), unit_step = (int)cluster_count_x();
+  const int m_pairs = (a.M_total + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = a.N_total / BN;
+  const int total_units = m_pairs * n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps{0, 0};
+      const int pq = a.P * a.Q;
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+        const int m0 = m_idx * 2 * BM + crank * BM;
+        const int n_img = m0 / pq;
+        const int rem = m0 - n_img * pq;
+        const int p = rem / a.Q, q = rem - p * a.Q;
+        const int w0 = q * a.stride + a.lower, h0 = p * a.stride + a.lower;
+        const int brow = n_idx * BN + crank * (BN / 2);
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const int r = tap / a.S, s = tap - r * a.S;
+          const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
+          for (int cb = 0; cb < a.kc_blocks; ++cb) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+            const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? Cfg::STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
+            tma2_load_im2col(&tmAh, lbar, st, cb * BK, w0, h0, n_img, ow, oh);
+            if constexpr (!FAST) tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+            tma2_load_3d(&tmBh, lbar, st + 2 * A_BYTES, cb * BK, brow, tap);
+            if constexpr (!FAST) tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
+            ps.advance<STAGES>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      PipeState ps{0, 0};
+      int acc = 0; uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_lo = sa_hi + A_BYTES;
+          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
+          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 32, 16, 1024);
+            const uint64_t dal = make_smem_desc_sw128(sa_lo + k * 32, 16, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(sb_hi + k * 32, 16, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(sb_lo + k * 32, 16, 1024);
+            if constexpr (FAST) {
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, accumulate);
+            } else {
+              tc2_mma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              tc2_mma_bf16(tmem_d, dah, dbl, idesc, 1);
+              tc2_mma_bf16(tmem_d, dah, dbh, idesc, 1);
+            }
+            accumulate = 1;
+          }
+          tc2_commit_mc(&empty_bar[ps.stage], 0x3);
+          ps.advance<STAGES>();
+        }
+        tc2_commit_mc(&tfull_bar[acc], 0x3);
+        acc ^= 1; if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* slab_hi = slabs + (size_t)(warp - 2) * SLAB_BYTES;
+    uint8_t* slab_lo = slab_hi + SLAB_PLANE_BYTES;
+    uint8_t* slab_hi_row = slab_hi + lane * 128;
+    uint8_t* slab_lo_row = slab_lo + lane * 128;
+    int acc = 0; uint32_t acc_phase = 0;
+    // this warp's part of a tile: rows m_tile0 + quad*32 .. +32, channels n_col0 + half*128 .. +128 = 2 pieces x 2 chunks
+    ChunkPref<RES, MASK> pfA, pfB;
+    auto tile_rc = [&](int unit, int& m_warp0, int& c_warp0) {
+      const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
+      m_warp0 = m_idx * 2 * BM + crank * BM + quad * 32;
+      c_warp0 = n_idx * BN + half * (BN / 2);
+    };
+    if (unit0 < total_units) {
+      int mw, cw;
+      tile_rc(unit0, mw, cw);
+      prefetch_chunk<RES, MASK>(a, mw + lane, cw, pfA);           // in flight while the first accumulator is produced
+    }
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
+      int m_warp0, c_warp0;
+      tile_rc(unit, m_warp0, c_warp0);
+      const int m = m_warp0 + lane;
+      int m_next = 0, c_next = 0;
+      const bool has_next = unit + unit_step < total_units;
+      if (has_next) tile_rc(unit + unit_step, m_next, c_next);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
+#pragma unroll 1
+      for (int jp = 0; jp < 2; ++jp) {
+        const int c_piece = c_warp0 + jp * 64;
+        uint32_t r[32];
+        tmem_ld32(tbase + jp * 64, r);
+        prefetch_chunk<RES, MASK>(a, m, c_piece + 32, pfB);       // second chunk of this piece
+        tmem_ld_wait();
+        // the slab is free once the TMA store of the previous piece has read it (issued one piece of math ago)
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        epilogue2_chunk<RES, MASK>(a, s_scale, s_shift, s_colsum, r, pfA, m, c_piece, lane, slab_hi_row, slab_lo_row, 0);
+        tmem_ld32(tbase + jp * 64 + 32, r);
+        // first chunk of the next piece: same tile, or the next tile of this cluster
+        if (jp == 0) prefetch_chunk<RES, MASK>(a, m, c_piece + 64, pfA);
+        else if (has_next) prefetch_chunk<RES, MASK>(a, m_next + lane, c_next, pfA);
+        tmem_ld_wait();
+        epilogue2_chunk<RES, MASK>(a, s_scale, s_shift, s_colsum, r, pfB, m, c_piece + 32, lane, slab_hi_row, slab_lo_row, 1);
+        fence_proxy_async();                                      // generic-proxy STS -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0 && m_warp0 < a.M_total) {
+          tma_store_2d(&tmOh, slab_hi, c_piece, m_warp0);
+          tma_store_2d(&tmOl, slab_lo, c_piece, m_warp0);
+          bulk_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&tempty_bar[acc], 0);
+      acc ^= 1; if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait0();                                  // all stores of this warp have landed before the CTA exits
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (a.colsum) {
+    for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) {
+      const float cs = s_colsum[i];
+      if (cs != 0.f) atomicAdd(&a.colsum[i], cs);
+    }
+  }
+  if (warp == 1) tmem2_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------
 // wgrad:  D[rows, cols] (+)= sum_{pixels} A[pixels, rows] * B[pixels, cols]   (both operands MN-major)
 //   swap=0: rows = output channels (G, tiled map), cols = input channels (X, im2col map)
@@ -1238,6 +1575,9 @@ static bool g_no_bn256 = false;       // SACB_NO_BN256=1: cap the N tile at 128 
 static bool g_epi_staged = false;
 // SACB_TAIL_SPLIT=1: half tiles in the last partial wave of the pair kernel (conv_gemm_pair_kernel<.., .., true>); also unverified
 static bool g_tail_split = false;
+// SACB_EPI2=0 switches the prefetch + TMA-store epilogue kernel (conv_gemm_pair2_kernel) off: the short-K pair layers then run
+// the default pair kernel again (A/B runs, bit-identity test)
+static bool g_epi2 = true;
 
 static void init_once() {
   cudaDriverEntryPointQueryResult q;
@@ -1257,6 +1597,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_PAIR")) g_pair = (e[0] != '0');
   if (const char* e = getenv("SACB_EPI_STAGED")) g_epi_staged = (e[0] == '1');
   if (const char* e = getenv("SACB_TAIL_SPLIT")) g_tail_split = (e[0] == '1');
+  if (const char* e = getenv("SACB_EPI2")) g_epi2 = (e[0] != '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1340,6 +1681,36 @@ static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const 
   SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<STAGED, FAST, TSPLIT>, ah, al, bh, bl, rh, rl, a));
   g_launches++;
   return 0;
+}
+
+template <bool RES, bool MASK, bool FAST>
+static int launch_gemm_pair2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                             const CUtensorMap& oh, const CUtensorMap& ol, const GemmArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair2_kernel<RES, MASK, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair2Cfg::SMEM));
+    attr_set = true;
+  }
+  const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
+  const int grid = units * 2 < g_num_sms ? units * 2 : (g_num_sms / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Pair2Cfg::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair2_kernel<RES, MASK, FAST>, ah, al, bh, bl, oh, ol, a));
+  g_launches++;
+  return 0;
+}
+
+template <bool FAST>
+static int dispatch_gemm_pair2(bool res, bool mask, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                               const CUtensorMap& bl, const CUtensorMap& oh, const CUtensorMap& ol, const GemmArgs& a, cudaStream_t st) {
+  if (res && mask) return launch_gemm_pair2<true, true, FAST>(ah, al, bh, bl, oh, ol, a, st);
+  if (res) return launch_gemm_pair2<true, false, FAST>(ah, al, bh, bl, oh, ol, a, st);
+  if (mask) return launch_gemm_pair2<false, true, FAST>(ah, al, bh, bl, oh, ol, a, st);
+  return launch_gemm_pair2<false, false, FAST>(ah, al, bh, bl, oh, ol, a, st);
 }
 
 template <bool FAST>
@@ -1432,6 +1803,20 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) {
+    // epilogue-bound layers (short K loop, split-plane outputs, channel vectors that fit the shared-memory staging): the
+    // prefetch + TMA-store epilogue kernel
+    const bool epi2 = g_epi2 && !g_epi_staged && a.taps * a.kc_blocks <= 8 && d->out_hi && !d->out_f32 && !d->out_nchw && !d->add_f32 &&
+                      (d->add_hi == nullptr) == (d->add_lo == nullptr) && a.N_total <= MAX_AFFINE && a.n_valid == a.N_total;
+    if (epi2) {
+      CUtensorMap oh, ol;
+      cuuint64_t od[2] = {(cuuint64_t)d->K, (cuuint64_t)a.M_total};
+      cuuint64_t os[1] = {(cuuint64_t)d->K * 2};
+      cuuint32_t ob[2] = {64, 32};
+      if (int e = make_tiled_map(&oh, d->out_hi, 2, od, os, ob)) return e;
+      if (int e = make_tiled_map(&ol, d->out_lo, 2, od, os, ob)) return e;
+      return fast ? dispatch_gemm_pair2<true>(d->add_hi != nullptr, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, a, st)
+                  : dispatch_gemm_pair2<false>(d->add_hi != nullptr, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, a, st);
+    }
     // residual-staging variant: short K loops (<= 8 k-blocks: the 1x1 layers up to 512 input channels) whose epilogue adds
     // split-plane residuals; two operand stages are enough there because the layer is bound by the epilogue's HBM traffic
     const bool staged = g_epi_staged && d->add_hi && d->add_lo && a.taps * a.kc_blocks <= 8;

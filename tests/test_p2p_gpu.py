@@ -143,12 +143,10 @@ def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
         assert same and err < 1e-4, (rank, err, same)
 
 
-@pytest.mark.skipif(os.environ.get("SACB_RUN_UNVERIFIED") != "1",
-                    reason="NVLS (multimem) exchange not yet verified on a multi-GPU box (set SACB_RUN_UNVERIFIED=1 to run)")
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
 def test_allreduce_sgd_world2_nvls_matches_allreduce_then_sgd(monkeypatch):
     """SACB_NVLS=1: multimem.ld_reduce / multimem.st through the NVSwitch (buffers and multicast mapping from torch symmetric
     memory).  At world 2 the switch's sum a + b is order-independent, so the result must still equal NCCL all-reduce + sacb_sgd
-    bit for bit and all replicas must agree."""
+    bit for bit and all replicas must agree.  Green on a 2 x B200 box since round 2 (profiles/r2b_pytest_p2p.log)."""
     monkeypatch.setenv("SACB_NVLS", "1")
     test_allreduce_sgd_world2_matches_allreduce_then_sgd()

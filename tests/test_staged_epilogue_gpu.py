@@ -1,6 +1,11 @@
-"""Residual-staging variant of the CTA-pair GEMM kernel (SACB_EPI_STAGED=1; csrc/sacb_gemm.cu conv_gemm_pair_kernel<true>):
-fprop + BN affine + residual + ReLU of the 1x1 expand layers and the dgrad-with-skip-gradient form, against fp64, and
-bit-identical to the default kernel (same MMA order, same epilogue arithmetic -- only where the residual is read from differs).
+"""Epilogue variants of the CTA-pair GEMM kernel on the short-K (1x1 expand) layers (csrc/sacb_gemm.cu):
+  * ``conv_gemm_pair2_kernel`` -- the default there since round 2: residual / mask planes prefetched into registers one chunk
+    ahead, outputs through shared-memory slabs and TMA stores (SACB_EPI2=0 switches it off),
+  * ``conv_gemm_pair_kernel<false>`` -- the round-1 default (LDG residual, lane-transposed STG),
+  * ``conv_gemm_pair_kernel<true>`` -- the residual-staging variant (SACB_EPI_STAGED=1).
+fprop + BN affine + residual + ReLU, the dgrad-with-skip-gradient form (mask + column sums), mask only and the plain form,
+including ragged last tiles: each against fp64, and all three BIT-IDENTICAL to each other (same MMA order, same epilogue
+arithmetic -- only how the operands of the epilogue travel differs).
 
 The switch is read once per process, so the check runs in a subprocess.  Green on a B200 since round 2
 (profiles/r2a_test_staged_epilogue_gpu.log)."""
@@ -26,7 +31,7 @@ def split(x):
 
 def nhwc(x): return x.permute(0, 2, 3, 1).contiguous()
 
-def run(N, H, W, C, K, seed, with_mask):
+def run(N, H, W, C, K, seed, form):
     torch.manual_seed(seed)
     x = torch.randn(N, C, H, W, device="cuda"); w = torch.randn(K, C, 1, 1, device="cuda") / C ** 0.5
     scale = torch.rand(K, device="cuda") + 0.5; shift = torch.randn(K, device="cuda") * 0.1
@@ -36,41 +41,55 @@ def run(N, H, W, C, K, seed, with_mask):
     act = F.relu(torch.randn(N, H, W, K, device="cuda")); mh, _ = split(act)
     conv = F.conv2d(x.double(), w.double())
     resd = (rh.float() + rl.float()).double().permute(0, 3, 1, 2)
-    if with_mask:      # dgrad form: (acc + skip gradient) masked by the ReLU of the layer input, plus its column sums
-        ref = (conv + resd) * (act > 0).permute(0, 3, 1, 2)
+    maskd = (act > 0).permute(0, 3, 1, 2)
+    aff = conv * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    if form == "dgrad_res":      # (acc + skip gradient) masked by the ReLU of the layer input, plus its column sums
+        ref = (conv + resd) * maskd
         kw = dict(add_hi=rh, add_lo=rl, mask_hi=mh)
-    else:              # fprop form: relu(acc * scale + shift + residual)
-        ref = F.relu(conv * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1) + resd)
+    elif form == "dgrad_mask":   # acc masked, plus column sums
+        ref = conv * maskd
+        kw = dict(mask_hi=mh)
+    elif form == "fprop_res":    # relu(acc * scale + shift + residual)
+        ref = F.relu(aff + resd)
         kw = dict(scale=scale, shift=shift, add_hi=rh, add_lo=rl, relu=True)
-    oh = torch.empty(N, H, W, K, device="cuda", dtype=torch.bfloat16); ol = torch.empty_like(oh)
+    elif form == "fprop":        # relu(acc * scale + shift)
+        ref = F.relu(aff)
+        kw = dict(scale=scale, shift=shift, relu=True)
+    else:                        # affine only (downsample branch)
+        ref = aff
+        kw = dict(scale=scale, shift=shift)
+    oh = torch.full((N, H, W, K), float("nan"), device="cuda", dtype=torch.bfloat16); ol = torch.full_like(oh, float("nan"))
     cs = torch.zeros(K, device="cuda")
-    L.conv_gemm(xh, xl, wh, wl, (N, H, W, C, K, 1, 1, 1, 0), out_hi=oh, out_lo=ol, colsum=cs, **kw)
+    L.conv_gemm(xh, xl, wh, wl, (N, H, W, C, K, 1, 1, 1, 0), out_hi=oh, out_lo=ol, colsum=cs if form.startswith("dgrad") else None, **kw)
     torch.cuda.synchronize()
     got = (oh.float() + ol.float()).permute(0, 3, 1, 2).double()
+    assert not torch.isnan(got).any(), "output rows left unwritten"
     err = ((got - ref).abs().max() / ref.abs().max()).item()
-    cerr = ((cs.double() - ref.sum((0, 2, 3))).abs().max() / ref.sum((0, 2, 3)).abs().max()).item()
+    cerr = ((cs.double() - ref.sum((0, 2, 3))).abs().max() / ref.sum((0, 2, 3)).abs().max()).item() if form.startswith("dgrad") else 0.0
     return err, cerr, oh.clone(), ol.clone()
 
 out = []
-for (N, H, W, C, K, seed, m) in [(3, 33, 33, 256, 1024, 1, False), (2, 20, 31, 512, 256, 2, False), (3, 33, 33, 256, 1024, 3, True),
-                                 (1, 65, 65, 256, 512, 4, True)]:
-    err, cerr, oh, ol = run(N, H, W, C, K, seed, m)
-    print("staged=%%s N%%d %%dx%%d C%%d K%%d mask=%%s: err %%.2e colsum err %%.2e" %% (sys.argv[1], N, H, W, C, K, m, err, cerr))
+for (N, H, W, C, K, seed, form) in [(3, 33, 33, 256, 1024, 1, "fprop_res"), (2, 20, 31, 512, 256, 2, "fprop_res"), (3, 33, 33, 256, 1024, 3, "dgrad_res"),
+                                    (1, 65, 65, 256, 512, 4, "dgrad_res"), (1, 65, 65, 256, 512, 5, "dgrad_mask"), (2, 33, 33, 128, 512, 6, "fprop"),
+                                    (1, 9, 9, 256, 256, 7, "affine"), (5, 65, 65, 64, 256, 8, "fprop"), (24, 65, 65, 256, 1024, 9, "fprop_res")]:
+    err, cerr, oh, ol = run(N, H, W, C, K, seed, form)
+    print("variant=%%s N%%d %%dx%%d C%%d K%%d %%s: err %%.2e colsum err %%.2e" %% (sys.argv[1], N, H, W, C, K, form, err, cerr))
     assert err < 5e-5 and cerr < 1e-4, (err, cerr)
     out.append((oh.cpu(), ol.cpu()))
 torch.save(out, sys.argv[2])
 ''' % ROOT
 
 
-def test_staged_epilogue_matches_fp64_and_the_default_kernel(tmp_path):
+def test_epilogue_variants_match_fp64_and_each_other(tmp_path):
     import torch
     outs = {}
-    for flag in ("0", "1"):
-        path = str(tmp_path / ("planes%s.pt" % flag))
-        env = dict(os.environ, SACB_EPI_STAGED=flag)
-        r = subprocess.run([sys.executable, "-c", CHECK, flag, path], env=env, capture_output=True, text=True, timeout=600)
+    for name, env in (("epi2", {}), ("round1", {"SACB_EPI2": "0"}), ("staged", {"SACB_EPI2": "0", "SACB_EPI_STAGED": "1"})):
+        path = str(tmp_path / ("planes_%s.pt" % name))
+        r = subprocess.run([sys.executable, "-c", CHECK, name, path], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         print(r.stdout, r.stderr[-2000:])
         assert r.returncode == 0, r.stderr[-2000:]
-        outs[flag] = torch.load(path)
-    for (h0, l0), (h1, l1) in zip(outs["0"], outs["1"]):
-        assert torch.equal(h0, h1) and torch.equal(l0, l1), "staged and default epilogues must produce identical planes"
+        outs[name] = torch.load(path)
+    for other in ("round1", "staged"):
+        for i, ((h0, l0), (h1, l1)) in enumerate(zip(outs["epi2"], outs[other])):
+            assert torch.equal(h0.view(torch.int16), h1.view(torch.int16)) and torch.equal(l0.view(torch.int16), l1.view(torch.int16)), \
+                "case %d: the prefetch + TMA-store epilogue and the %s epilogue must produce identical planes" % (i, other)

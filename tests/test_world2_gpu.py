@@ -237,7 +237,8 @@ def test_fractional_group_on_two_ranks():
     for r, out in enumerate(res):
         l2, mx = rel(out["logits"], g["r%d_logits" % r])
         assert l2 < 1e-3 and mx < 1e-3, (r, l2, mx)
-        assert np.allclose(out["rc"], g["r%d_running_conf" % r], rtol=1e-4, atol=1e-7)
+        # running_conf is a mean of softmax outputs of logits that agree to ~1e-5: same bar as the single-GPU golden test
+        assert rel(out["rc"], g["r%d_running_conf" % r])[1] < 1e-4
         assert np.abs(out["conf"] - g["r%d_teacher_conf" % r]).max() < 1e-3
         agree = float((out["labels"] == g["r%d_teacher_labels" % r]).mean())
         amb = torch.from_numpy(g["r%d_ambiguous" % r])
