@@ -48,6 +48,8 @@ struct GemmArgs {
   uint16_t* out_hi; uint16_t* out_lo; float* out_f32; float* out_nchw;
   float* colsum;      // optional [N_total]: += column sums of the final values (BN d(beta) of the producer unit)
   int split_from;     // pair kernel, TSPLIT instantiation: tiles >= split_from are processed as two 256 x 128 halves
+  int debug;          // conv_gemm_pair2 only, profiling experiments (SACB_EPI2_DEBUG; results are then WRONG): bit 0 = do not load
+                      // the residual / mask planes, bit 1 = do not issue the TMA stores, bit 2 = no TMEM loads either
 };
 
 struct WgradArgs {
@@ -855,6 +857,9 @@ SACB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// (Tried on the B200 and rejected, profiles/r2d3_*: 16 epilogue warps with 32-channel SWIZZLE_64B slabs.  18 warps cap the
+// kernel at 96 registers -> spills in the chunk loop, and the half-line TMA stores were slower: 1x1 + residual 229 -> 252 us,
+// dgrad + skip gradient 328 -> 425 us.  Eight warps, 64-channel slabs it is.)
 constexpr uint32_t SLAB_PLANE_BYTES = 32 * 64 * 2;                 // [32 rows][64 channels] bf16 = one warp, one plane, one piece
 constexpr uint32_t SLAB_BYTES = 2 * SLAB_PLANE_BYTES;              // hi + lo
 struct Pair2Cfg {
@@ -874,7 +879,7 @@ struct ChunkPref {
 };
 template <bool RES, bool MASK>
 SACB_DEVINL void prefetch_chunk(const GemmArgs& a, int m, int c0, ChunkPref<RES, MASK>& p) {
-  if (m < a.M_total) {
+  if (m < a.M_total && !(a.debug & 1)) {
     const size_t row = (size_t)m * a.N_total + c0;
     if constexpr (RES) {
       uint32_t t[8];
@@ -912,21 +917,26 @@ SACB_DEVINL void prefetch_chunk(const GemmArgs& a, int m, int c0, ChunkPref<RES,
   }
 }
 
-// fused math of one chunk (same operations in the same order as epilogue_row) -> packed words into the warp's slab
+// fused math of one chunk in two halves (same operations as epilogue_row; ReLU and the mask commute, so the mask is applied at
+// consumption time): (1) affine + residual + mask -- CONSUMES the prefetched planes, after which the caller re-issues the
+// prefetch for the following chunk into the same registers; (2) ReLU, split, packed words into the warp's slab, column sums.
+// (One prefetch set, not two: a warp has six scoreboard slots, and with two sets in flight the first use of one set also
+// waited for the loads of the other that had only just been issued -- profiles/r2d_ncu_pair2_1x1res: 26 % of all samples.)
 template <bool RES, bool MASK>
-SACB_DEVINL void epilogue2_chunk(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
-                                 float* __restrict__ s_colsum, uint32_t (&r)[32], const ChunkPref<RES, MASK>& pf, int m, int c0,
-                                 int lane, uint8_t* slab_hi_row, uint8_t* slab_lo_row, int e) {
-  float v[32];
+SACB_DEVINL void epilogue2_consume(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
+                                   const uint32_t (&r)[32], const ChunkPref<RES, MASK>& pf, int c0, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
   if (a.scale) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 4 * i);
-      const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + 4 * i);
-      v[4 * i + 0] = fmaf(v[4 * i + 0], sc.x, sh.x); v[4 * i + 1] = fmaf(v[4 * i + 1], sc.y, sh.y);
-      v[4 * i + 2] = fmaf(v[4 * i + 2], sc.z, sh.z); v[4 * i + 3] = fmaf(v[4 * i + 3], sc.w, sh.w);
+      // explicit ld.shared (LDS, short scoreboard): as generic loads these sat on the long scoreboard behind the LDGs
+      const uint4 sc = lds128(reinterpret_cast<const uint8_t*>(s_scale + c0 + 4 * i));
+      const uint4 sh = lds128(reinterpret_cast<const uint8_t*>(s_shift + c0 + 4 * i));
+      v[4 * i + 0] = fmaf(v[4 * i + 0], __uint_as_float(sc.x), __uint_as_float(sh.x));
+      v[4 * i + 1] = fmaf(v[4 * i + 1], __uint_as_float(sc.y), __uint_as_float(sh.y));
+      v[4 * i + 2] = fmaf(v[4 * i + 2], __uint_as_float(sc.z), __uint_as_float(sh.z));
+      v[4 * i + 3] = fmaf(v[4 * i + 3], __uint_as_float(sc.w), __uint_as_float(sh.w));
     }
   }
   if constexpr (RES) {
@@ -937,10 +947,6 @@ SACB_DEVINL void epilogue2_chunk(const GemmArgs& a, const float* __restrict__ s_
       v[2 * j] += h0 + l0; v[2 * j + 1] += h1 + l1;
     }
   }
-  if (a.relu) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
   if constexpr (MASK) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -948,7 +954,15 @@ SACB_DEVINL void epilogue2_chunk(const GemmArgs& a, const float* __restrict__ s_
       v[2 * j] = m0 > 0.f ? v[2 * j] : 0.f; v[2 * j + 1] = m1 > 0.f ? v[2 * j + 1] : 0.f;
     }
   }
+}
+SACB_DEVINL void epilogue2_finish(const GemmArgs& a, float* __restrict__ s_colsum, float (&v)[32], int m, int c0, int lane,
+                                  uint8_t* slab_hi_row, uint8_t* slab_lo_row, int e) {
+  if (a.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
   // 32 channels = four 16-byte chunks of the row's 128-byte line, positions 4e .. 4e+3 XOR-swizzled by (row & 7)
+  // (SWIZZLE_128B; a quarter warp covers all 32 banks once: conflict-free STS.128)
   const int sw = lane & 7;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -1101,7 +1115,7 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
     uint8_t* slab_lo_row = slab_lo + lane * 128;
     int acc = 0; uint32_t acc_phase = 0;
     // this warp's part of a tile: rows m_tile0 + quad*32 .. +32, channels n_col0 + half*128 .. +128 = 2 pieces x 2 chunks
-    ChunkPref<RES, MASK> pfA, pfB;
+    ChunkPref<RES, MASK> pf;
     auto tile_rc = [&](int unit, int& m_warp0, int& c_warp0) {
       const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
       m_warp0 = m_idx * 2 * BM + crank * BM + quad * 32;
@@ -1110,7 +1124,7 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
     if (unit0 < total_units) {
       int mw, cw;
       tile_rc(unit0, mw, cw);
-      prefetch_chunk<RES, MASK>(a, mw + lane, cw, pfA);           // in flight while the first accumulator is produced
+      prefetch_chunk<RES, MASK>(a, mw + lane, cw, pf);            // in flight while the first accumulator is produced
     }
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       int m_warp0, c_warp0;
@@ -1126,22 +1140,25 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       for (int jp = 0; jp < 2; ++jp) {
         const int c_piece = c_warp0 + jp * 64;
         uint32_t r[32];
+        float v[32];
         tmem_ld32(tbase + jp * 64, r);
-        prefetch_chunk<RES, MASK>(a, m, c_piece + 32, pfB);       // second chunk of this piece
         tmem_ld_wait();
+        epilogue2_consume<RES, MASK>(a, s_scale, s_shift, r, pf, c_piece, v);
+        prefetch_chunk<RES, MASK>(a, m, c_piece + 32, pf);        // second chunk of this piece, into the registers just consumed
         // the slab is free once the TMA store of the previous piece has read it (issued one piece of math ago)
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        epilogue2_chunk<RES, MASK>(a, s_scale, s_shift, s_colsum, r, pfA, m, c_piece, lane, slab_hi_row, slab_lo_row, 0);
+        epilogue2_finish(a, s_colsum, v, m, c_piece, lane, slab_hi_row, slab_lo_row, 0);
         tmem_ld32(tbase + jp * 64 + 32, r);
-        // first chunk of the next piece: same tile, or the next tile of this cluster
-        if (jp == 0) prefetch_chunk<RES, MASK>(a, m, c_piece + 64, pfA);
-        else if (has_next) prefetch_chunk<RES, MASK>(a, m_next + lane, c_next, pfA);
         tmem_ld_wait();
-        epilogue2_chunk<RES, MASK>(a, s_scale, s_shift, s_colsum, r, pfB, m, c_piece + 32, lane, slab_hi_row, slab_lo_row, 1);
+        epilogue2_consume<RES, MASK>(a, s_scale, s_shift, r, pf, c_piece + 32, v);
+        // first chunk of the next piece: same tile, or the next tile of this cluster
+        if (jp == 0) prefetch_chunk<RES, MASK>(a, m, c_piece + 64, pf);
+        else if (has_next) prefetch_chunk<RES, MASK>(a, m_next + lane, c_next, pf);
+        epilogue2_finish(a, s_colsum, v, m, c_piece + 32, lane, slab_hi_row, slab_lo_row, 1);
         fence_proxy_async();                                      // generic-proxy STS -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0 && m_warp0 < a.M_total) {
+        if (lane == 0 && m_warp0 < a.M_total && !(a.debug & 2)) {
           tma_store_2d(&tmOh, slab_hi, c_piece, m_warp0);
           tma_store_2d(&tmOl, slab_lo, c_piece, m_warp0);
           bulk_commit();
@@ -1630,10 +1647,10 @@ static int make_im2col_map(CUtensorMap* m, const void* base, int N, int H, int W
 
 // bf16 row-major [rows][cols] (cols contiguous) optionally with a third dim; box = 64 cols x box_rows rows
 static int make_tiled_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                          const cuuint32_t* box) {
+                          const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return -4; }
   return 0;
@@ -1799,6 +1816,9 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   a.out_hi = (uint16_t*)d->out_hi; a.out_lo = (uint16_t*)d->out_lo; a.out_f32 = d->out_f32; a.out_nchw = d->out_nchw;
   a.colsum = d->colsum;
   a.split_from = 0;
+  static int epi2_debug = -1;
+  if (epi2_debug < 0) { const char* e = getenv("SACB_EPI2_DEBUG"); epi2_debug = e ? atoi(e) : 0; }
+  a.debug = epi2_debug;
   SACB_REQUIRE((d->scale == nullptr) == (d->shift == nullptr), "sacb_conv_gemm: scale and shift go together");
   SACB_REQUIRE((d->out_hi == nullptr) == (d->out_lo == nullptr), "sacb_conv_gemm: out_hi and out_lo go together");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1811,7 +1831,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
       CUtensorMap oh, ol;
       cuuint64_t od[2] = {(cuuint64_t)d->K, (cuuint64_t)a.M_total};
       cuuint64_t os[1] = {(cuuint64_t)d->K * 2};
-      cuuint32_t ob[2] = {64, 32};
+      cuuint32_t ob[2] = {64, 32};                       // [32 rows][64 channels]: one warp's slab, SWIZZLE_128B
       if (int e = make_tiled_map(&oh, d->out_hi, 2, od, os, ob)) return e;
       if (int e = make_tiled_map(&ol, d->out_lo, 2, od, os, ob)) return e;
       return fast ? dispatch_gemm_pair2<true>(d->add_hi != nullptr, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, a, st)

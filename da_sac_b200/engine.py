@@ -13,10 +13,16 @@ re-expressed as a fixed schedule of C-ABI kernel calls:
 No PyTorch op touches the activations; torch provides memory and streams only.
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import lib as L
+
+# SACB_BWD_TWO_STREAM=1: the filter-gradient GEMMs of the backward pass run on a side stream.  They are off the critical path
+# (nothing but the final wgrad_finalize consumes them) while the data-gradient GEMMs form a dependent chain; every GEMM is a
+# persistent kernel whose last partial wave and prologue / drain leave SMs idle, which the other stream's kernel fills.
+BWD_TWO_STREAM = os.environ.get("SACB_BWD_TWO_STREAM", "0") == "1"
 
 BN_EPS = 1e-5
 NUM_CLASSES = 19
@@ -310,24 +316,30 @@ class WeightPlanes(object):
 
 
 class Planes(object):
-    """a bf16 hi/lo pair viewed as [M, C]"""
-    __slots__ = ("hi", "lo")
+    """a bf16 hi/lo pair viewed as [M, C]; ``slot`` = index of the scratch-pool buffers it lives in (None: persistent planes)"""
+    __slots__ = ("hi", "lo", "slot")
 
-    def __init__(self, hi, lo):
-        self.hi, self.lo = hi, lo
+    def __init__(self, hi, lo, slot=None):
+        self.hi, self.lo, self.slot = hi, lo, slot
 
 
 class BufferPool(object):
-    """fixed set of max-size scratch buffers handed out round-robin by name"""
+    """fixed set of max-size scratch buffers handed out by name.  ``fifo``: the buffer that has been free longest is handed out
+    next (two-stream backward: a freed buffer may still be read by a kernel on the side stream; ``readers[i]`` holds the events
+    the next user has to wait for)"""
 
-    def __init__(self, n_elems, count, dtype, device):
+    def __init__(self, n_elems, count, dtype, device, fifo=False):
         self.bufs = [torch.empty(n_elems, device=device, dtype=dtype) for _ in range(count)]
         self.free = list(range(count))
         self.used = {}
+        self.fifo = fifo
+        self.readers = {}
 
     def get(self, tag, n):
         assert tag not in self.used, tag
-        i = self.free.pop()
+        i = self.free.pop(0) if self.fifo else self.free.pop()
+        for ev in self.readers.pop(i, ()):
+            torch.cuda.current_stream().wait_event(ev)
         self.used[tag] = i
         return self.bufs[i][:n]
 
@@ -335,7 +347,7 @@ class BufferPool(object):
         self.free.append(self.used.pop(tag))
 
     def reset(self):
-        self.free = list(range(len(self.bufs))); self.used = {}
+        self.free = list(range(len(self.bufs))); self.used = {}; self.readers = {}
 
 
 class EngineBase(object):
@@ -360,11 +372,17 @@ class EngineBase(object):
     def _make_pools(self, max_elems, n_planes, n_f32):
         bf = torch.bfloat16
         self.max_elems = max_elems
-        self.tpool_hi = BufferPool(max_elems, n_planes, bf, self.device); self.tpool_lo = BufferPool(max_elems, n_planes, bf, self.device)
+        self._side = None
+        if BWD_TWO_STREAM and L.on_device(self.dwraw):
+            self._side = torch.cuda.Stream()
+            n_planes += 4              # distance between freeing a gradient buffer and overwriting it: the side stream's slack
+        fifo = self._side is not None
+        self.tpool_hi = BufferPool(max_elems, n_planes, bf, self.device, fifo); self.tpool_lo = BufferPool(max_elems, n_planes, bf, self.device, fifo)
         self.fpool = BufferPool(max_elems, n_f32, torch.float32, self.device)
 
     def _tplanes(self, tag, n):
-        return Planes(self.tpool_hi.get(tag, n), self.tpool_lo.get(tag, n))
+        hi = self.tpool_hi.get(tag, n)
+        return Planes(hi, self.tpool_lo.get(tag, n), slot=(self.tpool_hi.used[tag], self.tpool_lo.used[tag]))
 
     def _tput(self, tag):
         self.tpool_hi.put(tag); self.tpool_lo.put(tag)
@@ -511,8 +529,22 @@ class EngineBase(object):
         return t
 
     def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
-        dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, lambda n: self._dw_for(s.name, n),
-                                     (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad), k_valid=s.K)
+        geom = (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad)
+        side = getattr(self, "_side", None)
+        if side is None:
+            dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, lambda n: self._dw_for(s.name, n), geom, k_valid=s.K)
+        else:
+            # side stream: ordered after everything issued so far (g and xin are complete), its result is only read by the
+            # batched finalize after the join; whoever re-uses g's (or xin's) scratch buffers first waits for this kernel
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, lambda n: self._dw_for(s.name, n), geom, k_valid=s.K)
+                done = torch.cuda.Event()
+                done.record(side)
+            for pl in (g, xin):
+                if pl.slot is not None:
+                    self.tpool_hi.readers.setdefault(pl.slot[0], []).append(done)
+                    self.tpool_lo.readers.setdefault(pl.slot[1], []).append(done)
         self._finalize(flat, wp, s, dwraw, grad, dbeta, C_eff=s.C, RS=s.R * s.R, splits=splits)
 
     def _finalize(self, flat, wp, s, dwraw, grad, dbeta, C_eff, RS, splits=1):
@@ -521,6 +553,8 @@ class EngineBase(object):
         self._fin_pending.append((s, dwraw, dbeta, C_eff, RS, splits))
 
     def _finalize_all(self, flat, wp, grad):
+        if getattr(self, "_side", None) is not None:
+            torch.cuda.current_stream().wait_stream(self._side)      # join: every filter gradient has been written
         key = (flat.buf.data_ptr(), grad.buf.data_ptr(), wp.scale.data_ptr(), len(self._fin_pending))
         tab = getattr(self, "_fin_table", None)
         if tab is None or tab[0] != key:
