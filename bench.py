@@ -323,7 +323,9 @@ def main():
     L.lib()        # fail loudly if the CUDA extension is missing
 
     cfg = {"resnet101": synth.ModelCfg, "vgg16": synth.ModelCfgVGG16, "fcn": synth.ModelCfgFCN}[args.arch]()
-    net = get_model(cfg, rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the model constructors print what the reference's print; stdout carries the JSON line only
+        net = get_model(cfg, rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
     net.backbone.load_state_dict({"resnet101": lambda: synth.make_backbone_params(seed=123), "vgg16": lambda: synth.make_vgg16_params(seed=321),
                                   "fcn": lambda: synth.make_fcn_params(seed=213)}[args.arch]())
     net.to(dev).train()
@@ -398,9 +400,15 @@ def main():
         if opt._built is None: opt._build()
         b_ = opt._built
         p0, m0, g0, steps0 = bb._flat.buf.clone(), b_["mom"].clone(), bb._grad.buf.clone(), opt.steps
+        barrier()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
         opt.step()                                               # (a) fused
+        ev1.record()
         torch.cuda.synchronize()
         barrier()
+        ex_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        dist.all_reduce(ex_ms, op=dist.ReduceOp.MAX)
         p_fused, m_fused = bb._flat.buf.clone(), b_["mom"].clone()
         # (b) NCCL + sacb_sgd from the same state.  The fused kernel keeps the momentum SHARDED (ZeRO-1: a rank only ever touches
         # the slice it owns, the rest of its buffer stays zero), so the full momentum is the sum of the ranks' buffers.
@@ -425,8 +433,14 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         replicas_equal = bool((lo == hi).all())
         bit_exact = stats[0].item() == 0
+        n_opt = sum(r1 - r0 for r0, r1 in zip(b_["ranges_host"][0::2], b_["ranges_host"][1::2]))     # optimiser elements
+        link_bytes = (world - 1) / world * n_opt * 4 * (1.0 / world if opt.p2p.nvls else 1.0)
         exchange_check = {"vs_nccl_allreduce_plus_sgd": "bit-exact" if bit_exact else "rel-L2 of the update %.3e (%d elements differ)" % (stats[1].item(), int(stats[0].item())),
-                          "replicas_equal": replicas_equal, "update_rel_l2": stats[1].item(), "elements": int(bits.numel())}
+                          "replicas_equal": replicas_equal, "update_rel_l2": stats[1].item(), "elements": int(bits.numel()),
+                          # one launch of the fused kernel right after a barrier (ranks aligned): reduce-scatter + SGD + all-gather of
+                          # the whole flat buffer; bytes a rank pulls from / pushes to its peers over NVLink, each way
+                          "fused_kernel_ms": float(ex_ms), "nvlink_bytes_per_rank_each_way": link_bytes,
+                          "nvlink_gbs_each_way": link_bytes / (float(ex_ms) * 1e-3) / 1e9}
         note("exchange check: %s" % exchange_check)
         assert replicas_equal, "replicas diverged after the fused exchange"
         assert bit_exact or (world > 2 and stats[1].item() < 1e-6), "fused exchange differs from NCCL all-reduce + SGD: %s" % exchange_check

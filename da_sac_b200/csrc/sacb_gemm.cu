@@ -49,7 +49,7 @@ struct GemmArgs {
   float* colsum;      // optional [N_total]: += column sums of the final values (BN d(beta) of the producer unit)
   int split_from;     // pair kernel, TSPLIT instantiation: tiles >= split_from are processed as two 256 x 128 halves
   int debug;          // conv_gemm_pair2 only, profiling experiments (SACB_EPI2_DEBUG; results are then WRONG): bit 0 = do not load
-                      // the residual / mask planes, bit 1 = do not issue the TMA stores, bit 2 = no TMEM loads either
+                      // the residual / mask planes, bit 1 = do not issue the TMA stores, bit 2 = no L2 prefetch of the next tile
 };
 
 struct WgradArgs {
@@ -877,6 +877,22 @@ template <bool RES, bool MASK>
 struct ChunkPref {
   uint32_t h[RES ? 16 : 1], l[RES ? 16 : 1], m[MASK ? 16 : 1];
 };
+// L2 prefetch of the residual / mask lines one TILE ahead: 128 channels of one row = two 128-byte lines per plane.  The register
+// prefetch one chunk ahead then hits L2 (a few hundred cycles, inside its window) instead of waiting ~1500 cycles for HBM:
+// profiles/r2f_epilogues_dbg*.txt showed the epilogue's memory time ADDING to its compute time (118 us compute-only + 82 us
+// loads + 51 us stores = 229 us measured) -- every chunk stalled on its residual load.
+SACB_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <bool RES, bool MASK>
+SACB_DEVINL void prefetch_tile_l2(const GemmArgs& a, int m, int c_warp0) {
+  if (m >= a.M_total || (a.debug & 4)) return;
+  const size_t row = (size_t)m * a.N_total + c_warp0;
+  if constexpr (RES) {
+    prefetch_l2(a.add_hi + row); prefetch_l2(a.add_hi + row + 64);
+    prefetch_l2(a.add_lo + row); prefetch_l2(a.add_lo + row + 64);
+  }
+  if constexpr (MASK) { prefetch_l2(a.mask_hi + row); prefetch_l2(a.mask_hi + row + 64); }
+}
+
 template <bool RES, bool MASK>
 SACB_DEVINL void prefetch_chunk(const GemmArgs& a, int m, int c0, ChunkPref<RES, MASK>& p) {
   if (m < a.M_total && !(a.debug & 1)) {
@@ -1125,6 +1141,7 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       int mw, cw;
       tile_rc(unit0, mw, cw);
       prefetch_chunk<RES, MASK>(a, mw + lane, cw, pf);            // in flight while the first accumulator is produced
+      prefetch_tile_l2<RES, MASK>(a, mw + lane, cw);
     }
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       int m_warp0, c_warp0;
@@ -1132,7 +1149,10 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       const int m = m_warp0 + lane;
       int m_next = 0, c_next = 0;
       const bool has_next = unit + unit_step < total_units;
-      if (has_next) tile_rc(unit + unit_step, m_next, c_next);
+      if (has_next) {
+        tile_rc(unit + unit_step, m_next, c_next);
+        prefetch_tile_l2<RES, MASK>(a, m_next + lane, c_next);    // next tile's residual / mask lines -> L2, a whole tile ahead
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
