@@ -685,7 +685,10 @@ prepare_batched_kernel(const SacbPrepItem* __restrict__ items, const int32_t* __
       const int k = (int)(t % Kf);
       const int rs = (int)(t / Kf);
       float v = 0.f;
-      if (k < K) v = d.w[((size_t)k * C + c) * RS + rs];
+      if (k < K) {
+        v = d.w[((size_t)k * C + c) * RS + rs];
+        if (d.fold_wf && d.gamma) v *= d.gamma[k] * (1.0f / sqrtf(d.var[k] + eps));     // same expression as the scale vector
+      }
       st_split(wf_hi, wf_lo, i, v);
     } else {
       const size_t j = i - nf;

@@ -49,7 +49,7 @@ struct GemmArgs {
   float* colsum;      // optional [N_total]: += column sums of the final values (BN d(beta) of the producer unit)
   int split_from;     // pair kernel, TSPLIT instantiation: tiles >= split_from are processed as two 256 x 128 halves
   int debug;          // conv_gemm_pair2 only, profiling experiments (SACB_EPI2_DEBUG; results are then WRONG): bit 0 = do not load
-                      // the residual / mask planes, bit 1 = do not issue the TMA stores, bit 2 = no L2 prefetch of the next tile
+                      // the residual / mask planes, bit 1 = do not issue the TMA stores
 };
 
 struct WgradArgs {
@@ -568,6 +568,12 @@ SACB_DEVINL void tma2_load_3d(const CUtensorMap* m, uint32_t bar_addr, void* dst
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+SACB_DEVINL void tma2_load_2d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 SACB_DEVINL void tc2_commit_mc(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
@@ -869,7 +875,8 @@ struct Pair2Cfg {
   static constexpr int TMEM_COLS = 2 * PAIR_BN;
   static constexpr size_t OPER_BYTES = (size_t)STAGES * STAGE_BYTES;
   static constexpr size_t SLABS = (size_t)EPI_WARPS * SLAB_BYTES;
-  static constexpr size_t SMEM = OPER_BYTES + SLABS + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
+  static constexpr size_t IDENT_BYTES = 32 * 64 * 2;             // this CTA's 32 rows of the 64 x 64 identity (B operand of the residual MMAs)
+  static constexpr size_t SMEM = OPER_BYTES + SLABS + IDENT_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
 };
 
 // one 32-channel chunk of residual / mask planes of one row, as loaded (bf16 pairs)
@@ -877,22 +884,6 @@ template <bool RES, bool MASK>
 struct ChunkPref {
   uint32_t h[RES ? 16 : 1], l[RES ? 16 : 1], m[MASK ? 16 : 1];
 };
-// L2 prefetch of the residual / mask lines one TILE ahead: 128 channels of one row = two 128-byte lines per plane.  The register
-// prefetch one chunk ahead then hits L2 (a few hundred cycles, inside its window) instead of waiting ~1500 cycles for HBM:
-// profiles/r2f_epilogues_dbg*.txt showed the epilogue's memory time ADDING to its compute time (118 us compute-only + 82 us
-// loads + 51 us stores = 229 us measured) -- every chunk stalled on its residual load.
-SACB_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <bool RES, bool MASK>
-SACB_DEVINL void prefetch_tile_l2(const GemmArgs& a, int m, int c_warp0) {
-  if (m >= a.M_total || (a.debug & 4)) return;
-  const size_t row = (size_t)m * a.N_total + c_warp0;
-  if constexpr (RES) {
-    prefetch_l2(a.add_hi + row); prefetch_l2(a.add_hi + row + 64);
-    prefetch_l2(a.add_lo + row); prefetch_l2(a.add_lo + row + 64);
-  }
-  if constexpr (MASK) { prefetch_l2(a.mask_hi + row); prefetch_l2(a.mask_hi + row + 64); }
-}
-
 template <bool RES, bool MASK>
 SACB_DEVINL void prefetch_chunk(const GemmArgs& a, int m, int c0, ChunkPref<RES, MASK>& p) {
   if (m < a.M_total && !(a.debug & 1)) {
@@ -999,19 +990,34 @@ SACB_DEVINL void epilogue2_finish(const GemmArgs& a, float* __restrict__ s_colsu
   }
 }
 
-template <bool RES, bool MASK, bool FAST = false>
+// RESM: how the residual planes (add_hi / add_lo) reach the output.
+//   RES_NONE    no residual
+//   RES_EPI     prefetched into registers by the epilogue warps (any scale)
+//   RES_TENSOR  through the tensor core: four extra k-blocks per tile whose A operand is the residual tile itself -- TMA brings
+//               [128 rows][64 channels] of both planes into an operand stage, exactly like a 1x1 conv's activation tile -- and
+//               whose B operand is a 64 x 64 identity held in shared memory: tcgen05.mma with N = 64 adds R_hi and R_lo into
+//               columns 64j .. 64j+63 of the SAME TMEM accumulator the conv accumulates into (exact: products with 1.0,
+//               fp32 accumulation).  The residual then rides the deep TMA / mbarrier pipeline of the main loop instead of
+//               the epilogue's register loads (profiles/r2f_*: those added 82 us to a 118 us launch because an SM whose L1 is
+//               all shared memory can only keep a few sectors in flight), at the price of 16 half-cost MMAs per tile on layers
+//               whose tensor pipe is two-thirds idle.  Needs acc + R before the affine: scale == 1 (SacbConvGemm.unit_scale).
+enum { RES_NONE = 0, RES_EPI = 1, RES_TENSOR = 2 };
+template <int RESM, bool MASK, bool FAST = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                        const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                        const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+                       const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,
                        const GemmArgs a) {
+  constexpr bool RES = RESM == RES_EPI;               // residual handled by the epilogue warps
   using Cfg = Pair2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = PAIR_BN;
-  constexpr size_t BAR_OFF = Cfg::OPER_BYTES + Cfg::SLABS;
+  constexpr size_t BAR_OFF = Cfg::OPER_BYTES + Cfg::SLABS + Cfg::IDENT_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* slabs = smem + Cfg::OPER_BYTES;                        // 1024-byte aligned
+  uint8_t* ident = slabs + Cfg::SLABS;                            // 1024-byte aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -1027,6 +1033,18 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
   const bool leader = crank == 0;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmAh); prefetch_tmap(&tmAl); prefetch_tmap(&tmBh); prefetch_tmap(&tmBl); prefetch_tmap(&tmOh); prefetch_tmap(&tmOl);
+    if constexpr (RESM == RES_TENSOR) { prefetch_tmap(&tmRh); prefetch_tmap(&tmRl); }
+  }
+  if constexpr (RESM == RES_TENSOR) {
+    // rows crank*32 .. +32 of the 64 x 64 bf16 identity as a K-major SWIZZLE_128B operand: row i = 128 bytes, its 16-byte chunk c
+    // (k = 8c .. 8c+7) sits at position c ^ (i & 7); the one of row i is at k = crank*32 + i
+    for (int i = threadIdx.x; i < (int)Cfg::IDENT_BYTES / 16; i += GEMM_THREADS) reinterpret_cast<uint4*>(ident)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int i = threadIdx.x, kk = crank * 32 + i;
+      *reinterpret_cast<uint16_t*>(ident + i * 128 + (((kk >> 3) ^ (i & 7)) << 4) + (kk & 7) * 2) = 0x3F80;     // bf16 1.0
+    }
+    fence_proxy_async();                               // generic-proxy writes -> visible to tcgen05.mma (async proxy)
   }
   if (a.scale) {
     for (int i = threadIdx.x; i < a.N_total; i += GEMM_THREADS) { s_scale[i] = a.scale[i]; s_shift[i] = a.shift[i]; }
@@ -1058,6 +1076,9 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
     if (lane == 0) {
       PipeState ps{0, 0};
       const int pq = a.P * a.Q;
+      // (Tried and rejected on the B200, profiles/r2j2_*: pulling the next tile's residual boxes into L2 with
+      // cp.async.bulk.prefetch.tensor -- 1x1 + residual 226 -> 245 us, dgrad + skip gradient 245 -> 269 us: the prefetches queue in
+      // the same TMA unit in front of the loads the MMA is waiting for.  Round 1 saw the same with the LDG epilogue.)
       for (int unit = unit0; unit < total_units; unit += unit_step) {
         const int m_idx = unit / n_tiles, n_idx = unit - m_idx * n_tiles;
         const int m0 = m_idx * 2 * BM + crank * BM;
@@ -1078,6 +1099,18 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
             if constexpr (!FAST) tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
             tma2_load_3d(&tmBh, lbar, st + 2 * A_BYTES, cb * BK, brow, tap);
             if constexpr (!FAST) tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
+            ps.advance<STAGES>();
+          }
+        }
+        if constexpr (RESM == RES_TENSOR) {
+          // residual tile as four more k-blocks: [128 rows][64 channels] of both planes, K-major SWIZZLE_128B (rows past M zero-filled)
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+            const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+            if (leader) mbar_expect_tx(&full_bar[ps.stage], 4 * A_BYTES);          // hi + lo planes of BOTH CTAs
+            tma2_load_2d(&tmRh, lbar, st, n_idx * BN + j * 64, m0);
+            tma2_load_2d(&tmRl, lbar, st + A_BYTES, n_idx * BN + j * 64, m0);
             ps.advance<STAGES>();
           }
         }
@@ -1118,6 +1151,26 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
           tc2_commit_mc(&empty_bar[ps.stage], 0x3);
           ps.advance<STAGES>();
         }
+        if constexpr (RESM == RES_TENSOR) {
+          constexpr uint32_t idesc_r = make_idesc_bf16(2 * BM, 64, 0, 0);          // M = 256 rows of the pair, N = 64 columns
+          const uint32_t sb_id = smem_u32(ident);
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&full_bar[ps.stage], ps.phase);
+            tc_fence_after();
+            const uint32_t sr_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+            const uint32_t sr_lo = sr_hi + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t drh = make_smem_desc_sw128(sr_hi + k * 32, 16, 1024);
+              const uint64_t drl = make_smem_desc_sw128(sr_lo + k * 32, 16, 1024);
+              const uint64_t did = make_smem_desc_sw128(sb_id + k * 32, 16, 1024);
+              tc2_mma_bf16(tmem_d + (uint32_t)(j * 64), drh, did, idesc_r, 1);
+              tc2_mma_bf16(tmem_d + (uint32_t)(j * 64), drl, did, idesc_r, 1);
+            }
+            tc2_commit_mc(&empty_bar[ps.stage], 0x3);
+            ps.advance<STAGES>();
+          }
+        }
         tc2_commit_mc(&tfull_bar[acc], 0x3);
         acc ^= 1; if (acc == 0) acc_phase ^= 1;
       }
@@ -1141,7 +1194,6 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       int mw, cw;
       tile_rc(unit0, mw, cw);
       prefetch_chunk<RES, MASK>(a, mw + lane, cw, pf);            // in flight while the first accumulator is produced
-      prefetch_tile_l2<RES, MASK>(a, mw + lane, cw);
     }
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       int m_warp0, c_warp0;
@@ -1149,10 +1201,7 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       const int m = m_warp0 + lane;
       int m_next = 0, c_next = 0;
       const bool has_next = unit + unit_step < total_units;
-      if (has_next) {
-        tile_rc(unit + unit_step, m_next, c_next);
-        prefetch_tile_l2<RES, MASK>(a, m_next + lane, c_next);    // next tile's residual / mask lines -> L2, a whole tile ahead
-      }
+      if (has_next) tile_rc(unit + unit_step, m_next, c_next);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
@@ -1416,12 +1465,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constan
 // Each CTA stages 128 G channels (2 boxes) and 128 X channels (2 boxes) per 64-pixel k-block; same barrier protocol as
 // conv_gemm_pair_kernel.
 // ------------------------------------------------------------------------------------------------
-SACB_DEVINL void tma2_load_2d(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
 
 template <bool FAST = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -1615,6 +1658,7 @@ static bool g_tail_split = false;
 // SACB_EPI2=0 switches the prefetch + TMA-store epilogue kernel (conv_gemm_pair2_kernel) off: the short-K pair layers then run
 // the default pair kernel again (A/B runs, bit-identity test)
 static bool g_epi2 = true;
+static bool g_res_mma = true;         // SACB_RES_MMA=0: residuals of the pair2 layers through the epilogue, never the tensor core
 
 static void init_once() {
   cudaDriverEntryPointQueryResult q;
@@ -1635,6 +1679,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_EPI_STAGED")) g_epi_staged = (e[0] == '1');
   if (const char* e = getenv("SACB_TAIL_SPLIT")) g_tail_split = (e[0] == '1');
   if (const char* e = getenv("SACB_EPI2")) g_epi2 = (e[0] != '0');
+  if (const char* e = getenv("SACB_RES_MMA")) g_res_mma = (e[0] != '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1720,12 +1765,13 @@ static int launch_gemm_pair(const CUtensorMap& ah, const CUtensorMap& al, const 
   return 0;
 }
 
-template <bool RES, bool MASK, bool FAST>
+template <int RESM, bool MASK, bool FAST>
 static int launch_gemm_pair2(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                             const CUtensorMap& oh, const CUtensorMap& ol, const GemmArgs& a, cudaStream_t st) {
+                             const CUtensorMap& oh, const CUtensorMap& ol, const CUtensorMap& rh, const CUtensorMap& rl,
+                             const GemmArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair2_kernel<RES, MASK, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair2Cfg::SMEM));
+    SACB_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair2_kernel<RESM, MASK, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair2Cfg::SMEM));
     attr_set = true;
   }
   const int units = ((a.M_total + 2 * BM - 1) / (2 * BM)) * (a.N_total / PAIR_BN);
@@ -1736,18 +1782,21 @@ static int launch_gemm_pair2(const CUtensorMap& ah, const CUtensorMap& al, const
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair2_kernel<RES, MASK, FAST>, ah, al, bh, bl, oh, ol, a));
+  SACB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair2_kernel<RESM, MASK, FAST>, ah, al, bh, bl, oh, ol, rh, rl, a));
   g_launches++;
   return 0;
 }
 
 template <bool FAST>
-static int dispatch_gemm_pair2(bool res, bool mask, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
-                               const CUtensorMap& bl, const CUtensorMap& oh, const CUtensorMap& ol, const GemmArgs& a, cudaStream_t st) {
-  if (res && mask) return launch_gemm_pair2<true, true, FAST>(ah, al, bh, bl, oh, ol, a, st);
-  if (res) return launch_gemm_pair2<true, false, FAST>(ah, al, bh, bl, oh, ol, a, st);
-  if (mask) return launch_gemm_pair2<false, true, FAST>(ah, al, bh, bl, oh, ol, a, st);
-  return launch_gemm_pair2<false, false, FAST>(ah, al, bh, bl, oh, ol, a, st);
+static int dispatch_gemm_pair2(int resm, bool mask, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                               const CUtensorMap& bl, const CUtensorMap& oh, const CUtensorMap& ol, const CUtensorMap& rh,
+                               const CUtensorMap& rl, const GemmArgs& a, cudaStream_t st) {
+  if (resm == RES_TENSOR) return mask ? launch_gemm_pair2<RES_TENSOR, true, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st)
+                                      : launch_gemm_pair2<RES_TENSOR, false, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st);
+  if (resm == RES_EPI) return mask ? launch_gemm_pair2<RES_EPI, true, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st)
+                                   : launch_gemm_pair2<RES_EPI, false, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st);
+  return mask ? launch_gemm_pair2<RES_NONE, true, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st)
+              : launch_gemm_pair2<RES_NONE, false, FAST>(ah, al, bh, bl, oh, ol, rh, rl, a, st);
 }
 
 template <bool FAST>
@@ -1854,8 +1903,20 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
       cuuint32_t ob[2] = {64, 32};                       // [32 rows][64 channels]: one warp's slab, SWIZZLE_128B
       if (int e = make_tiled_map(&oh, d->out_hi, 2, od, os, ob)) return e;
       if (int e = make_tiled_map(&ol, d->out_lo, 2, od, os, ob)) return e;
-      return fast ? dispatch_gemm_pair2<true>(d->add_hi != nullptr, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, a, st)
-                  : dispatch_gemm_pair2<false>(d->add_hi != nullptr, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, a, st);
+      // residual: through the tensor core when it may be added before the affine (no scale, or the caller's unit-scale promise),
+      // else prefetched by the epilogue warps.  SACB_RES_MMA=0 forces the epilogue route (A/B runs).
+      int resm = RES_NONE;
+      CUtensorMap rh = oh, rl = ol;                      // not referenced unless RES_TENSOR
+      if (d->add_hi) {
+        resm = (g_res_mma && (d->scale == nullptr || d->unit_scale)) ? RES_TENSOR : RES_EPI;
+        if (resm == RES_TENSOR) {
+          cuuint32_t rb[2] = {64, (cuuint32_t)BM};
+          if (int e = make_tiled_map(&rh, d->add_hi, 2, od, os, rb)) return e;
+          if (int e = make_tiled_map(&rl, d->add_lo, 2, od, os, rb)) return e;
+        }
+      }
+      return fast ? dispatch_gemm_pair2<true>(resm, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, rh, rl, a, st)
+                  : dispatch_gemm_pair2<false>(resm, d->mask_hi != nullptr, ah, al, bh, bl, oh, ol, rh, rl, a, st);
     }
     // residual-staging variant: short K loops (<= 8 k-blocks: the 1x1 layers up to 512 input channels) whose epilogue adds
     // split-plane residuals; two operand stages are enough there because the layer is bound by the epilogue's HBM traffic

@@ -19,10 +19,10 @@ import torch
 
 from . import lib as L
 
-# SACB_BWD_TWO_STREAM=1: the filter-gradient GEMMs of the backward pass run on a side stream.  They are off the critical path
+# SACB_BWD_TWO_STREAM (default on, 0 = off): the filter-gradient GEMMs of the backward pass run on a side stream.  They are off the critical path
 # (nothing but the final wgrad_finalize consumes them) while the data-gradient GEMMs form a dependent chain; every GEMM is a
 # persistent kernel whose last partial wave and prologue / drain leave SMs idle, which the other stream's kernel fills.
-BWD_TWO_STREAM = os.environ.get("SACB_BWD_TWO_STREAM", "0") == "1"
+BWD_TWO_STREAM = os.environ.get("SACB_BWD_TWO_STREAM", "1") != "0"
 
 BN_EPS = 1e-5
 NUM_CLASSES = 19
@@ -245,6 +245,11 @@ class WeightPlanes(object):
         if with_dgrad:
             self.wt_hi = torch.empty(nt, device=device, dtype=bf); self.wt_lo = torch.empty(nt, device=device, dtype=bf)
         self.scale = torch.ones(nsc, device=device); self.shift = torch.zeros(nsc, device=device)
+        # units whose fprop planes carry the folded BN scale (SacbPrepItem.fold_wf): their epilogue runs with a unit scale, which
+        # lets the pair kernel add a residual through the tensor core (SacbConvGemm.unit_scale); the true scale vector is still
+        # produced -- wgrad_finalize needs gamma / sigma
+        self.ones = torch.ones(max(s.Kf for s in net["specs"].values()), device=device)
+        self.folded = set()
 
     def wf(self, name):
         s = self.net["specs"][name]; o = self.off[name][0]; n = s.R * s.R * s.Kf * s.C
@@ -269,6 +274,13 @@ class WeightPlanes(object):
         s = self.net["specs"][name]; o = self.off[name][2]
         return self.scale[o:o + s.Kf], self.shift[o:o + s.Kf]
 
+    def epi_affine(self, name):
+        """(scale, shift, unit_scale) for the fprop epilogue of a conv unit"""
+        sc, sh = self.affine(name)
+        if name in self.folded:
+            return self.ones[:sc.numel()], sh, True
+        return sc, sh, False
+
     def _prep_table(self, flat):
         """device descriptor table for sacb_prepare_batched (rebuilt if the flat buffer moved, e.g. into peer memory)"""
         key = flat.buf.data_ptr()
@@ -283,6 +295,9 @@ class WeightPlanes(object):
             sc, sh = self.affine(name)
             bn = s.bn is not None and self.fold_bn
             planes = s.C != 3
+            fold_wf = 1 if (bn and planes) else 0
+            if fold_wf:
+                self.folded.add(name)
             fh, fl = self.wf(name) if planes else (None, None)
             th, tl = self.wt(name) if (planes and self.with_dgrad) else (None, None)
             items.append(L.PrepItem(L.dptr(flat.view(name + ".weight")),
@@ -292,7 +307,7 @@ class WeightPlanes(object):
                                     L.dptr(flat.view(s.bn + ".running_var")) if bn else None,
                                     L.dptr(flat.view(name + ".bias")) if s.bias else None,
                                     L.dptr(sc), L.dptr(sh), L.dptr(fh), L.dptr(fl), L.dptr(th), L.dptr(tl),
-                                    s.K, s.C, s.R, s.R, s.Kf, s.Kt))
+                                    s.K, s.C, s.R, s.R, s.Kf, s.Kt, fold_wf, 0))
             blocks.append(lib.sacb_prep_item_blocks(s.K, s.C, s.R, s.R, s.Kf, s.Kt, 1 if planes else 0,
                                                     1 if (planes and self.with_dgrad) else 0))
         self._ptab = (key, L.item_table(items, blocks, flat.buf.device))
@@ -402,10 +417,10 @@ class EngineBase(object):
                     scale=sc, shift=sh, relu=True, out_hi=out.hi, out_lo=out.lo)
 
     def _unit(self, wp, s, xin, out, relu, res=None):
-        fh, fl = wp.wf(s.name); sc, sh = wp.affine(s.name)
+        fh, fl = wp.wf(s.name); sc, sh, unit = wp.epi_affine(s.name)
         L.conv_gemm(xin.hi, xin.lo, fh, fl, s.geom(self.N), scale=sc, shift=sh,
                     add_hi=None if res is None else res.hi, add_lo=None if res is None else res.lo,
-                    relu=relu, out_hi=out.hi, out_lo=out.lo)
+                    relu=relu, out_hi=out.hi, out_lo=out.lo, unit_scale=unit)
 
     def _aspp_fwd(self, flat, wp, a, logits_out):
         """ASPP head (deeplabv2.py:112-116) as one tap-unrolled 1x1 GEMM + shift-and-add (csrc/sacb_aspp.cu)"""

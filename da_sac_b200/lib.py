@@ -17,7 +17,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SACB_LIB") or os.path.join(_HERE, "libsac_b200.so")      # SACB_LIB: A/B runs of two builds
-ABI_VERSION = 5          # SACB_ABI_VERSION in include/sacb.h
+ABI_VERSION = 6          # SACB_ABI_VERSION in include/sacb.h
 
 
 class SacbError(RuntimeError):
@@ -87,7 +87,7 @@ class ConvGemm(C.Structure):
                 ("scale", _vp), ("shift", _vp), ("add_f32", _vp), ("add_hi", _vp), ("add_lo", _vp), ("mask_hi", _vp),
                 ("relu", C.c_int32),
                 ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp), ("out_nchw", _vp), ("colsum", _vp),
-                ("precision", C.c_int32)]
+                ("precision", C.c_int32), ("unit_scale", C.c_int32)]
 
 
 class ConvWgrad(C.Structure):
@@ -124,7 +124,8 @@ class Loss(C.Structure):
 class PrepItem(C.Structure):
     _fields_ = [("w", _vp), ("gamma", _vp), ("beta", _vp), ("mean", _vp), ("var", _vp), ("conv_bias", _vp),
                 ("scale", _vp), ("shift", _vp), ("wf_hi", _vp), ("wf_lo", _vp), ("wt_hi", _vp), ("wt_lo", _vp),
-                ("K", C.c_int32), ("C", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kf", C.c_int32), ("Kt", C.c_int32)]
+                ("K", C.c_int32), ("C", C.c_int32), ("R", C.c_int32), ("S", C.c_int32), ("Kf", C.c_int32), ("Kt", C.c_int32),
+                ("fold_wf", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FinalizeItem(C.Structure):
@@ -201,14 +202,15 @@ def conv_out_hw(H, W, R, stride, dil, pad):
 
 
 def conv_gemm(x_hi, x_lo, wt_hi, wt_lo, geom, *, k_valid=None, scale=None, shift=None, add_f32=None, add_hi=None,
-              add_lo=None, mask_hi=None, relu=False, out_hi=None, out_lo=None, out_f32=None, out_nchw=None, colsum=None):
-    """geom = (N, H, W, C, K, R, stride, dil, pad)"""
+              add_lo=None, mask_hi=None, relu=False, out_hi=None, out_lo=None, out_f32=None, out_nchw=None, colsum=None,
+              unit_scale=False):
+    """geom = (N, H, W, C, K, R, stride, dil, pad).  ``unit_scale``: the caller promises scale == 1 (BN scale folded into the weights)"""
     N, H, W, Cc, K, R, s, d, p = geom
     P, Q = conv_out_hw(H, W, R, s, d, p)
     desc = ConvGemm(C.sizeof(ConvGemm), N, H, W, Cc, K, K if k_valid is None else k_valid, R, R, s, d, p, P, Q,
                     ptr(x_hi), ptr(x_lo), ptr(wt_hi), ptr(wt_lo), ptr(scale), ptr(shift), ptr(add_f32), ptr(add_hi),
                     ptr(add_lo), ptr(mask_hi), 1 if relu else 0, ptr(out_hi), ptr(out_lo), ptr(out_f32), ptr(out_nchw), ptr(colsum),
-                    _precision())
+                    _precision(), 1 if unit_scale else 0)
     # mirrors the dispatch in csrc/sacb_gemm.cu (sacb_conv_gemm)
     pair = os.environ.get("SACB_PAIR", "1") != "0" and K % 256 == 0
     kind = "conv_gemm_pair<256x256>" if pair else "conv_gemm<%d>" % (128 if K % 128 == 0 else (64 if K % 64 == 0 else 32))

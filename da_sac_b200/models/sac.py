@@ -18,7 +18,9 @@ from .. import engine as E
 from .. import lib as L
 
 
-_TWO_STREAM = os.environ.get("SACB_TWO_STREAM", "0") == "1"
+# teacher forward + tail on a side stream (own engine), student forward on the main stream: on since round 2 (measured with the
+# backward's wgrad side stream: 108.8 -> 107.5 ms per step at N=1, 110.3 -> 108.5 at N=2, profiles/r2e_*, r2g_*); SACB_TWO_STREAM=0 = off
+_TWO_STREAM = os.environ.get("SACB_TWO_STREAM", "1") != "0"
 
 
 class LazyOuts(dict):
@@ -317,7 +319,7 @@ class SAC(SAC_Baseline):
         if update_teacher:
             losses["teacher_diff"] = self._momentum_update(True)         # sac.py:342-344
         tail = None
-        # SACB_TWO_STREAM=1 (written in round 1, not yet run on a GPU -> off by default): the teacher forward + tail and the
+        # SACB_TWO_STREAM (default on): the teacher forward + tail and the
         # student forward are independent until the loss, so they are issued on two streams.  Every GEMM is a persistent
         # kernel that owns all SMs, but its last partial wave (5.36 waves on the 256-channel layers) and the launch gaps leave
         # SMs idle that the other stream's next kernel can take.  The teacher then needs its own engine (im2col matrix, ASPP

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SACB_ABI_VERSION 5
+#define SACB_ABI_VERSION 6
 
 const char* sacb_last_error(void);
 int sacb_abi_version(void);
@@ -71,6 +71,11 @@ typedef struct SacbConvGemm {
   float* colsum;                          /* [K] or NULL: BN d(beta) of the unit that consumes this gradient */
   int32_t precision;                      /* SACB_PRECISION_*: 0 = bf16x3 split (parity mode, fp32-equivalent), 1 = single-pass
                                              bf16 on the hi planes only (fast mode; the lo planes are still written) */
+  int32_t unit_scale;                     /* caller's promise: scale == NULL or scale[c] == 1 for every c (the BN scale lives in
+                                             the weights, SacbPrepItem.fold_wf).  The residual add_hi/add_lo may then be added
+                                             BEFORE the affine, which lets the CTA-pair kernel feed it to the tensor core through
+                                             TMA (residual x identity into the same TMEM accumulator) instead of loading it in
+                                             the epilogue.  0 = no promise (always correct). */
 } SacbConvGemm;
 int sacb_conv_gemm(const SacbConvGemm* d, void* stream);
 
@@ -161,6 +166,9 @@ typedef struct SacbPrepItem {
   float* scale; float* shift;                       /* [K] folded affine out */
   void* wf_hi; void* wf_lo; void* wt_hi; void* wt_lo;
   int32_t K, C, R, S, Kf, Kt;
+  int32_t fold_wf;                                  /* 1: the fprop planes carry the folded BN scale too (wf = w * gamma / sigma), the
+                                                       caller then runs the conv with a unit scale (SacbConvGemm.unit_scale) */
+  int32_t reserved;
 } SacbPrepItem;
 int sacb_prep_item_blocks(int K, int C, int R, int S, int Kf, int Kt, int with_wf, int with_wt);
 int sacb_prepare_batched(const SacbPrepItem* items_dev, const int32_t* block_begin_dev, int n_items, int total_blocks,

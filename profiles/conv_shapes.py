@@ -56,6 +56,13 @@ def run(d, mode):
             d["res"] = (rnd(d["M"] * s.Kf), rnd(d["M"] * s.Kf))
         L.conv_gemm(d["x"][0], d["x"][1], d["wf"][0], d["wf"][1], s.geom(N), scale=d["sc"], shift=d["sh"], relu=True,
                     add_hi=d["res"][0], add_lo=d["res"][1], out_hi=d["out"][0], out_lo=d["out"][1])
+    elif mode == "fprop_res_unit":  # the same with the BN scale folded into the weights (what the engine runs since round 2): residual via the tensor core
+        if "res" not in d:
+            d["res"] = (rnd(d["M"] * s.Kf), rnd(d["M"] * s.Kf))
+        if "ones" not in d:
+            d["ones"] = torch.ones_like(d["sc"])
+        L.conv_gemm(d["x"][0], d["x"][1], d["wf"][0], d["wf"][1], s.geom(N), scale=d["ones"], shift=d["sh"], relu=True,
+                    add_hi=d["res"][0], add_lo=d["res"][1], out_hi=d["out"][0], out_lo=d["out"][1], unit_scale=True)
     elif mode in ("dgrad_cs", "dgrad_res"):   # data gradient as it runs in the step: ReLU mask + d(beta) column sums (+ residual gradient)
         if "cs" not in d:
             d["cs"] = torch.zeros(s.C, device=dev)
@@ -83,7 +90,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "epilogues":
         # the epilogue variants the real step uses, on the shapes that carry them
         print("%-28s %-10s %9s %8s" % ("shape", "mode", "us", "TF/s"))
-        for nm, modes in (("model.layer3.1.conv3", ("fprop", "fprop_res", "dgrad", "dgrad_cs")),
+        for nm, modes in (("model.layer3.1.conv3", ("fprop", "fprop_res", "fprop_res_unit", "dgrad", "dgrad_cs")),
                           ("model.layer3.1.conv1", ("fprop", "dgrad", "dgrad_cs", "dgrad_res")),
                           ("model.layer3.1.conv2", ("fprop", "dgrad", "dgrad_cs"))):
             s = net["specs"][nm]

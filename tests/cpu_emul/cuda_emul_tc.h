@@ -439,6 +439,31 @@ inline bool elect_one() { return (cuda_emul::t_bs->cur & 31) == 0; }
 inline void stg256(void* p, const uint32_t (&v)[8]) { if ((uintptr_t)p & 31) cuda_emul::die("st.global.v8: 32-byte alignment"); memcpy(p, v, 32); }
 inline void ldg256(const void* p, uint32_t (&v)[8]) { if ((uintptr_t)p & 31) cuda_emul::die("ld.global.v8: 32-byte alignment"); memcpy(v, p, 32); }
 inline uint4 lds128(const uint8_t* p) { cuda_emul::shared_addr(p); uint4 v; memcpy(&v, p, 16); return v; }
+// --- conv_gemm_pair2_kernel (round 2): shared-memory slabs + TMA stores.  Stores complete at issue, so the bulk-group waits are no-ops.
+inline void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  cuda_emul::shared_addr(p); const uint32_t v[4] = {a, b, c, d}; memcpy(p, v, 16);
+}
+inline void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  const cuda_emul::EmulMap& e = cuda_emul::map_of(m);
+  if (e.im2col || e.rank != 2) cuda_emul::die("TMA store: 2-D tiled tensor map expected");
+  const uint32_t s0 = smem_u32(src);
+  if (s0 & 1023u) cuda_emul::die("TMA store source of a SWIZZLE_128B box must be 1024-byte aligned");
+  for (int r = 0; r < (int)e.box[1]; ++r) {
+    const long long y = (long long)c1 + r;
+    if (y < 0 || y >= (long long)e.dims[1]) continue;                       // rows outside the tensor are clipped
+    char* dst = const_cast<char*>(e.base) + (size_t)y * e.strides[0];
+    for (int chunk = 0; chunk < 8; ++chunk) {
+      const char* sp = cuda_emul::shared_ptr(cuda_emul::sw128(s0 + (uint32_t)r * 128u + (uint32_t)chunk * 16u));
+      for (int i = 0; i < 8; ++i) {
+        const long long x = (long long)c0 + chunk * 8 + i;
+        if (x >= 0 && x < (long long)e.dims[0]) memcpy(dst + 2 * x, sp + 2 * i, 2);
+      }
+    }
+  }
+}
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait0() {}
 inline void tma2_load_im2col(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c, int w, int h, int n, uint16_t ow, uint16_t oh) {
   cuda_emul::tma_im2col(m, smem_u32(dst), as_bar(cuda_emul::shared_ptr(bar_addr)), c, w, h, n, ow, oh);
 }
