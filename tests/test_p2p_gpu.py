@@ -127,26 +127,33 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
+def _world2(nvls):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 30500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs: p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
-    for p in procs: p.join(timeout=120)
-    print(res)
+    port = 30500 + (os.getpid() % 2000) + (7 if nvls else 0)
+    old = os.environ.get("SACB_NVLS")
+    os.environ["SACB_NVLS"] = "1" if nvls else "0"          # inherited by the spawned ranks
+    try:
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+        for p in procs: p.start()
+        res = sorted(q.get(timeout=600) for _ in procs)
+        for p in procs: p.join(timeout=120)
+    finally:
+        if old is None: os.environ.pop("SACB_NVLS", None)
+        else: os.environ["SACB_NVLS"] = old
+    print("NVLS" if nvls else "peer loads / stores", res)
     for rank, err, same, msg in res:
         assert msg == "", msg
         assert same and err < 1e-4, (rank, err, same)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-def test_allreduce_sgd_world2_nvls_matches_allreduce_then_sgd(monkeypatch):
-    """SACB_NVLS=1: multimem.ld_reduce / multimem.st through the NVSwitch (buffers and multicast mapping from torch symmetric
-    memory).  At world 2 the switch's sum a + b is order-independent, so the result must still equal NCCL all-reduce + sacb_sgd
-    bit for bit and all replicas must agree.  Green on a 2 x B200 box since round 2 (profiles/r2b_pytest_p2p.log)."""
-    monkeypatch.setenv("SACB_NVLS", "1")
-    test_allreduce_sgd_world2_matches_allreduce_then_sgd()
+def test_allreduce_sgd_world2_matches_allreduce_then_sgd():
+    """two ranks, both instantiations of the fused kernel, one after the other:
+    (1) plain peer loads / stores: every replica bit-identical, and equal bit for bit to NCCL all-reduce (mean) + sacb_sgd;
+    (2) SACB_NVLS=1: multimem.ld_reduce / multimem.st through the NVSwitch (buffers and multicast mapping from torch symmetric
+        memory).  At world 2 the switch's sum a + b is order-independent, so the same bit-exactness must hold.
+    Green on a 2 x B200 box since round 2 (profiles/r2b_pytest_p2p.log, r2g_pytest_world2.log)."""
+    _world2(nvls=False)
+    _world2(nvls=True)

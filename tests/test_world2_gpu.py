@@ -1,6 +1,6 @@
 """Two real GPUs, NCCL: the drop-in under the reference's own wrapper, and the fractional-group path on real ranks.
 
-(1) ``test_dropin_under_ddp_and_torch_sgd``: what /root/reference/train.py does with the model, line by line, with
+(1) ``check_dropin_under_ddp_and_torch_sgd``: what /root/reference/train.py does with the model, line by line, with
     ``da_sac_b200.models`` in place of the reference's ``models``: ``get_model`` -> ``base_trainer.get_optim``
     (torch.optim.SGD over ``net.parameter_groups``, base_trainer.py:61-66) -> ``net.cuda(gpu)`` ->
     ``DistributedDataParallel(net, device_ids=[gpu])`` (train.py:100-104) -> two ``_step_target`` iterations
@@ -8,7 +8,7 @@
     one view-group.  Expected values come from the CPU oracle run per rank: DDP averages the per-rank gradients, so the
     parameters after step 0 are SGD(mean of the two oracle gradients) and step 1 runs on them; DDP broadcasts rank 0's buffers
     before every forward, which makes rank 0's ``running_conf`` authoritative.
-(2) ``test_fractional_group_on_two_ranks``: the reference's default recipe gives a GPU only part of a view-group
+(2) ``check_fractional_group_on_two_ranks``: the reference's default recipe gives a GPU only part of a view-group
     (train.py:185-209, sac.py:198-216).  1 group x K=4 views on two ranks, two views each, the sub-group all-reduce of
     ``SAC._exchange_partial_sums`` on NCCL, against the golden vectors the REAL reference produced on two gloo ranks
     (tests/golden/make_golden_fractional.py).
@@ -177,7 +177,7 @@ def _oracle_expectation():
     return exp
 
 
-def test_dropin_under_ddp_and_torch_sgd():
+def check_dropin_under_ddp_and_torch_sgd():
     res = _spawn(_ddp_rank, "ddp")
     exp = _oracle_expectation()
     for r, out in enumerate(res):
@@ -231,7 +231,7 @@ def _frac_rank(rank, dev):
                 self_ce=float(losses["self_ce"]), refined_sub=refined[:, :, ::3, ::3].cpu())
 
 
-def test_fractional_group_on_two_ranks():
+def check_fractional_group_on_two_ranks():
     g = np.load(os.path.join(HERE, "golden", "sac_fractional_w2.npz"))
     res = _spawn(_frac_rank, "frac")
     for r, out in enumerate(res):
@@ -247,3 +247,9 @@ def test_fractional_group_on_two_ranks():
         assert np.abs(out["refined_sub"] - g["r%d_teacher_refined_sub" % r]).max() < 1e-3
         ce = float(g["r%d_self_ce" % r].reshape(-1)[0])
         assert abs(out["self_ce"] - ce) <= 5e-3 * max(abs(ce), 1e-3), (out["self_ce"], ce)
+
+
+def test_world2_dropin_under_ddp_and_fractional_groups():
+    """both checks of this file in one test (one skip on a single-GPU box instead of two); each prints its own numbers"""
+    check_dropin_under_ddp_and_torch_sgd()
+    check_fractional_group_on_two_ranks()
