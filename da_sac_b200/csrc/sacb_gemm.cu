@@ -868,12 +868,17 @@ SACB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t
 // dgrad + skip gradient 328 -> 425 us.  Eight warps, 64-channel slabs it is.)
 constexpr uint32_t SLAB_PLANE_BYTES = 32 * 64 * 2;                 // [32 rows][64 channels] bf16 = one warp, one plane, one piece
 constexpr uint32_t SLAB_BYTES = 2 * SLAB_PLANE_BYTES;              // hi + lo
+// Operand ring of FOUR 32 KB units instead of two 64 KB stages: a unit holds the hi and lo plane of ONE operand box -- the
+// activation tile of a k-block, its weight tile, or a residual tile -- on its own full / empty barrier pair.  Same bytes, but the
+// four residual tiles of a tile (the only operand that always comes from HBM) are all in flight together, and an activation
+// box no longer waits for the weight box of the previous k-block to be consumed.
 struct Pair2Cfg {
   static constexpr uint32_t B_BYTES = (PAIR_BN / 2) * BK * 2;
-  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = 2;
+  static_assert(B_BYTES == A_BYTES, "one unit size for all operand boxes");
+  static constexpr uint32_t UNIT_BYTES = 2 * A_BYTES;
+  static constexpr int STAGES = 4;                                // units
   static constexpr int TMEM_COLS = 2 * PAIR_BN;
-  static constexpr size_t OPER_BYTES = (size_t)STAGES * STAGE_BYTES;
+  static constexpr size_t OPER_BYTES = (size_t)STAGES * UNIT_BYTES;
   static constexpr size_t SLABS = (size_t)EPI_WARPS * SLAB_BYTES;
   static constexpr size_t IDENT_BYTES = 32 * 64 * 2;             // this CTA's 32 rows of the 64 x 64 identity (B operand of the residual MMAs)
   static constexpr size_t SMEM = OPER_BYTES + SLABS + IDENT_BYTES + 1024 + 256 + 3 * MAX_AFFINE * sizeof(float);
@@ -1091,22 +1096,31 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
           const int r = tap / a.S, s = tap - r * a.S;
           const uint16_t ow = (uint16_t)(s * a.dil), oh = (uint16_t)(r * a.dil);
           for (int cb = 0; cb < a.kc_blocks; ++cb) {
-            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
-            const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
-            if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? Cfg::STAGE_BYTES : 2 * Cfg::STAGE_BYTES);
-            tma2_load_im2col(&tmAh, lbar, st, cb * BK, w0, h0, n_img, ow, oh);
-            if constexpr (!FAST) tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
-            tma2_load_3d(&tmBh, lbar, st + 2 * A_BYTES, cb * BK, brow, tap);
-            if constexpr (!FAST) tma2_load_3d(&tmBl, lbar, st + 2 * A_BYTES + Cfg::B_BYTES, cb * BK, brow, tap);
-            ps.advance<STAGES>();
+            {                                                      // activation unit
+              mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+              uint8_t* st = smem + (size_t)ps.stage * Cfg::UNIT_BYTES;
+              const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+              if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? 2 * A_BYTES : 4 * A_BYTES);     // bytes of BOTH CTAs
+              tma2_load_im2col(&tmAh, lbar, st, cb * BK, w0, h0, n_img, ow, oh);
+              if constexpr (!FAST) tma2_load_im2col(&tmAl, lbar, st + A_BYTES, cb * BK, w0, h0, n_img, ow, oh);
+              ps.advance<STAGES>();
+            }
+            {                                                      // weight unit
+              mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+              uint8_t* st = smem + (size_t)ps.stage * Cfg::UNIT_BYTES;
+              const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
+              if (leader) mbar_expect_tx(&full_bar[ps.stage], FAST ? 2 * A_BYTES : 4 * A_BYTES);
+              tma2_load_3d(&tmBh, lbar, st, cb * BK, brow, tap);
+              if constexpr (!FAST) tma2_load_3d(&tmBl, lbar, st + A_BYTES, cb * BK, brow, tap);
+              ps.advance<STAGES>();
+            }
           }
         }
         if constexpr (RESM == RES_TENSOR) {
           // residual tile as four more k-blocks: [128 rows][64 channels] of both planes, K-major SWIZZLE_128B (rows past M zero-filled)
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-            uint8_t* st = smem + (size_t)ps.stage * Cfg::STAGE_BYTES;
+            uint8_t* st = smem + (size_t)ps.stage * Cfg::UNIT_BYTES;
             const uint32_t lbar = leader_bar_addr(&full_bar[ps.stage]);
             if (leader) mbar_expect_tx(&full_bar[ps.stage], 4 * A_BYTES);          // hi + lo planes of BOTH CTAs
             tma2_load_2d(&tmRh, lbar, st, n_idx * BN + j * 64, m0);
@@ -1127,12 +1141,17 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         uint32_t accumulate = 0;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[ps.stage], ps.phase);
+          const int ua = ps.stage;
+          mbar_wait(&full_bar[ua], ps.phase);
+          ps.advance<STAGES>();
+          const int ub = ps.stage;
+          mbar_wait(&full_bar[ub], ps.phase);
+          ps.advance<STAGES>();
           tc_fence_after();
-          const uint32_t sa_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+          const uint32_t sa_hi = smem_u32(smem + (size_t)ua * Cfg::UNIT_BYTES);
           const uint32_t sa_lo = sa_hi + A_BYTES;
-          const uint32_t sb_hi = sa_hi + 2 * A_BYTES;
-          const uint32_t sb_lo = sb_hi + Cfg::B_BYTES;
+          const uint32_t sb_hi = smem_u32(smem + (size_t)ub * Cfg::UNIT_BYTES);
+          const uint32_t sb_lo = sb_hi + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t dah = make_smem_desc_sw128(sa_hi + k * 32, 16, 1024);
@@ -1148,8 +1167,8 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
             }
             accumulate = 1;
           }
-          tc2_commit_mc(&empty_bar[ps.stage], 0x3);
-          ps.advance<STAGES>();
+          tc2_commit_mc(&empty_bar[ua], 0x3);                    // frees both units in both CTAs
+          tc2_commit_mc(&empty_bar[ub], 0x3);
         }
         if constexpr (RESM == RES_TENSOR) {
           constexpr uint32_t idesc_r = make_idesc_bf16(2 * BM, 64, 0, 0);          // M = 256 rows of the pair, N = 64 columns
@@ -1157,7 +1176,7 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
           for (int j = 0; j < 4; ++j) {
             mbar_wait(&full_bar[ps.stage], ps.phase);
             tc_fence_after();
-            const uint32_t sr_hi = smem_u32(smem + (size_t)ps.stage * Cfg::STAGE_BYTES);
+            const uint32_t sr_hi = smem_u32(smem + (size_t)ps.stage * Cfg::UNIT_BYTES);
             const uint32_t sr_lo = sr_hi + A_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {

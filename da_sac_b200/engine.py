@@ -545,7 +545,7 @@ class EngineBase(object):
 
     def _wgrad(self, flat, wp, s, xin, g, grad, dbeta):
         geom = (self.N, s.hin, s.win, s.C, s.Kt, s.R, s.stride, s.dil, s.pad)
-        side = getattr(self, "_side", None)
+        side = None if L.SERIALIZE else getattr(self, "_side", None)
         if side is None:
             dwraw, splits = L.conv_wgrad(xin.hi, xin.lo, g.hi, g.lo, lambda n: self._dw_for(s.name, n), geom, k_valid=s.K)
         else:

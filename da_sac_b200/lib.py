@@ -155,16 +155,22 @@ def item_table(items, blocks, device):
 
 # optional per-launch CUDA-event profiling of the GEMM kernels (used by bench.py's roofline leg only)
 _prof = None
+# True while that profiling step runs: the two-stream modes (teacher || student forward, wgrad || dgrad) are switched off so that
+# every kernel is timed alone on the launching stream -- events around a launch that overlaps another stream's kernel would
+# charge it with the other kernel's time
+SERIALIZE = False
 
 
 def profile_begin():
-    global _prof
+    global _prof, SERIALIZE
     _prof = []
+    SERIALIZE = True
 
 
 def profile_end():
-    global _prof
+    global _prof, SERIALIZE
     rec, _prof = _prof, None
+    SERIALIZE = False
     torch.cuda.synchronize()
     return [(kind, flops, e0.elapsed_time(e1)) for (kind, flops, e0, e1) in rec]
 

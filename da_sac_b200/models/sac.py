@@ -324,7 +324,7 @@ class SAC(SAC_Baseline):
         # kernel that owns all SMs, but its last partial wave (5.36 waves on the 256-channel layers) and the launch gaps leave
         # SMs idle that the other stream's next kernel can take.  The teacher then needs its own engine (im2col matrix, ASPP
         # scratch and plane pools are per engine).
-        two_stream = use_teacher and _TWO_STREAM and L.on_device(x)
+        two_stream = use_teacher and _TWO_STREAM and not L.SERIALIZE and L.on_device(x)
         side = None
         if use_teacher:
             self.slow_net.eval()

@@ -256,3 +256,44 @@ def test_target_stepper_with_the_fused_peer_memory_exchange(emul):
     assert epochs == 2, "the fused exchange kernel did not run once per step"
     # (bit-identical on the real kernel source; the formula model's column sums are added in a run-dependent order)
     assert ((res[0] - res[1]).abs().max() / res[0].abs().max()).item() < 1e-5
+
+
+def test_fused_sgd_set_lr_keeps_momentum_and_device_tensors(emul):
+    """``FusedSGD.set_lr`` (learning-rate schedule between steps): the momentum buffer must survive and the device tensors a
+    captured CUDA graph reads through raw pointers (lr, wd, segment table, momentum) must stay where they are -- only their
+    contents change.  Checked against torch.optim.SGD taking the same two steps with the same change of learning rate."""
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import FusedSGD
+    cfg = synth.ModelCfgVGG16()
+    net = get_model(cfg, 0, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    net.backbone.load_state_dict(synth.make_vgg16_params(seed=321))
+    bb = net.backbone
+    bb.ensure_flat(torch.device("cpu"))
+    opt = FusedSGD(bb, net.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY), cfg.MOMENTUM)
+    ref_params = [p.detach().clone().requires_grad_(True) for p in bb.parameters()]
+    groups = net.parameter_groups(cfg.LR, cfg.WEIGHT_DECAY)
+    index = {id(p): i for i, p in enumerate(bb.parameters())}
+    ref_groups = [dict(params=[ref_params[index[id(p)]] for p in g["params"]], lr=g["lr"], weight_decay=g["weight_decay"]) for g in groups]
+    ref = torch.optim.SGD(ref_groups, momentum=cfg.MOMENTUM)
+    gen = torch.Generator().manual_seed(3)
+    ptrs = None
+    for step in range(3):
+        g = torch.randn(bb._flat.total, generator=gen) * 1e-2
+        bb._grad.buf.copy_(g)
+        for k, p in zip(bb._param_keys, ref_params):
+            p.grad = bb._grad.view(k).detach().clone()
+        opt.step(); ref.step()
+        b = opt._built
+        now = (b["lr"].data_ptr(), b["wd"].data_ptr(), b["ranges"].data_ptr(), b["mom"].data_ptr())
+        if step == 0:
+            ptrs = now
+            assert float(b["mom"].abs().sum()) > 0
+            opt.set_lr(net.parameter_groups(0.5 * cfg.LR, cfg.WEIGHT_DECAY))        # schedule step
+            for gr in ref.param_groups:
+                gr["lr"] *= 0.5
+            assert opt._built is b and float(b["mom"].abs().sum()) > 0, "set_lr dropped the momentum buffer"
+        assert now == ptrs, "set_lr moved tensors a captured graph points at"
+    got = torch.cat([p.detach().reshape(-1) for p in bb.parameters()])
+    want = torch.cat([p.detach().reshape(-1) for p in ref_params])
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-6
