@@ -306,16 +306,20 @@ SACB_DEVINL void epilogue_row(const GemmArgs& a, const float* __restrict__ s_sca
 // STAGED (pair kernel, residual layers): per 64-channel piece the residual comes from the shared-memory staging buffer
 // `res_buf` ([plane][half][128 rows][64 ch], filled by the residual-producer warp, signalled on res_full); once a warp has
 // read its rows it arrives on res_empty so that the next piece can be fetched while this one is transposed and stored.
+// `narrow` (pair kernel, tail split): the tile is only BN/2 columns wide; every warp then owns half as many chunks.  A RUNTIME
+// bound on the same loop -- the first tail-split build instantiated epilogue_tile<BN/2> next to epilogue_tile<BN> and lost 5 % of
+// the step to instruction-cache misses in an epilogue that is ~25 KB of SASS per 64-channel piece.
 template <int BN, bool STAGED = false>
 SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_scale, const float* __restrict__ s_shift,
                                float* __restrict__ s_colsum, uint32_t tcol0, int m_row0, int n_col0, int quad, int half,
                                int lane, const uint8_t* res_buf = nullptr, uint64_t* res_full = nullptr,
-                               uint64_t* res_empty = nullptr, uint32_t* res_phase = nullptr) {
+                               uint64_t* res_empty = nullptr, uint32_t* res_phase = nullptr, bool narrow = false) {
   constexpr int CHUNKS = BN / 32;
   constexpr int MY_CHUNKS = (CHUNKS + 1) / 2;
   const int m = m_row0 + quad * 32 + lane;
   const uint32_t tbase = tcol0 + ((uint32_t)(quad * 32) << 16);
-  const int ch0 = half * MY_CHUNKS;          // adjacent chunks: one warp covers MY_CHUNKS*32 contiguous channels
+  const int my_chunks = narrow ? MY_CHUNKS / 2 : MY_CHUNKS;
+  const int ch0 = half * my_chunks;          // adjacent chunks: one warp covers my_chunks*32 contiguous channels
   if constexpr (MY_CHUNKS % 2 == 0) {
     // chunk pairs (64 channels = one 128-byte line per row and plane): math per chunk, stores transposed per pair
     const int m_warp0 = m_row0 + quad * 32;
@@ -323,7 +327,7 @@ SACB_DEVINL void epilogue_tile(const GemmArgs& a, const float* __restrict__ s_sc
     // on instruction fetch (ncu: no_instruction second only to long_scoreboard).  Rolled: 256->1024 fprop + residual
     // 281 -> 253 us, 1024->256 dgrad + residual gradient 364 -> 324 us, tensor-bound 3x3 layers unchanged.
 #pragma unroll 1
-    for (int jp = 0; jp < MY_CHUNKS / 2; ++jp) {
+    for (int jp = 0; jp < my_chunks / 2; ++jp) {
       uint32_t ph[4][8], pl[4][8];
       {
         const int ch = ch0 + 2 * jp;
@@ -792,8 +796,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_con
         epilogue_tile<BN, true>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
                                 n_idx * BN, quad, half, lane, res_buf, res_full, res_empty, &res_phase);
       else if (TSPLIT && is_half)
-        epilogue_tile<BN / 2>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
-                              n_idx * BN + hh * (BN / 2), quad, half, lane);
+        epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM,
+                          n_idx * BN + hh * (BN / 2), quad, half, lane, nullptr, nullptr, nullptr, nullptr, true);
       else
         epilogue_tile<BN>(a, s_scale, s_shift, s_colsum, tmem_base + (uint32_t)(acc * BN), m_idx * 2 * BM + crank * BM, n_idx * BN,
                           quad, half, lane);
