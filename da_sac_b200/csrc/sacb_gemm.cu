@@ -1681,6 +1681,7 @@ static bool g_tail_split = false;
 // SACB_EPI2=0 switches the prefetch + TMA-store epilogue kernel (conv_gemm_pair2_kernel) off: the short-K pair layers then run
 // the default pair kernel again (A/B runs, bit-identity test)
 static bool g_epi2 = true;
+static bool g_wgrad_one_wave = true;  // SACB_WGRAD_ONE_WAVE=0: two K ranges per CTA pair in the pair wgrad kernel (round-1 plan)
 static bool g_res_mma = true;         // SACB_RES_MMA=0: residuals of the pair2 layers through the epilogue, never the tensor core
 
 static void init_once() {
@@ -1703,6 +1704,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_TAIL_SPLIT")) g_tail_split = (e[0] == '1');
   if (const char* e = getenv("SACB_EPI2")) g_epi2 = (e[0] != '0');
   if (const char* e = getenv("SACB_RES_MMA")) g_res_mma = (e[0] != '0');
+  if (const char* e = getenv("SACB_WGRAD_ONE_WAVE")) g_wgrad_one_wave = (e[0] != '0');
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2007,6 +2009,13 @@ static int plan_wgrad(const SacbConvWgrad* d, WgradArgs& a, int& BN) {
     const int base = a.m_tiles * a.n_tiles * a.taps;
     // aim at ~2 work units per CTA (per CTA pair for the pair kernel), rounded down so the last wave stays full
     splits = pair ? (g_num_sms / base) : (2 * g_num_sms + base - 1) / base;
+    if (pair && g_wgrad_one_wave) {
+      // ONE unit per CTA pair when that fills the clusters as well as two do: the same MMA work in half as many, twice as long
+      // K ranges -- half the split-K partial planes to write here and to read back in wgrad_finalize (3.6 GB -> 1.8 GB per step)
+      const int clusters = g_num_sms / 2;
+      const int s1 = clusters / base, s2 = g_num_sms / base;
+      if (s1 >= 1 && (double)(base * s1) / clusters >= (double)(base * s2) / g_num_sms - 0.03) splits = s1;
+    }
     const int max_splits = a.num_pix_blocks / 8 > 0 ? a.num_pix_blocks / 8 : 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
