@@ -571,7 +571,8 @@ def main():
             "e2e": {"value": e2e, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps},
             "self_ce_last": {"device_resident": self_ce_dev, "e2e": self_ce_e2e},
-            "gpu_launches": launches, "clocks": dict(sampler.summary(), remeasured=remeasured), "roofline": roofline}
+            "gpu_launches": launches, "clocks": dict(sampler.summary(), remeasured=remeasured), "roofline": roofline,
+            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
     if exchange_check is not None:
         line["exchange_check"] = exchange_check
         line["replicas_equal_after_timed_steps"] = replicas_after

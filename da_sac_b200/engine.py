@@ -598,18 +598,30 @@ class ResNet101Engine(EngineBase):
         EngineBase.__init__(self, build_resnet101(H, W), N, H, W, device)
         net = self.net
         st = net["stem"]
-        self.act["stem"] = self._planes(N * st.hout * st.wout, 64)
         ph, pw = net["pool_hw"]
-        self.act["pool"] = self._planes(N * ph * pw, 64)
         self.pool_idx = torch.empty(N * ph * pw * 64, device=device, dtype=torch.uint8)
         max_elems = N * st.hout * st.wout * 64
         for (p, c1, c2, c3, ds) in net["blocks"]:
             for c in (c1, c2, c3):
-                self.act[c.name] = self._planes(N * c.hout * c.wout, c.K)
                 max_elems = max(max_elems, N * c.hout * c.wout * c.K)
+        self._make_pools(max_elems, 5, 2)
+
+    def _ensure_act(self):
+        """the persistent activation set of a forward pass that will be back-propagated (about 1 GB per 512^2 crop): allocated
+        on the first such pass, so that an engine that only ever runs the no-grad teacher / inference forward (scratch planes)
+        does not hold it"""
+        if self.act:
+            return
+        net, N = self.net, self.N
+        st = net["stem"]
+        ph, pw = net["pool_hw"]
+        self.act["stem"] = self._planes(N * st.hout * st.wout, 64)
+        self.act["pool"] = self._planes(N * ph * pw, 64)
+        for (p, c1, c2, c3, ds) in net["blocks"]:
+            for c in (c1, c2, c3):
+                self.act[c.name] = self._planes(N * c.hout * c.wout, c.K)
             if ds is not None:
                 self.act[ds.name] = self._planes(N * ds.hout * ds.wout, ds.K)
-        self._make_pools(max_elems, 5, 2)
 
     # ------------------------------------------------------------------ forward
     def forward(self, flat, wp, x, logits_out, keep):
@@ -618,6 +630,8 @@ class ResNet101Engine(EngineBase):
         stem = net["stem"]
         ph, pw = net["pool_hw"]
         self.tpool_hi.reset(); self.tpool_lo.reset()
+        if keep:
+            self._ensure_act()
         get = (lambda tag, n: self.act[tag]) if keep else self._tplanes
         put = (lambda tag: None) if keep else self._tput
         a_stem = get("stem", N * stem.hout * stem.wout * 64)

@@ -155,6 +155,8 @@ class ResNet101TrainBNEngine(TrainBNMixin, E.ResNet101Engine):
         stem = net["stem"]
         ph, pw = net["pool_hw"]
         self.tpool_hi.reset(); self.tpool_lo.reset()
+        if keep:
+            self._ensure_act()
         get = (lambda tag, n: self.act[tag]) if keep else self._tplanes
         put = (lambda tag: None) if keep else self._tput
         # stem: im2col GEMM (raw) -> BN(train) -> ReLU -> max-pool
