@@ -443,7 +443,8 @@ def main():
                           "nvlink_gbs_each_way": link_bytes / (float(ex_ms) * 1e-3) / 1e9}
         note("exchange check: %s" % exchange_check)
         assert replicas_equal, "replicas diverged after the fused exchange"
-        assert bit_exact or (world > 2 and stats[1].item() < 1e-6), "fused exchange differs from NCCL all-reduce + SGD: %s" % exchange_check
+        # W > 2: measured 4e-7 ... 6e-7 of the update (profiles/r2h_*, r2i_*: fp32 summation order of 4 / 8 addends); a wrong exchange is O(1)
+        assert bit_exact or (world > 2 and stats[1].item() < 1e-5), "fused exchange differs from NCCL all-reduce + SGD: %s" % exchange_check
         # continue from the fused result (identical on all ranks) with the fused kernel's own (sharded) momentum
         bb._flat.buf.copy_(p_fused); b_["mom"].copy_(m_fused); opt.steps = steps0 + 1
         bb.mark_dirty()
