@@ -557,6 +557,66 @@ upsample_adj_rows_kernel(const float* __restrict__ g, float* __restrict__ t, siz
     t[o] = acc;
   }
 }
+// Stages A + B(rows) fused, one block per (image, up-sampled row): the per-pixel gradients of the row stay in shared memory
+// and only their row adjoint t[b, c, i, 0..w) leaves the SM -- the full-resolution gradient (BT x C x H x W fp32 = 478 MB at
+// 24 x 19 x 512^2) is never written to or read back from HBM.  Per-pixel arithmetic is loss_grad_px_kernel's, the adjoint sums
+// the same terms in the same order as upsample_adj_rows_kernel: bit-identical results.  The block keeps classes
+// [c_begin, c_end) of its row (static shared memory, 48 640 bytes): all 19 for rows up to 640 pixels, two passes of 10 + 9
+// classes (softmax recomputed) up to 1216.
+constexpr int GRAD_ROW_FLOATS = 19 * 640;
+template <int C_>
+__global__ void __launch_bounds__(256)
+loss_grad_rows_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ labels, const int64_t* __restrict__ y,
+                      const float* __restrict__ conf_mean, const float* __restrict__ running_conf, float focal_p, float coef,
+                      float* __restrict__ t, int C, int h, int w, int H, int W, int c_begin, int c_end) {
+  __shared__ float s_g[GRAD_ROW_FLOATS];               // [c_end - c_begin][W]
+  const int b = blockIdx.y, i = blockIdx.x;
+  const int HW = H * W;
+  const UpCoef cy = up_coef(i, h, H);
+  for (int j = threadIdx.x; j < W; j += 256) {
+    const int pix = i * W + j;
+    int lab;
+    if (labels) lab = labels[(size_t)b * HW + pix];
+    else { const long long tt = y[(size_t)b * HW + pix]; lab = (tt >= 0 && tt < C) ? (int)tt : 255; }
+    if (lab >= C) {
+#pragma unroll
+      for (int c = 0; c < C_; ++c) if (c >= c_begin && c < c_end) s_g[(c - c_begin) * W + j] = 0.f;
+      continue;
+    }
+    float v[C_];
+    up_logits<C_>(logits + (size_t)b * C * h * w, C, h, w, cy, up_coef(j, w, W), v);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C_; ++c) if (c < C) mx = fmaxf(mx, v[c]);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C_; ++c) if (c < C) { v[c] = expf(v[c] - mx); sum += v[c]; }
+    float k = coef;
+    if (labels) {
+      const float base = 1.f - fmaxf(running_conf[lab], 0.f);
+      const float fw = (focal_p == 3.f) ? base * base * base : powf(base, focal_p);
+      k *= fw * conf_mean[pix];
+    }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int c = 0; c < C_; ++c) if (c >= c_begin && c < c_end) s_g[(c - c_begin) * W + j] = k * (v[c] * inv - (c == lab ? 1.f : 0.f));
+  }
+  __syncthreads();
+  const float sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  for (int o = threadIdx.x; o < (c_end - c_begin) * w; o += 256) {
+    const int cc = o / w, xx = o - cc * w;
+    const int j_lo = sx > 0.f ? max(0, (int)floorf((float)(xx - 1) / sx) - 1) : 0;
+    const int j_hi = sx > 0.f ? min(W - 1, (int)ceilf((float)(xx + 1) / sx) + 1) : W - 1;
+    const float* src = s_g + cc * W;
+    float acc = 0.f;
+    for (int j = j_lo; j <= j_hi; ++j) {
+      const UpCoef cx = up_coef(j, w, W);
+      const float wx = (cx.i0 == xx ? cx.l0 : 0.f) + (cx.i1 == xx ? cx.l1 : 0.f);
+      if (wx != 0.f) acc += wx * src[j];
+    }
+    t[(((size_t)b * C + c_begin + cc) * H + i) * w + xx] = acc;
+  }
+}
 // columns: out[bc, yy, xx] = sum_i wy(i, yy) t[bc, i, xx]
 __global__ void __launch_bounds__(256)
 upsample_adj_cols_kernel(const float* __restrict__ t, float* __restrict__ out, int BC, int h, int w, int H) {
@@ -842,6 +902,21 @@ extern "C" int sacb_student_loss_bwd(const SacbLoss* d, void* stream) {
   SACB_REQUIRE(d->C == 19 && d->dlogits, "sacb_student_loss_bwd: built for 19 classes, needs dlogits");
   const int HW = d->H * d->W;
   const float coef = d->grad_scale / (float)((double)d->BT * HW);
+  if (d->grad_rows && d->C == 19 && 10 * d->W <= GRAD_ROW_FLOATS) {
+    // fused form: per-pixel gradient + row adjoint in one pass over the row (no full-resolution gradient in HBM), then the
+    // column adjoint.  One pass with all classes when they fit the block's shared memory, else two passes of 10 + 9 classes.
+    const int split = d->C * d->W <= GRAD_ROW_FLOATS ? d->C : 10;
+    for (int c0 = 0; c0 < d->C; c0 += split) {
+      loss_grad_rows_kernel<19><<<dim3(d->H, d->BT), 256, 0, ST>>>(d->logits, d->labels, d->y, d->conf_mean, d->running_conf, d->focal_p,
+                                                                   coef, d->grad_rows, d->C, d->h, d->w, d->H, d->W, c0,
+                                                                   c0 + split < d->C ? c0 + split : d->C);
+      LAUNCHED();
+    }
+    upsample_adj_cols_kernel<<<grid1((size_t)d->BT * d->C * d->h * d->w, 256), 256, 0, ST>>>(d->grad_rows, d->dlogits, d->BT * d->C,
+                                                                                             d->h, d->w, d->H);
+    LAUNCHED();
+    return 0;
+  }
   if (d->grad_px && d->grad_rows) {                 // two-stage form (workspace provided)
     dim3 grid((HW + 255) / 256, d->BT);
     loss_grad_px_kernel<19><<<grid, 256, 0, ST>>>(d->logits, d->labels, d->y, d->conf_mean, d->running_conf, d->focal_p, coef,

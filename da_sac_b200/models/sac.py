@@ -101,10 +101,12 @@ class SAC_Baseline(BaseNet):
         d = L.Loss(C.sizeof(L.Loss), BT, Cn, h, w, H, W, L.ptr(logits.contiguous()), L.ptr(y), None, L.ptr(ws["conf_mean"]),
                    L.ptr(ws["running_conf"]), 3.0, L.ptr(ws["losses"]), L.ptr(ws["scratch"]), float(grad_scale), L.ptr(dlogits), None, None)
         if dlogits is not None:                         # backward: workspace of the two-stage form
-            if ws["grad_px"] is None:
-                ws["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device)
+            # row adjoint of the up-sampled gradient [BT, C, H, w]; the full-resolution gradient itself is never materialised
+            # (csrc/sacb_tail.cu loss_grad_rows_kernel)
+            if ws["grad_rows"] is None:
                 ws["grad_rows"] = torch.empty(BT * Cn * H * w, device=logits.device)
-            d.grad_px, d.grad_rows = L.ptr(ws["grad_px"]), L.ptr(ws["grad_rows"])
+                ws["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device) if W > 1216 else None    # very wide crops only
+            d.grad_rows, d.grad_px = L.ptr(ws["grad_rows"]), L.ptr(ws["grad_px"])
         return d
 
     def forward(self, x=None, y=None, x2=None, use_teacher=False, update_teacher=False):
@@ -287,10 +289,10 @@ class SAC(SAC_Baseline):
                    L.ptr(conf_mean), L.ptr(self.running_conf), float(self.cfg.FOCAL_P), L.ptr(tail["losses"]),
                    L.ptr(tail["scratch"]), float(grad_scale), L.ptr(dlogits), None, None)
         if dlogits is not None:                         # backward: workspace of the two-stage form
-            if "grad_px" not in tail:
-                tail["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device)
+            if "grad_rows" not in tail:
                 tail["grad_rows"] = torch.empty(BT * Cn * H * w, device=logits.device)
-            d.grad_px, d.grad_rows = L.ptr(tail["grad_px"]), L.ptr(tail["grad_rows"])
+                tail["grad_px"] = torch.empty(BT * Cn * H * W, device=logits.device) if W > 1216 else None  # very wide crops only
+            d.grad_rows, d.grad_px = L.ptr(tail["grad_rows"]), L.ptr(tail["grad_px"])
         return d, keep
 
     # ---------------------------------------------------------------- forward (sac.py:315-378)

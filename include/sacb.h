@@ -253,8 +253,9 @@ typedef struct SacbLoss {
   /* backward */
   float grad_scale;              /* d(total)/d(self_ce), e.g. LR_TARGET */
   float* dlogits;                /* [BT,C,h,w] or NULL */
-  /* optional backward workspace: both non-NULL selects the two-stage backward (per-pixel gradient once, then the
-   * separable adjoint of the upsample) instead of the gather kernel */
+  /* optional backward workspace.  grad_rows alone (W <= 1216): the per-pixel gradient of an up-sampled row stays in shared
+   * memory and only its row adjoint is written, then the column adjoint -- the full-resolution gradient is never
+   * materialised.  Both non-NULL (any W): two-stage form through grad_px.  Neither: the gather kernel. */
   float* grad_px;                /* [BT,C,H,W] */
   float* grad_rows;              /* [BT,C,H,w] */
 } SacbLoss;
