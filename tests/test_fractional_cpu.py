@@ -96,3 +96,42 @@ def test_fractional_subgroup_index_math():
     # 1 view per rank, groups of 4 on 8 ranks
     assert [fractional_subgroup(r, 1, 4)[0] for r in range(8)] == [0, 0, 0, 0, 4, 4, 4, 4]
     assert fractional_subgroup(3, 4, 4) == (3, 1)          # whole group on the rank: no exchange
+
+
+def _worker4(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from da_sac_b200 import synth
+    from da_sac_b200.models import get_model
+    from da_sac_b200.trainer import prep_batch
+    net = get_model(synth.ModelCfg(), rank, num_classes=19, criterion=torch.nn.CrossEntropyLoss(ignore_index=255, reduction="none"))
+    N, L = 2, 4                                            # the reference's default recipe: 2 groups x 4 views on 4 GPUs
+    # every rank's loader hands it ONE group ([1, T, ...], datasets/__init__.py:64); ranks 0,1 must end up with halves of
+    # rank 0's group, ranks 2,3 with halves of rank 1's (train.py:196-209)
+    mine = torch.arange(L, dtype=torch.float32).view(1, L, 1) + 100.0 * rank
+    out = prep_batch(mine, N, L, world, rank)
+    src, half = (rank * 2) // L, (rank * 2) % L
+    ok = torch.equal(out.flatten(), torch.tensor([100.0 * src + half, 100.0 * src + half + 1]))
+    # the product's exchange of the reference-frame partial sums: a sum over the ranks that share the group, nobody else
+    pooled = torch.full((7,), float(10 ** rank))
+    net._exchange_partial_sums(pooled, 2, L)
+    want = {0: 11.0, 1: 11.0, 2: 1100.0, 3: 1100.0}[rank]
+    ok = ok and torch.equal(pooled, torch.full((7,), want))
+    net._exchange_partial_sums(pooled, 2, L)               # second call re-uses the cached sub-groups
+    ok = ok and torch.equal(pooled, torch.full((7,), 2 * want))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_default_recipe_two_groups_of_four_views_on_four_ranks():
+    """configs/deeplabv2_resnet101_train.yaml:16-18 on 4 GPUs: `_prep_batch` slicing and `SAC._exchange_partial_sums` with two
+    sub-groups {0,1} and {2,3} (every rank creates every sub-group, in the same order: new_group is collective)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker4, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs: p.join(timeout=60)
+    assert res == [(0, True), (1, True), (2, True), (3, True)]
