@@ -184,7 +184,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": SCALING,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.arch, args.groups, GROUP_SIZE, CROP), "global_batch_crops": args.groups * GROUP_SIZE * world,
+            "config": {"workload": workload_name(args.arch, args.groups, GROUP_SIZE, CROP),
+                       "baseline_config": args.config if args.config is not None else 1,
+                       "global_batch_crops": args.groups * GROUP_SIZE * world, "parallelism": "dp%d" % world,
                        "reference_sample": "each step = %d of the %d view-groups per GPU (bounded CPU sample)" % (sample_groups, args.groups)},
             "self_ce_last": ce,
             "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": ref.kind, "sample": sample},
