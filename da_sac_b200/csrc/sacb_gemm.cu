@@ -871,7 +871,11 @@ SACB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t
 // kernel at 96 registers -> spills in the chunk loop, and the half-line TMA stores were slower: 1x1 + residual 229 -> 252 us,
 // dgrad + skip gradient 328 -> 425 us.  Eight warps, 64-channel slabs it is.)
 constexpr uint32_t SLAB_PLANE_BYTES = 32 * 64 * 2;                 // [32 rows][64 channels] bf16 = one warp, one plane, one piece
-constexpr uint32_t SLAB_BYTES = 2 * SLAB_PLANE_BYTES;              // hi + lo
+// ONE plane per warp: the hi plane of a piece is staged and stored first while the lo words wait in registers, then the lo plane
+// goes through the same 4 KB.  Halving the slabs (64 -> 32 KB) pays for a fifth operand unit: the MMA in flight always holds two
+// units, so the loads in flight grow from two units to three (profiles/ncu_gemm_pair2_r2u.txt: the MMA warp waited for operands
+// 57 % of the time, the epilogue warps for the accumulator 51 %).
+constexpr uint32_t SLAB_BYTES = SLAB_PLANE_BYTES;
 // Operand ring of FOUR 32 KB units instead of two 64 KB stages: a unit holds the hi and lo plane of ONE operand box -- the
 // activation tile of a k-block, its weight tile, or a residual tile -- on its own full / empty barrier pair.  Same bytes, but the
 // four residual tiles of a tile (the only operand that always comes from HBM) are all in flight together, and an activation
@@ -880,7 +884,7 @@ struct Pair2Cfg {
   static constexpr uint32_t B_BYTES = (PAIR_BN / 2) * BK * 2;
   static_assert(B_BYTES == A_BYTES, "one unit size for all operand boxes");
   static constexpr uint32_t UNIT_BYTES = 2 * A_BYTES;
-  static constexpr int STAGES = 4;                                // units
+  static constexpr int STAGES = 5;                                // units
   static constexpr int TMEM_COLS = 2 * PAIR_BN;
   static constexpr size_t OPER_BYTES = (size_t)STAGES * UNIT_BYTES;
   static constexpr size_t SLABS = (size_t)EPI_WARPS * SLAB_BYTES;
@@ -971,8 +975,10 @@ SACB_DEVINL void epilogue2_consume(const GemmArgs& a, const float* __restrict__ 
     }
   }
 }
+// ReLU, split, column sums of one chunk: the hi words go into the warp's slab (its 64-byte half `e` of every row), the lo words
+// come back in `pl` and are staged by the caller once the TMA store of the hi plane has read the slab.
 SACB_DEVINL void epilogue2_finish(const GemmArgs& a, float* __restrict__ s_colsum, float (&v)[32], int m, int c0, int lane,
-                                  uint8_t* slab_hi_row, uint8_t* slab_lo_row, int e) {
+                                  uint8_t* slab_row, int e, uint32_t (&pl)[16]) {
   if (a.relu) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -982,12 +988,10 @@ SACB_DEVINL void epilogue2_finish(const GemmArgs& a, float* __restrict__ s_colsu
   const int sw = lane & 7;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint32_t ph[4], pl[4];
+    uint32_t ph[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split_pack(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], ph[j], pl[j]);
-    const int pos = ((4 * e + i) ^ sw) << 4;
-    sts128(slab_hi_row + pos, ph[0], ph[1], ph[2], ph[3]);
-    sts128(slab_lo_row + pos, pl[0], pl[1], pl[2], pl[3]);
+    for (int j = 0; j < 4; ++j) split_pack(v[8 * i + 2 * j], v[8 * i + 2 * j + 1], ph[j], pl[4 * i + j]);
+    sts128(slab_row + (((4 * e + i) ^ sw) << 4), ph[0], ph[1], ph[2], ph[3]);
   }
   if (a.colsum) {                          // uniform across the warp
     if (m >= a.M_total) {
@@ -997,6 +1001,11 @@ SACB_DEVINL void epilogue2_finish(const GemmArgs& a, float* __restrict__ s_colsu
     const float cs = warp_colsum32(v, lane);
     atomicAdd(&s_colsum[c0 + lane], cs);
   }
+}
+SACB_DEVINL void stage_lo_words(uint8_t* slab_row, int e, int lane, const uint32_t (&pl)[16]) {
+  const int sw = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts128(slab_row + (((4 * e + i) ^ sw) << 4), pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
 }
 
 // RESM: how the residual planes (add_hi / add_lo) reach the output.
@@ -1201,10 +1210,8 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
   } else {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* slab_hi = slabs + (size_t)(warp - 2) * SLAB_BYTES;
-    uint8_t* slab_lo = slab_hi + SLAB_PLANE_BYTES;
-    uint8_t* slab_hi_row = slab_hi + lane * 128;
-    uint8_t* slab_lo_row = slab_lo + lane * 128;
+    uint8_t* slab = slabs + (size_t)(warp - 2) * SLAB_BYTES;
+    uint8_t* slab_row = slab + lane * 128;
     int acc = 0; uint32_t acc_phase = 0;
     // this warp's part of a tile: rows m_tile0 + quad*32 .. +32, channels n_col0 + half*128 .. +128 = 2 pieces x 2 chunks
     ChunkPref<RES, MASK> pf;
@@ -1231,30 +1238,34 @@ conv_gemm_pair2_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
 #pragma unroll 1
       for (int jp = 0; jp < 2; ++jp) {
         const int c_piece = c_warp0 + jp * 64;
-        uint32_t r[32];
+        uint32_t r[32], pl0[16], pl1[16];
         float v[32];
         tmem_ld32(tbase + jp * 64, r);
         tmem_ld_wait();
         epilogue2_consume<RES, MASK>(a, s_scale, s_shift, r, pf, c_piece, v);
         prefetch_chunk<RES, MASK>(a, m, c_piece + 32, pf);        // second chunk of this piece, into the registers just consumed
-        // the slab is free once the TMA store of the previous piece has read it (issued one piece of math ago)
+        // the slab is free once the TMA store of the previous piece's lo plane has read it (issued one piece of math ago)
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
-        epilogue2_finish(a, s_colsum, v, m, c_piece, lane, slab_hi_row, slab_lo_row, 0);
+        epilogue2_finish(a, s_colsum, v, m, c_piece, lane, slab_row, 0, pl0);
         tmem_ld32(tbase + jp * 64 + 32, r);
         tmem_ld_wait();
         epilogue2_consume<RES, MASK>(a, s_scale, s_shift, r, pf, c_piece + 32, v);
         // first chunk of the next piece: same tile, or the next tile of this cluster
         if (jp == 0) prefetch_chunk<RES, MASK>(a, m, c_piece + 64, pf);
         else if (has_next) prefetch_chunk<RES, MASK>(a, m_next + lane, c_next, pf);
-        epilogue2_finish(a, s_colsum, v, m, c_piece + 32, lane, slab_hi_row, slab_lo_row, 1);
+        epilogue2_finish(a, s_colsum, v, m, c_piece + 32, lane, slab_row, 1, pl1);
+        const bool store = lane == 0 && m_warp0 < a.M_total && !(a.debug & 2);
         fence_proxy_async();                                      // generic-proxy STS -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0 && m_warp0 < a.M_total && !(a.debug & 2)) {
-          tma_store_2d(&tmOh, slab_hi, c_piece, m_warp0);
-          tma_store_2d(&tmOl, slab_lo, c_piece, m_warp0);
-          bulk_commit();
-        }
+        if (store) { tma_store_2d(&tmOh, slab, c_piece, m_warp0); bulk_commit(); }
+        if (lane == 0) bulk_wait_read0();                         // the hi plane has left the slab (the one exposed wait per piece)
+        __syncwarp();
+        stage_lo_words(slab_row, 0, lane, pl0);
+        stage_lo_words(slab_row, 1, lane, pl1);
+        fence_proxy_async();
+        __syncwarp();
+        if (store) { tma_store_2d(&tmOl, slab, c_piece, m_warp0); bulk_commit(); }
       }
       tc_fence_before();
       __syncwarp();
