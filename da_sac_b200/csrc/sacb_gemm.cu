@@ -624,7 +624,7 @@ struct PairCfgT {
 };
 using PairCfg = PairCfgT<false>;
 
-// TSPLIT (SACB_TAIL_SPLIT=1, written in round 1, not yet run): the tiles of the last, partial wave are cut into two
+// TSPLIT (SACB_TAIL_SPLIT=1; GPU-verified in round 2, neutral inside the step, hence opt-in -- DESIGN 4.1): the tiles of the last, partial wave are cut into two
 // 256 x 128 halves (MMA N = 128; each CTA feeds 64 of the B rows it loads) so that twice as many clusters share that wave:
 // 397 tiles on 74 clusters = 5 full waves + 27 tiles -> 54 half tiles in one wave of about half the length.
 template <bool STAGED, bool FAST = false, bool TSPLIT = false>

@@ -108,7 +108,7 @@ class P2PContext(object):
         assert n % 4 == 0
         self.n = n
         if self.nvls:
-            # SACB_NVLS=1 (written in round 1, not yet run on a multi-GPU box): multimem.ld_reduce / multimem.st through the
+            # SACB_NVLS=1 (verified on 2 and 8 B200s in round 2, profiles/r2*_nvls*): multimem.ld_reduce / multimem.st through the
             # NVSwitch instead of W peer loads / W peer stores per element
             grp = dist.group.WORLD
             self._bufs = dict(params=TorchSymmBuffer(n, device, grp), grads=TorchSymmBuffer(n, device, grp),
