@@ -1692,6 +1692,7 @@ static bool g_tail_split = false;
 // SACB_EPI2=0 switches the prefetch + TMA-store epilogue kernel (conv_gemm_pair2_kernel) off: the short-K pair layers then run
 // the default pair kernel again (A/B runs, bit-identity test)
 static bool g_epi2 = true;
+static int g_epi2_max_kb = 8;       // SACB_EPI2_MAX_KB: longest K loop (in 64-wide k-blocks) routed to conv_gemm_pair2_kernel (A/B runs)
 static bool g_wgrad_one_wave = true;  // SACB_WGRAD_ONE_WAVE=0: two K ranges per CTA pair in the pair wgrad kernel (round-1 plan)
 static bool g_res_mma = true;         // SACB_RES_MMA=0: residuals of the pair2 layers through the epilogue, never the tensor core
 
@@ -1714,6 +1715,7 @@ static void init_once() {
   if (const char* e = getenv("SACB_EPI_STAGED")) g_epi_staged = (e[0] == '1');
   if (const char* e = getenv("SACB_TAIL_SPLIT")) g_tail_split = (e[0] == '1');
   if (const char* e = getenv("SACB_EPI2")) g_epi2 = (e[0] != '0');
+  if (const char* e = getenv("SACB_EPI2_MAX_KB")) g_epi2_max_kb = atoi(e);
   if (const char* e = getenv("SACB_RES_MMA")) g_res_mma = (e[0] != '0');
   if (const char* e = getenv("SACB_WGRAD_ONE_WAVE")) g_wgrad_one_wave = (e[0] != '0');
   int dev = 0;
@@ -1930,7 +1932,7 @@ extern "C" int sacb_conv_gemm(const SacbConvGemm* d, void* stream) {
   if (pair) {
     // epilogue-bound layers (short K loop, split-plane outputs, channel vectors that fit the shared-memory staging): the
     // prefetch + TMA-store epilogue kernel
-    const bool epi2 = g_epi2 && !g_epi_staged && a.taps * a.kc_blocks <= 8 && d->out_hi && !d->out_f32 && !d->out_nchw && !d->add_f32 &&
+    const bool epi2 = g_epi2 && !g_epi_staged && a.taps * a.kc_blocks <= g_epi2_max_kb && d->out_hi && !d->out_f32 && !d->out_nchw && !d->add_f32 &&
                       (d->add_hi == nullptr) == (d->add_lo == nullptr) && a.N_total <= MAX_AFFINE && a.n_valid == a.N_total;
     if (epi2) {
       CUtensorMap oh, ol;

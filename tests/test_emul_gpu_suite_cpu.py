@@ -41,6 +41,9 @@ SELECTION = [
     ("test_variants_gpu", "test_tail_variant_labels_and_losses", None),
     ("test_fractional_gpu", "test_whole_group_tail_unchanged_by_phase_split", None),
     ("test_augment_gpu", "test_augment_matches_oracle_and_reference_golden", None),
+    ("test_ragged_gpu", "test_ragged_crop_full_step_vs_cpu_oracle", (1,)),   # odd sides 97 x 131 by default; the other two under FULL
+    ("test_ragged_gpu", "test_single_view_group", ()),
+    ("test_ragged_gpu", "test_every_pixel_ignored", None),
     ("test_abn_gpu", "test_bn_moments_survive_large_mean", None),
     ("test_abn_gpu", "test_abn_iteration_matches_reference_golden", (0, 1)),  # never run on a B200: the reason this file exists
                                                                                # (0 resnet101, 1 vgg16 by default; 2 fcn under FULL)
@@ -118,6 +121,7 @@ FULL_SELECTION = [   # (module, function, parametrisation index or None, runs by
     ("test_step_gpu", "test_two_training_steps_match_reference_golden", None, False),      # 913 launches, 77 s on 8 cores
     ("test_step_gpu", "test_vgg16_config1_two_steps_match_reference_golden", None, False),
     ("test_abn_gpu", "test_abn_iteration_matches_reference_golden", 1, False),      # vgg16
+    ("test_ragged_gpu", "test_ragged_crop_full_step_vs_cpu_oracle", 1, False),      # 97 x 131: ragged M tiles, odd maps through im2col TMA
 ]
 
 
