@@ -44,6 +44,8 @@ SELECTION = [
     ("test_ragged_gpu", "test_ragged_crop_full_step_vs_cpu_oracle", (1,)),   # odd sides 97 x 131 by default; the other two under FULL
     ("test_ragged_gpu", "test_single_view_group", ()),
     ("test_ragged_gpu", "test_every_pixel_ignored", None),
+    ("test_prepare_finalize_gpu", "test_prepare_batched_planes_bit_exact", None),
+    ("test_prepare_finalize_gpu", "test_wgrad_finalize_batched_bit_exact_dw", None),
     ("test_abn_gpu", "test_bn_moments_survive_large_mean", None),
     ("test_abn_gpu", "test_abn_iteration_matches_reference_golden", (0, 1)),  # never run on a B200: the reason this file exists
                                                                                # (0 resnet101, 1 vgg16 by default; 2 fcn under FULL)
