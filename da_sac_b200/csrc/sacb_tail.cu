@@ -7,6 +7,7 @@
 // :151-187 (_pseudo_labels_probs), :238-269 (_avg_pool), :271-313 (_refine), :70-102 (_momentum_update)
 // and F.interpolate + CrossEntropyLoss in models/deeplabv2.py:217-224.
 #include <atomic>
+#include <cstdlib>
 #include "sacb_common.cuh"
 #include "../../include/sacb.h"
 
@@ -38,6 +39,50 @@ SACB_DEVINL void up_logits(const float* __restrict__ L, int C, int h, int w, con
       const float* p = L + c * hw;
       out[c] = cy.l0 * (cx.l0 * __ldg(p + o00) + cx.l1 * __ldg(p + o01)) +
                cy.l1 * (cx.l0 * __ldg(p + o10) + cx.l1 * __ldg(p + o11));
+    }
+  }
+}
+
+// The same, from low-resolution logits staged in shared memory.  The three kernels that up-sample the 19-class logits and take a
+// softmax per full-resolution pixel (tail_probs, loss_fwd, loss_grad_rows) spent most of their issue slots on 64-bit address
+// arithmetic for 76 scalar global loads per pixel (profiles/r2ab_*: LEA + IADD3 + IMAD + ISETP + SHF = 46 % of the instructions).
+// A block touches two to four low-resolution rows; staged pixel-major ([row][column][20]: 16-byte records) they are read with
+// 20 LDS.128 at immediate class offsets from four base addresses.  Same expression per class as up_logits: bit-identical.
+// Measured (profiles/r2ac_*): tail_probs 449 -> 389 us, loss_fwd 372 -> 309 us at 24 x 512^2.  The same idea for the loss backward
+// (256-pixel segments, staged logits, a table of the column coefficients) was bit-identical too but SLOWER than
+// loss_grad_rows_kernel in three builds (1.23 / 1.21 / 0.93 ms against 0.61 ms; profiles/r2ac..r2ae_*) and was removed.
+constexpr int UPS_FLOATS = 5200;            // 2 rows x 130 columns x 20 floats, or 4 rows x 65 columns
+template <int C_>
+SACB_DEVINL bool stage_up_rows(float* s_up, int cap_floats, const float* __restrict__ L, int C, int h, int w, int H,
+                               int i_first, int i_last, int& r_lo) {
+  constexpr int CS = (C_ + 3) / 4 * 4;
+  const UpCoef a = up_coef(i_first, h, H), z = up_coef(i_last, h, H);
+  r_lo = a.i0;
+  const int n = (z.i1 - a.i0 + 1) * w;       // staged low-resolution pixels: rows r_lo .. z.i1, contiguous in the source
+  if (C != C_ || n * CS > cap_floats) return false;             // block-uniform
+  for (int e = threadIdx.x; e < n * C_; e += blockDim.x) {
+    const int c = e / n, rx = e - c * n;
+    s_up[rx * CS + c] = __ldg(L + (size_t)c * h * w + (size_t)r_lo * w + rx);
+  }
+  __syncthreads();
+  return true;
+}
+template <int C_>
+SACB_DEVINL void up_logits_staged(const float* s_up, int w, int r_lo, const UpCoef& cy, const UpCoef& cx, float* out) {
+  constexpr int CS = (C_ + 3) / 4 * 4;
+  const int r0 = (cy.i0 - r_lo) * w, r1 = (cy.i1 - r_lo) * w;
+  const float4* p00 = reinterpret_cast<const float4*>(s_up + (r0 + cx.i0) * CS);
+  const float4* p01 = reinterpret_cast<const float4*>(s_up + (r0 + cx.i1) * CS);
+  const float4* p10 = reinterpret_cast<const float4*>(s_up + (r1 + cx.i0) * CS);
+  const float4* p11 = reinterpret_cast<const float4*>(s_up + (r1 + cx.i1) * CS);
+#pragma unroll
+  for (int q = 0; q < CS / 4; ++q) {
+    const float4 a = p00[q], b = p01[q], c = p10[q], d = p11[q];
+    const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {b.x, b.y, b.z, b.w}, vc[4] = {c.x, c.y, c.z, c.w}, vd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (4 * q + k < C_)
+        out[4 * q + k] = cy.l0 * (cx.l0 * va[k] + cx.l1 * vb[k]) + cy.l1 * (cx.l0 * vc[k] + cx.l1 * vd[k]);
     }
   }
 }
@@ -84,7 +129,7 @@ SACB_DEVINL float taps_of_ones(const Taps& t) {
 template <int C_>
 __global__ void __launch_bounds__(256)
 tail_probs_kernel(const float* __restrict__ logits, const int64_t* __restrict__ y, float* __restrict__ probs,
-                  float* __restrict__ part_sums, int C, int CP, int h, int w, int H, int W) {
+                  float* __restrict__ part_sums, int C, int CP, int h, int w, int H, int W, int stage) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int HW = H * W;
@@ -92,10 +137,16 @@ tail_probs_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
 #pragma unroll
   for (int c = 0; c < C_; ++c) p[c] = 0.f;
   const bool valid = pix < HW;
+  __shared__ float4 s_up4[UPS_FLOATS / 4];            // float4: 16-byte aligned records
+  float* s_up = reinterpret_cast<float*>(s_up4);
+  int r_lo;
+  const float* Lb = logits + (size_t)b * C * h * w;
+  const bool staged = stage_up_rows<C_>(s_up, stage ? UPS_FLOATS : 0, Lb, C, h, w, H, (blockIdx.x * 256) / W, (min(HW, blockIdx.x * 256 + 256) - 1) / W, r_lo);
   if (valid) {
     const int i = pix / W, j = pix - i * W;
     const UpCoef cy = up_coef(i, h, H), cx = up_coef(j, w, W);
-    up_logits<C_>(logits + (size_t)b * C * h * w, C, h, w, cy, cx, p);
+    if (staged) up_logits_staged<C_>(s_up, w, r_lo, cy, cx, p);
+    else up_logits<C_>(Lb, C, h, w, cy, cx, p);
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) mx = fmaxf(mx, p[c]);
@@ -382,15 +433,21 @@ template <int C_>
 __global__ void __launch_bounds__(256)
 loss_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ y, const uint8_t* __restrict__ labels,
                 const float* __restrict__ conf_mean, const float* __restrict__ running_conf, float focal_p,
-                double* __restrict__ scratch, int C, int h, int w, int H, int W) {
+                double* __restrict__ scratch, int C, int h, int w, int H, int W, int stage) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * 256 + threadIdx.x;
   const int HW = H * W;
   float l_ce = 0.f, l_self = 0.f;
+  __shared__ float4 s_up4[UPS_FLOATS / 4];            // float4: 16-byte aligned records
+  float* s_up = reinterpret_cast<float*>(s_up4);
+  int r_lo;
+  const float* Lb = logits + (size_t)b * C * h * w;
+  const bool staged = stage_up_rows<C_>(s_up, stage ? UPS_FLOATS : 0, Lb, C, h, w, H, (blockIdx.x * 256) / W, (min(HW, blockIdx.x * 256 + 256) - 1) / W, r_lo);
   if (pix < HW) {
     const int i = pix / W, j = pix - i * W;
     float v[C_];
-    up_logits<C_>(logits + (size_t)b * C * h * w, C, h, w, up_coef(i, h, H), up_coef(j, w, W), v);
+    if (staged) up_logits_staged<C_>(s_up, w, r_lo, up_coef(i, h, H), up_coef(j, w, W), v);
+    else up_logits<C_>(Lb, C, h, w, up_coef(i, h, H), up_coef(j, w, W), v);
     float mx = -INFINITY;
 #pragma unroll
     for (int c = 0; c < C_; ++c) if (c < C) mx = fmaxf(mx, v[c]);
@@ -819,6 +876,10 @@ static inline int grid1(size_t n, int block) {
 }  // namespace sacb
 
 using namespace sacb;
+// A/B switch (read once): SACB_UP_STAGED=0 -> tail_probs / loss_fwd read the low-resolution logits from global memory again.
+// Both forms are bit-identical (tests/test_tail_loss_variants_gpu.py); the switch exists for that test and for timing runs.
+static int up_staged() { static const int v = [] { const char* e = getenv("SACB_UP_STAGED"); return (e && e[0] == '0') ? 0 : 1; }(); return v; }
+
 #define ST ((cudaStream_t)stream)
 #define LAUNCHED() do { g_launches++; SACB_CHECK_CUDA(cudaGetLastError()); } while (0)
 
@@ -852,7 +913,7 @@ extern "C" int sacb_teacher_tail(const SacbTail* d, void* stream) {
   SACB_REQUIRE(d->pool_mode >= 0 && d->pool_mode <= 2, "sacb_teacher_tail: pool_mode must be 0 (avg), 1 (min-entropy) or 2 (off)");
   SACB_REQUIRE(d->pool_mode == 0 || d->phase == 0 || d->phase == 3, "sacb_teacher_tail: fractional groups need the average pool");
   if (d->phase != 2) {
-    tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W);
+    tail_probs_kernel<C_><<<gridB, 256, 0, ST>>>(d->teacher_logits, d->y, d->probs, d->part_sums, C, CP, d->h, d->w, d->H, d->W, up_staged());
     LAUNCHED();
     if (d->training) {
       tail_running_conf_kernel<<<1, dim3(32, 32), 0, ST>>>(d->part_sums, nb * d->BT, C, 1.0 / ((double)d->BT * HW), d->beta,
@@ -890,7 +951,7 @@ extern "C" int sacb_student_loss_fwd(const SacbLoss* d, void* stream) {
   SACB_CHECK_CUDA(cudaMemsetAsync(d->scratch, 0, 2 * sizeof(double), ST));
   dim3 grid((HW + 255) / 256, d->BT);
   loss_fwd_kernel<19><<<grid, 256, 0, ST>>>(d->logits, d->y, d->labels, d->conf_mean, d->running_conf, d->focal_p,
-                                           d->scratch, d->C, d->h, d->w, d->H, d->W);
+                                           d->scratch, d->C, d->h, d->w, d->H, d->W, up_staged());
   LAUNCHED();
   loss_finalize_kernel<<<1, 32, 0, ST>>>(d->scratch, d->losses, 1.0 / ((double)d->BT * HW));
   LAUNCHED();

@@ -303,3 +303,10 @@ def test_fused_sgd_set_lr_keeps_momentum_and_device_tensors(emul):
     got = torch.cat([p.detach().reshape(-1) for p in bb.parameters()])
     want = torch.cat([p.detach().reshape(-1) for p in ref_params])
     assert ((got - want).abs().max() / want.abs().max()).item() < 1e-6
+
+
+def test_tail_and_loss_kernel_forms_are_bit_identical_on_the_emulation():
+    """tests/test_tail_loss_variants_gpu.py on the host emulation (real kernel source, thin geometries): staged vs direct
+    up-sampling -- two subprocesses, digests of every output tensor must agree"""
+    m = importlib.import_module("test_tail_loss_variants_gpu")
+    m.check_variants({"SACB_PROBE_EMUL": "1"})
